@@ -1,0 +1,153 @@
+/* kwiiyatta_b200 -- C ABI of the B200-native alignment + spectral-mapping hot path.
+ *
+ * Drop-in boundary for Iselix/kwiiyatta (reference paths relative to /root/reference):
+ *   - kw_dtw_*        replaces the call  fastdtw.fastdtw(x_feature, y_feature, dist=2, radius=radius)
+ *                     at kwiiyatta/vocoder/align.py:71 (and fastdtw.dtw), batched over pairs;
+ *   - kw_gmm_*        replaces  GaussianMixture(...).fit(dataarray)  at kwiiyatta/converter/gmm.py:20-26;
+ *   - kw_convert_*    replaces  MLPG(self.gmm, windows, diff).transform(feature)  at
+ *                     kwiiyatta/converter/gmm.py:28-34;
+ *   - kw_delta_*      replaces  delta_features(feature, DELTA_WINDOWS)  at kwiiyatta/converter/delta.py:30,46.
+ *
+ * Conventions
+ *   - plain C types only; every "dev" pointer is a CUDA device pointer owned by the caller;
+ *   - "host" pointers are ordinary host memory, read before the call returns;
+ *   - every entry point is stream-ordered on `stream` (a cudaStream_t passed as void*), spawns no
+ *     threads, keeps no global state, and never frees or allocates caller-visible memory;
+ *   - return value: 0 = OK, negative = kw_status below; kw_last_error() gives a message for the
+ *     calling thread;
+ *   - all matrices are row-major float64 unless stated otherwise.
+ */
+#ifndef KWIIYATTA_B200_H_
+#define KWIIYATTA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum kw_status {
+    KW_OK = 0,
+    KW_ERR_INVALID = -1,      /* bad argument (maps to ValueError in the Python shim)          */
+    KW_ERR_WORKSPACE = -2,    /* workspace too small                                            */
+    KW_ERR_UNSUPPORTED = -3,  /* feature not built (maps to NotImplementedError)                */
+    KW_ERR_CUDA = -4,         /* a CUDA runtime call failed                                     */
+    KW_ERR_NO_DEVICE = -5     /* no usable sm_100 device                                        */
+};
+
+/* ABI version of this header; bumped on any signature change. */
+int kw_abi_version(void);
+/* Message describing the last failing call on this thread ("" if none). */
+const char* kw_last_error(void);
+/* Device properties the host-side roofline arithmetic needs. Any pointer may be NULL. */
+int kw_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* ------------------------------------------------------------------------------------------
+ * DTW / FastDTW  (kwiiyatta/vocoder/align.py:71; fastdtw==0.3.2 semantics)
+ *
+ * A batch holds n_pairs independent (x, y) problems.  x_dev is the row-major concatenation of
+ * all x sequences, shape (sum tx, feat_dim); y_dev likewise.  tx_host / ty_host are HOST arrays.
+ *   radius  >= 1 : FastDTW with that radius;  radius < 0 : exhaustive DTW (fastdtw.dtw).
+ *   p_norm  : 1 or 2 -- local distance (sum |d|) or sqrt(sum d^2)  (dist=1 / dist=2).
+ *   precision : 0 = fp64 exact (paths bit-exact to the oracle), 1 = fp32 accumulate.
+ * Outputs (device):
+ *   cost_dev[n_pairs]            accumulated distance D[tx][ty];
+ *   path_dev                     int32 (i, j) pairs; pair p owns the region of (tx[p]+ty[p]) points
+ *                                starting at point index  sum_{q<p} (tx[q]+ty[q]);  the path occupies
+ *                                the LAST path_len[p] points of its region, in forward order;
+ *   path_begin_dev[n_pairs]      index (within the region) of the first path point;
+ *   path_len_dev[n_pairs]        number of path points;
+ *   cells_dev[n_pairs]           window cells evaluated, summed over resolution levels (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+size_t kw_dtw_workspace_bytes(int n_pairs, const int32_t* tx_host, const int32_t* ty_host,
+                              int feat_dim, int radius);
+
+int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_dev,
+                 const int32_t* tx_host, const int32_t* ty_host, int feat_dim,
+                 int radius, int p_norm, int precision,
+                 double* cost_dev, int32_t* path_dev, int32_t* path_begin_dev,
+                 int32_t* path_len_dev, int64_t* cells_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Delta features  (nnmnkwii.preprocessing.delta_features with kwiiyatta's DELTA_WINDOWS,
+ * kwiiyatta/converter/delta.py:8-12,30,46).  n_utts utterances concatenated; off_dev[n_utts+1]
+ * are frame offsets (int64).  in (sum T, dim) -> out (sum T, 3*dim) = [static, delta, delta2],
+ * zero-padded at each utterance's edges.
+ * ------------------------------------------------------------------------------------------ */
+int kw_delta_features(int n_utts, const int64_t* off_dev, int64_t total_frames, int dim,
+                      const double* in_dev, double* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Joint full-covariance GMM EM  (sklearn GaussianMixture.fit as configured at
+ * kwiiyatta/converter/gmm.py:9-26).  One EM iteration = kw_gmm_estep + kw_gmm_mstep_accumulate
+ * (+ the caller's all-reduce of `stats` across ranks) + kw_gmm_mstep_finalize.
+ *
+ * Model buffers (device): weights (K), means (K, D), covariances (K, D, D),
+ *   prec_chol (K, D, D) upper-triangular L with Sigma^-1 = L L^T (sklearn precisions_cholesky_),
+ *   aux (K, D + 2): per component [ b = mu L (D values), log|L| (sum log diag), log w ].
+ * stats layout (device, float64): K blocks of (1 + D + D*D): [ n_k, sum r (x-c_k), sum r (x-c_k)(x-c_k)^T ]
+ *   followed by 2 scalars [ sum_n log p(x_n), n_frames ].  Length kw_gmm_stats_len(K, D).
+ *   c_k is the centre the statistics were accumulated around (centres_dev, (K, D)); the
+ *   finaliser undoes it, so any centre gives the same parameters up to rounding.
+ * precision: 0 = fp64 (CUDA-core DFMA), 1 = split-fp16 tcgen05 tensor-core contractions.
+ * ------------------------------------------------------------------------------------------ */
+size_t kw_gmm_stats_len(int n_components, int dim);
+size_t kw_gmm_workspace_bytes(int64_t n_frames, int n_components, int dim, int precision);
+
+/* E-step: resp_dev (n_frames, K) responsibilities, sum of log p(x) accumulated into
+ * stats[K*(1+D+D*D)] and n_frames into the next slot. */
+int kw_gmm_estep(int64_t n_frames, const double* x_dev, int n_components, int dim,
+                 const double* means_dev, const double* prec_chol_dev, const double* aux_dev,
+                 double* resp_dev, double* stats_dev, int precision,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* M-step sufficient statistics around centres_dev (K, D) from resp_dev. */
+int kw_gmm_mstep_accumulate(int64_t n_frames, const double* x_dev, int n_components, int dim,
+                            const double* resp_dev, const double* centres_dev,
+                            double* stats_dev, int precision,
+                            void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Parameters from (all-reduced) statistics.  weight_norm: 0 -> n_k / sum_k n_k (M-step),
+ * 1 -> n_k / n_frames (GaussianMixture._initialize).  info_dev[K] receives 0 or the 1-based
+ * index of the first non-positive Cholesky pivot. */
+int kw_gmm_mstep_finalize(int n_components, int dim, double reg_covar, int weight_norm,
+                          const double* stats_dev, const double* centres_dev,
+                          double* weights_dev, double* means_dev, double* covariances_dev,
+                          double* prec_chol_dev, double* aux_dev, int32_t* info_dev,
+                          void* stream);
+
+/* prec_chol / aux from given covariances (precisions_cholesky_ of an existing model). */
+int kw_gmm_precision_cholesky(int n_components, int dim, const double* weights_dev,
+                              const double* means_dev, const double* covariances_dev,
+                              double* prec_chol_dev, double* aux_dev, int32_t* info_dev,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Conversion: posterior + conditional Gaussian + MLPG  (nnmnkwii MLPG.transform,
+ * kwiiyatta/converter/gmm.py:28-34).  dim_half = D/2 (72), static_dim = dim_half/3 (24).
+ *
+ * kw_convert_prepare slices a joint model (optionally with the diff rewrite) into the
+ * `prepared` block (device, float64, length kw_convert_prepared_len):
+ *   [ px_prec_chol (K,Dh,Dh) | px_aux (K,Dh+2) | A^T (K,Dh,Dh) with A = Syx Sxx^-1 |
+ *     offset (K,Dh) = mu_y - A mu_x | var (K,Dh) diagonal conditional variance | scratch (K,Dh,Dh) ]
+ * kw_convert_batch converts n_utts utterances concatenated in src_dev (sum T, Dh) with int64
+ * frame offsets off_dev[n_utts+1]; out_dev is (sum T, static_dim); mix_dev (sum T) int32 receives
+ * the hard mixture sequence (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+size_t kw_convert_prepared_len(int n_components, int dim_half);
+int kw_convert_prepare(int n_components, int dim_half, int diff, const double* weights_dev,
+                       const double* means_dev, const double* covariances_dev,
+                       double* prepared_dev, int32_t* info_dev, void* stream);
+size_t kw_convert_workspace_bytes(int64_t total_frames, int n_components, int dim_half,
+                                  int precision);
+int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t total_frames, int max_frames,
+                     const double* src_dev, int n_components, int dim_half,
+                     const double* prepared_dev, double* out_dev, int32_t* mix_dev,
+                     int precision, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KWIIYATTA_B200_H_ */

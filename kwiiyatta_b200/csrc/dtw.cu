@@ -1,0 +1,496 @@
+// Batched DTW / FastDTW for sm_100a.
+//
+// Replaces fastdtw.fastdtw(x_feature, y_feature, dist=2, radius=radius) at
+// kwiiyatta/vocoder/align.py:71 (fastdtw==0.3.2 semantics, see oracle/fastdtw_ref.py):
+//   * multi-resolution pyramid ((a+b)/2, odd tail dropped) down to the first level with
+//     tx < radius+2 or ty < radius+2, exhaustive DP there;
+//   * per finer level the window of row a is the closed form
+//       S = { j : (i, j) on the coarser path, |i - a/2| <= radius }
+//       cols [ 2*(min S - radius), 2*(max S + radius) + 1 ] clipped to [0, ty-1]
+//     so only first_j / last_j per coarse row are carried between levels;
+//   * cell rule D = min(up + d, left + d, diag + d), compared after the addition, first
+//     minimum wins in the order up, left, diag; FP64 throughout; the local distance is
+//     sqrt(sum_k fma(d_k, d_k, s)) summed left to right (p = 2) or sum |d_k| (p = 1).
+//
+// Kernel structure (one CTA per pair per level):
+//   strip-mined systolic wavefront.  A strip is 2*NT consecutive rows; thread t keeps rows
+//   i0+2t and i0+2t+1 of x in registers and walks the columns with a skew of one step per
+//   thread, so the only inter-thread traffic per step is one double (its lower row's D value)
+//   through a double-buffered shared array.  y is staged k-major in a shared-memory ring of
+//   2*NT columns, refilled NT columns at a time with coalesced loads.  The D values of a
+//   strip's last row go through a small global ping-pong buffer to the next strip.
+//   Back-pointers are 2 bits per cell, packed 16 per word by the owning thread.
+//   The distance matrix never exists in memory.
+#include <algorithm>
+#include <vector>
+
+#include <climits>
+
+#include "common.cuh"
+
+namespace kw {
+
+constexpr int MAXLEV = 20;
+
+struct PairDesc {
+    int nlev;
+    int pad_;
+    int tx[MAXLEV];
+    int ty[MAXLEV];
+    long long xoff[MAXLEV];    // doubles, k-major (F x tx) block per level
+    long long yoff[MAXLEV];
+    long long rj_off[MAXLEV];  // int32: first_j[tx] then last_j[tx] for levels >= 1
+    long long xrow0, yrow0;    // first row in the caller's concatenated inputs
+    long long bp_off;          // uint32 words, tx0 * ceil(ty0/16)
+    long long brow_off;        // doubles, 2 * ty0
+    long long path_off;        // points, capacity tx0 + ty0
+};
+
+struct DtwPlan {
+    std::vector<PairDesc> descs;
+    std::vector<int> order;
+    int maxlev = 0;
+    size_t n_pyr_x = 0, n_pyr_y = 0, n_rowj = 0, n_bp = 0, n_brow = 0;
+    std::vector<int> level_max_tx;
+};
+
+static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radius, int F,
+                     DtwPlan& plan) {
+    plan.descs.resize(n_pairs);
+    long long xrow = 0, yrow = 0, path = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        PairDesc& d = plan.descs[p];
+        if (tx[p] <= 0 || ty[p] <= 0) {
+            set_error("pair %d has an empty sequence (tx=%d, ty=%d)", p, tx[p], ty[p]);
+            return KW_ERR_INVALID;
+        }
+        int a = tx[p], b = ty[p], l = 0;
+        for (;;) {
+            if (l >= MAXLEV) {
+                set_error("pair %d needs more than %d resolution levels", p, MAXLEV);
+                return KW_ERR_INVALID;
+            }
+            d.tx[l] = a;
+            d.ty[l] = b;
+            d.xoff[l] = (long long)plan.n_pyr_x;
+            d.yoff[l] = (long long)plan.n_pyr_y;
+            plan.n_pyr_x += (size_t)a * F;
+            plan.n_pyr_y += (size_t)b * F;
+            if (l >= 1) {
+                d.rj_off[l] = (long long)plan.n_rowj;
+                plan.n_rowj += 2 * (size_t)a;
+            } else {
+                d.rj_off[l] = 0;
+            }
+            if ((int)plan.level_max_tx.size() <= l) plan.level_max_tx.push_back(0);
+            plan.level_max_tx[l] = std::max(plan.level_max_tx[l], a);
+            ++l;
+            if (radius < 0 || a < radius + 2 || b < radius + 2) break;
+            a /= 2;
+            b /= 2;
+        }
+        d.nlev = l;
+        d.pad_ = 0;
+        plan.maxlev = std::max(plan.maxlev, l);
+        d.xrow0 = xrow;
+        d.yrow0 = yrow;
+        xrow += tx[p];
+        yrow += ty[p];
+        d.bp_off = (long long)plan.n_bp;
+        plan.n_bp += (size_t)tx[p] * (size_t)((ty[p] + 15) / 16);
+        d.brow_off = (long long)plan.n_brow;
+        plan.n_brow += 2 * (size_t)ty[p];
+        d.path_off = path;
+        path += (long long)tx[p] + ty[p];
+    }
+    plan.order.resize(n_pairs);
+    for (int p = 0; p < n_pairs; ++p) plan.order[p] = p;
+    std::stable_sort(plan.order.begin(), plan.order.end(), [&](int a, int b) {
+        return (long long)tx[a] * ty[a] > (long long)tx[b] * ty[b];
+    });
+    return KW_OK;
+}
+
+struct DtwWorkspace {
+    PairDesc* descs;
+    int* order;
+    double* xpyr;
+    double* ypyr;
+    int* rowj;
+    uint32_t* bp;
+    double* brow;
+    size_t bytes;
+};
+
+static DtwWorkspace carve(const DtwPlan& plan, void* base) {
+    Carver c(base);
+    DtwWorkspace w;
+    w.descs = c.take<PairDesc>(plan.descs.size());
+    w.order = c.take<int>(plan.order.size());
+    w.xpyr = c.take<double>(plan.n_pyr_x);
+    w.ypyr = c.take<double>(plan.n_pyr_y);
+    w.rowj = c.take<int>(plan.n_rowj + 1);
+    w.bp = c.take<uint32_t>(plan.n_bp);
+    w.brow = c.take<double>(plan.n_brow);
+    w.bytes = align_up(c.used, 256);
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pyramid: level 0 = transpose of the caller's row-major rows into k-major; level l>0 =
+// pairwise mean of level l-1.  grid (n_pairs, 2): y = 0 -> x side, 1 -> y side.
+// ---------------------------------------------------------------------------------------
+__global__ void dtw_pyramid_kernel(const PairDesc* __restrict__ descs, int level, int F,
+                                   const double* __restrict__ x_in,
+                                   const double* __restrict__ y_in, double* __restrict__ xpyr,
+                                   double* __restrict__ ypyr) {
+    const PairDesc& d = descs[blockIdx.x];
+    if (level >= d.nlev) return;
+    const bool is_y = blockIdx.y == 1;
+    const int T = is_y ? d.ty[level] : d.tx[level];
+    double* out = is_y ? ypyr + d.yoff[level] : xpyr + d.xoff[level];
+    if (level == 0) {
+        const double* in = is_y ? y_in + d.yrow0 * F : x_in + d.xrow0 * F;
+        const long long n = (long long)T * F;
+        for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+            const int i = (int)(e / F), k = (int)(e % F);
+            out[(size_t)k * T + i] = in[e];
+        }
+    } else {
+        const int Tp = is_y ? d.ty[level - 1] : d.tx[level - 1];
+        const double* in = is_y ? ypyr + d.yoff[level - 1] : xpyr + d.xoff[level - 1];
+        const long long n = (long long)T * F;
+        for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+            const int k = (int)(e / T), i = (int)(e % T);
+            const double a = in[(size_t)k * Tp + 2 * i];
+            const double b = in[(size_t)k * Tp + 2 * i + 1];
+            out[e] = __dmul_rn(__dadd_rn(a, b), 0.5);
+        }
+    }
+}
+
+template <int P>
+__device__ __forceinline__ double dist_acc(double s, double d) {
+    if (P == 2) return __fma_rn(d, d, s);
+    return __dadd_rn(s, fabs(d));
+}
+template <int P>
+__device__ __forceinline__ double dist_fin(double s) {
+    if (P == 2) return __dsqrt_rn(s);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Windowed DP for one resolution level.
+// ---------------------------------------------------------------------------------------
+template <int FP, int NT, int P>
+__global__ void __launch_bounds__(NT)
+dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
+              int radius, int F, const double* __restrict__ xpyr,
+              const double* __restrict__ ypyr, const int* __restrict__ rowj,
+              uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost,
+              unsigned long long* __restrict__ cells) {
+    constexpr int CH = NT;
+    constexpr int RING = 2 * NT;
+    constexpr int RS = RING + 1;
+    extern __shared__ double smem[];
+    double* ys = smem;             // FP * RS, k-major ring of y columns
+    double* xch = ys + FP * RS;    // 2 * NT: lower-row D values, double-buffered by step parity
+    double* brs = xch + 2 * NT;    // RING: previous strip's last row, staged with the y ring
+    __shared__ unsigned long long cell_count;
+
+    const int pair = order[blockIdx.x];
+    const PairDesc& d = descs[pair];
+    if (level >= d.nlev) return;
+    const int t = threadIdx.x;
+    const int tx = d.tx[level], ty = d.ty[level];
+    const double* __restrict__ xT = xpyr + d.xoff[level];
+    const double* __restrict__ yT = ypyr + d.yoff[level];
+    const bool full = (level == d.nlev - 1);
+    const int ctx = full ? 0 : d.tx[level + 1];
+    const int* __restrict__ cfirst = full ? nullptr : rowj + d.rj_off[level + 1];
+    const int* __restrict__ clast = full ? nullptr : cfirst + ctx;
+    const int pitchw = (ty + 15) >> 4;
+    uint32_t* bp_pair = bp + d.bp_off;
+    double* brow_pair = brow + d.brow_off;
+    const double INF = CUDART_INF;
+
+    auto window = [&](int a, int& lo, int& hi) {
+        if (full) {
+            lo = 0;
+            hi = ty - 1;
+            return;
+        }
+        const int ca = a >> 1;
+        int r0 = max(0, ca - radius);
+        const int r1 = min(ctx - 1, ca + radius);
+        r0 = min(r0, r1);
+        lo = max(0, 2 * (cfirst[r0] - radius));
+        hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
+    };
+
+    if (t == 0) cell_count = 0ull;
+    // zero the padded feature rows of the ring once
+    for (int e = t; e < (FP - F) * RS; e += NT) ys[F * RS + e] = 0.0;
+
+    unsigned int my_cells = 0;
+    int strip = 0;
+    for (int i0 = 0; i0 < tx; i0 += 2 * NT, ++strip) {
+        const int ia = i0 + 2 * t, ib = ia + 1;
+        int loa = INT_MAX, hia = INT_MIN, lob = INT_MAX, hib = INT_MIN;
+        if (ia < tx) window(ia, loa, hia);
+        if (ib < tx) window(ib, lob, hib);
+        double xa[FP], xb[FP];
+#pragma unroll
+        for (int k = 0; k < FP; ++k) {
+            xa[k] = (k < F && ia < tx) ? xT[(size_t)k * tx + ia] : 0.0;
+            xb[k] = (k < F && ib < tx) ? xT[(size_t)k * tx + ib] : 0.0;
+        }
+        // strip-wide quantities (uniform across the CTA)
+        int jstart, dummy;
+        window(i0, jstart, dummy);
+        const int il = min(tx, i0 + 2 * NT) - 1;
+        int hil;
+        window(il, dummy, hil);
+        const int n_steps = hil - jstart + ((il - i0) >> 1) + 1;
+        int plo = INT_MAX, phi = INT_MIN;
+        if (i0 > 0) window(i0 - 1, plo, phi);
+        const double* brow_in = brow_pair + ((strip & 1) ? 0 : ty);
+        double* brow_out = brow_pair + ((strip & 1) ? ty : 0);
+        const bool writes_boundary = (t == NT - 1) && (i0 + 2 * NT < tx);
+
+        double va_prev = INF, vb_prev = INF, diag_in = INF;
+        if (t == 0) {
+            const int jm = jstart - 1;
+            if (i0 == 0)
+                diag_in = (jm == -1) ? 0.0 : INF;  // virtual origin D[0][0] = 0
+            else
+                diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
+        }
+        xch[NT + t] = INF;  // parity 1 is read at step 0
+        uint32_t wa = 0u, wb = 0u;
+        uint32_t* bpa = bp_pair + (size_t)ia * pitchw;
+        uint32_t* bpb = bp_pair + (size_t)ib * pitchw;
+        __syncthreads();
+
+        for (int s = 0; s < n_steps; ++s) {
+            if ((s % CH) == 0) {
+                const int jbase = jstart + s;
+                for (int e = t; e < F * CH; e += NT) {
+                    const int k = e / CH, jj = e - k * CH;
+                    const int j = jbase + jj;
+                    if (j < ty) ys[k * RS + (j & (RING - 1))] = yT[(size_t)k * ty + j];
+                }
+                {
+                    const int j = jbase + t;
+                    brs[j & (RING - 1)] =
+                        (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                }
+                __syncthreads();
+            }
+            const int j = jstart + s - t;
+            const double up_in =
+                (t == 0) ? brs[j & (RING - 1)] : xch[((s + 1) & 1) * NT + t - 1];
+            const bool act_a = (j >= loa) && (j <= hia);
+            const bool act_b = (j >= lob) && (j <= hib);
+            double va = INF, vb = INF;
+            if (act_a || act_b) {
+                double sa = 0.0, sb = 0.0;
+                const double* yp = ys + (j & (RING - 1));
+#pragma unroll
+                for (int k = 0; k < FP; ++k) {
+                    const double yv = yp[k * RS];
+                    sa = dist_acc<P>(sa, __dsub_rn(xa[k], yv));
+                    sb = dist_acc<P>(sb, __dsub_rn(xb[k], yv));
+                }
+                if (act_a) {
+                    const double dt = dist_fin<P>(sa);
+                    double best = __dadd_rn(up_in, dt);
+                    uint32_t code = 0u;
+                    double c = __dadd_rn(va_prev, dt);
+                    if (c < best) { best = c; code = 1u; }
+                    c = __dadd_rn(diag_in, dt);
+                    if (c < best) { best = c; code = 2u; }
+                    va = best;
+                    wa |= code << (2 * (j & 15));
+                    if ((j & 15) == 15 || j == hia) { bpa[j >> 4] = wa; wa = 0u; }
+                    if (ia == tx - 1 && j == ty - 1) cost[pair] = va;
+                    ++my_cells;
+                }
+                if (act_b) {
+                    const double dt = dist_fin<P>(sb);
+                    double best = __dadd_rn(va, dt);
+                    uint32_t code = 0u;
+                    double c = __dadd_rn(vb_prev, dt);
+                    if (c < best) { best = c; code = 1u; }
+                    c = __dadd_rn(va_prev, dt);
+                    if (c < best) { best = c; code = 2u; }
+                    vb = best;
+                    wb |= code << (2 * (j & 15));
+                    if ((j & 15) == 15 || j == hib) { bpb[j >> 4] = wb; wb = 0u; }
+                    if (ib == tx - 1 && j == ty - 1) cost[pair] = vb;
+                    if (writes_boundary) __stcg(brow_out + j, vb);
+                    ++my_cells;
+                }
+            }
+            xch[(s & 1) * NT + t] = vb;
+            va_prev = va;
+            vb_prev = vb;
+            diag_in = up_in;
+            __syncthreads();
+        }
+    }
+    if (cells != nullptr) {
+        atomicAdd(&cell_count, (unsigned long long)my_cells);
+        __syncthreads();
+        if (t == 0) atomicAdd(cells + pair, cell_count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backtrace: one thread per pair walks the 2-bit codes from (tx-1, ty-1) to the origin.
+// Level 0 writes the path (backwards, into the tail of the pair's region); levels >= 1 only
+// record first_j / last_j per row for the next finer level's window.
+// ---------------------------------------------------------------------------------------
+__global__ void dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
+                                     const uint32_t* __restrict__ bp, int* __restrict__ rowj,
+                                     int32_t* __restrict__ path, int32_t* __restrict__ path_begin,
+                                     int32_t* __restrict__ path_len) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const PairDesc& d = descs[pair];
+    if (level >= d.nlev) return;
+    const int tx = d.tx[level], ty = d.ty[level];
+    const int pitchw = (ty + 15) >> 4;
+    const uint32_t* bpp = bp + d.bp_off;
+    int* first = (level > 0) ? rowj + d.rj_off[level] : nullptr;
+    int* last = (level > 0) ? first + tx : nullptr;
+    const int cap = d.tx[0] + d.ty[0];
+    int32_t* out = path + 2 * d.path_off;
+    int i = tx - 1, j = ty - 1, n = 0, prev_i = -1, prev_j = -1;
+    while (i >= 0 && j >= 0 && n < tx + ty) {
+        if (level == 0) {
+            out[2 * (cap - 1 - n)] = i;
+            out[2 * (cap - 1 - n) + 1] = j;
+        } else if (i != prev_i) {
+            last[i] = j;
+            if (prev_i >= 0) first[prev_i] = prev_j;
+        }
+        prev_i = i;
+        prev_j = j;
+        const uint32_t w = __ldcg(bpp + (size_t)i * pitchw + (j >> 4));
+        const uint32_t code = (w >> (2 * (j & 15))) & 3u;
+        if (code == 0u) {
+            --i;
+        } else if (code == 1u) {
+            --j;
+        } else {
+            --i;
+            --j;
+        }
+        ++n;
+    }
+    if (level > 0 && prev_i >= 0) first[prev_i] = prev_j;
+    if (level == 0) {
+        path_begin[pair] = cap - n;
+        path_len[pair] = n;
+    }
+}
+
+template <int FP, int NT, int P>
+static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
+                     double* cost, unsigned long long* cells, cudaStream_t st) {
+    constexpr int RS = 2 * NT + 1;
+    const size_t smem = sizeof(double) * ((size_t)FP * RS + 2 * NT + 2 * NT);
+    auto kern = dtw_dp_kernel<FP, NT, P>;
+    KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    kern<<<n_pairs, NT, smem, st>>>(w.descs, w.order, level, radius, F, w.xpyr, w.ypyr, w.rowj,
+                                    w.bp, w.brow, cost, cells);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+template <int FP, int P>
+static int launch_dp_nt(int nt, int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
+                        double* cost, unsigned long long* cells, cudaStream_t st) {
+    if (nt == 32) return launch_dp<FP, 32, P>(n_pairs, w, level, radius, F, cost, cells, st);
+    if (nt == 64) return launch_dp<FP, 64, P>(n_pairs, w, level, radius, F, cost, cells, st);
+    return launch_dp<FP, 128, P>(n_pairs, w, level, radius, F, cost, cells, st);
+}
+
+template <int P>
+static int launch_dp_fp(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
+                        double* cost, unsigned long long* cells, cudaStream_t st) {
+    if (F <= 8) return launch_dp_nt<8, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    if (F <= 16) return launch_dp_nt<16, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    if (F <= 26) return launch_dp_nt<26, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    return launch_dp_nt<32, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+}
+
+}  // namespace kw
+
+using namespace kw;
+
+extern "C" size_t kw_dtw_workspace_bytes(int n_pairs, const int32_t* tx_host,
+                                         const int32_t* ty_host, int feat_dim, int radius) {
+    if (n_pairs <= 0 || feat_dim <= 0) return 0;
+    DtwPlan plan;
+    if (make_plan(n_pairs, tx_host, ty_host, radius, feat_dim, plan) != KW_OK) return 0;
+    return carve(plan, nullptr).bytes;
+}
+
+extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_dev,
+                            const int32_t* tx_host, const int32_t* ty_host, int feat_dim,
+                            int radius, int p_norm, int precision, double* cost_dev,
+                            int32_t* path_dev, int32_t* path_begin_dev, int32_t* path_len_dev,
+                            int64_t* cells_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_pairs == 0) return KW_OK;
+    KW_REQUIRE(n_pairs > 0, "n_pairs must be >= 0");
+    KW_REQUIRE(feat_dim > 0, "feat_dim must be positive");
+    KW_REQUIRE(p_norm == 1 || p_norm == 2, "p_norm must be 1 or 2 (got %d)", p_norm);
+    if (feat_dim > 32) {
+        set_error("feat_dim %d > 32 is not supported by the sm_100a DTW kernels", feat_dim);
+        return KW_ERR_UNSUPPORTED;
+    }
+    if (precision != 0) {
+        set_error("DTW precision %d is not built (0 = fp64 exact)", precision);
+        return KW_ERR_UNSUPPORTED;
+    }
+    DtwPlan plan;
+    int rc = make_plan(n_pairs, tx_host, ty_host, radius, feat_dim, plan);
+    if (rc != KW_OK) return rc;
+    DtwWorkspace w = carve(plan, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("DTW workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    KW_CUDA_CHECK(cudaMemcpyAsync(w.descs, plan.descs.data(), sizeof(PairDesc) * n_pairs,
+                                  cudaMemcpyHostToDevice, st));
+    KW_CUDA_CHECK(cudaMemcpyAsync(w.order, plan.order.data(), sizeof(int) * n_pairs,
+                                  cudaMemcpyHostToDevice, st));
+    if (cells_dev != nullptr)
+        KW_CUDA_CHECK(cudaMemsetAsync(cells_dev, 0, sizeof(int64_t) * n_pairs, st));
+    for (int l = 0; l < plan.maxlev; ++l) {
+        dtw_pyramid_kernel<<<dim3(n_pairs, 2), 256, 0, st>>>(w.descs, l, feat_dim, x_dev, y_dev,
+                                                             w.xpyr, w.ypyr);
+        KW_CUDA_CHECK(cudaGetLastError());
+    }
+    for (int l = plan.maxlev - 1; l >= 0; --l) {
+        const int mtx = plan.level_max_tx[l];
+        const int nt = (mtx <= 64) ? 32 : (mtx <= 128 ? 64 : 128);
+        unsigned long long* cells = reinterpret_cast<unsigned long long*>(cells_dev);
+        if (p_norm == 2)
+            rc = launch_dp_fp<2>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        else
+            rc = launch_dp_fp<1>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        if (rc != KW_OK) return rc;
+        dtw_backtrace_kernel<<<(n_pairs + 31) / 32, 32, 0, st>>>(
+            w.descs, n_pairs, l, w.bp, w.rowj, path_dev, path_begin_dev, path_len_dev);
+        KW_CUDA_CHECK(cudaGetLastError());
+    }
+    // the host-side plan vectors were consumed by the (staged) async copies above
+    return KW_OK;
+}

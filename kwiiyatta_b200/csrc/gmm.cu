@@ -1,0 +1,653 @@
+// Full-covariance joint-GMM EM, FP64 CUDA-core path (precision = 0), for sm_100a.
+//
+// Replaces sklearn GaussianMixture.fit as configured at kwiiyatta/converter/gmm.py:9-26
+// (formulae: sklearn/mixture/_gaussian_mixture.py _estimate_log_gaussian_prob,
+// _estimate_gaussian_parameters, _compute_precision_cholesky; restated in oracle/gmm_ref.py).
+//
+//   E-step   wlp[n,k] = -1/2 (D log 2pi + || x_n L_k - mu_k L_k ||^2) + log|L_k| + log w_k
+//            resp = exp(wlp - logsumexp_k wlp);  sum_n logsumexp -> lower bound
+//   M-step   n_k = sum r, m_k = sum r (x - c_k), S_k = sum r (x - c_k)(x - c_k)^T accumulated
+//            around the previous means c_k (so the cancellation in S/n - delta delta^T is
+//            second order), partials reduced in a fixed order (bitwise reproducible)
+//   finalize weights, means, covariances (+reg I), Cholesky, triangular inverse -> L, log|L|.
+#include <cfloat>
+#include <climits>
+
+#include "common.cuh"
+
+namespace kw {
+
+constexpr int E_FT = 64;   // frames per CTA tile in the E-step
+constexpr int E_KC = 16;   // contraction chunk
+constexpr int M_FB = 8;    // frames per smem stage in the M-step (static smem < 48 KB)
+
+__host__ __device__ static inline size_t stats_block(int D) { return 1 + (size_t)D + (size_t)D * D; }
+
+// ---------------------------------------------------------------------------------------
+// E-step.  CTA = 64 frames x all K components.  256 threads = 16 frame groups (4 frames
+// each, interleaved) x 16 column groups (TN contiguous columns each).
+// mode 0: write resp + per-CTA sum of logsumexp.  mode 1: hard argmax (np.argmax: first max).
+// ---------------------------------------------------------------------------------------
+template <int TN>
+__global__ void __launch_bounds__(256)
+gmm_estep_kernel(long long N, const double* __restrict__ X, int K, int D,
+                 const double* __restrict__ prec_chol, const double* __restrict__ aux,
+                 double* __restrict__ resp, double* __restrict__ lse_partial, int mode,
+                 int32_t* __restrict__ mix_out) {
+    constexpr int WT = 16 * TN;
+    extern __shared__ double sm[];
+    const int Dp = (D + E_KC - 1) / E_KC * E_KC;
+    const int XS = Dp + 1;
+    double* xs = sm;                 // E_FT * XS
+    double* ls = xs + E_FT * XS;     // 2 * E_KC * WT
+    __shared__ double warp_lse[8];
+
+    const int tid = threadIdx.x;
+    const int tr = tid >> 4, tc = tid & 15;
+    const long long n0 = (long long)blockIdx.x * E_FT;
+    const int nchunks = Dp / E_KC;
+    const double LOG2PI = 1.8378770664093453;
+
+    for (int e = tid; e < E_FT * Dp; e += 256) {
+        const int f = e / Dp, dd = e - f * Dp;
+        const long long n = n0 + f;
+        xs[f * XS + dd] = (n < N && dd < D) ? X[n * D + dd] : 0.0;
+    }
+
+    double best_v[4];
+    int best_k[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { best_v[m] = -CUDART_INF; best_k[m] = 0; }
+
+    for (int k = 0; k < K; ++k) {
+        const double* __restrict__ Lk = prec_chol + (size_t)k * D * D;
+        double acc[4][TN];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int c = 0; c < TN; ++c) acc[m][c] = 0.0;
+        double pre[TN];
+        auto prefetch = [&](int dc) {
+#pragma unroll
+            for (int q = 0; q < TN; ++q) {
+                const int e = tid + 256 * q;
+                const int dd = e / WT, j = e - dd * WT;
+                const int dg = dc * E_KC + dd;
+                pre[q] = (dg < D && j < D) ? Lk[(size_t)dg * D + j] : 0.0;
+            }
+        };
+        auto stash = [&](int buf) {
+#pragma unroll
+            for (int q = 0; q < TN; ++q) ls[buf * E_KC * WT + tid + 256 * q] = pre[q];
+        };
+        prefetch(0);
+        __syncthreads();  // previous k finished reading ls / first pass: xs complete
+        stash(0);
+        __syncthreads();
+        for (int dc = 0; dc < nchunks; ++dc) {
+            if (dc + 1 < nchunks) prefetch(dc + 1);
+            const double* lb = ls + (dc & 1) * E_KC * WT + tc * TN;
+            const double* xb = xs + tr * XS + dc * E_KC;
+#pragma unroll
+            for (int dd = 0; dd < E_KC; ++dd) {
+                double a[4], b[TN];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) a[m] = xb[(16 * m) * XS + dd];
+#pragma unroll
+                for (int c = 0; c < TN; ++c) b[c] = lb[dd * WT + c];
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int c = 0; c < TN; ++c) acc[m][c] = fma(a[m], b[c], acc[m][c]);
+            }
+            if (dc + 1 < nchunks) stash((dc + 1) & 1);
+            __syncthreads();
+        }
+        const double* ak = aux + (size_t)k * (D + 2);
+        double bk[TN];
+#pragma unroll
+        for (int c = 0; c < TN; ++c) {
+            const int j = tc * TN + c;
+            bk[c] = (j < D) ? ak[j] : 0.0;
+        }
+        const double cst = ak[D] /* log|L| */, lw = ak[D + 1];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            double q = 0.0;
+#pragma unroll
+            for (int c = 0; c < TN; ++c) {
+                const double y = acc[m][c] - bk[c];
+                q = fma(y, y, q);
+            }
+            q += __shfl_xor_sync(0xffffffffu, q, 8);
+            q += __shfl_xor_sync(0xffffffffu, q, 4);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            if (tc == 0) {
+                const long long n = n0 + tr + 16 * m;
+                const double wlp = (-0.5 * ((double)D * LOG2PI + q) + cst) + lw;
+                if (mode == 0) {
+                    if (n < N) __stcg(resp + n * K + k, wlp);
+                } else if (wlp > best_v[m]) {
+                    best_v[m] = wlp;
+                    best_k[m] = k;
+                }
+            }
+        }
+    }
+    if (mode == 1) {
+        if (tc == 0) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const long long n = n0 + tr + 16 * m;
+                if (n < N) mix_out[n] = best_k[m];
+            }
+        }
+        return;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    double lse_acc = 0.0;
+    for (int f = warp * 8; f < warp * 8 + 8; ++f) {
+        const long long n = n0 + f;
+        if (n >= N) break;
+        double* row = resp + n * K;
+        double mx = -CUDART_INF;
+        for (int k = lane; k < K; k += 32) mx = fmax(mx, __ldcg(row + k));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double s = 0.0;
+        for (int k = lane; k < K; k += 32) s += exp(__ldcg(row + k) - mx);
+        s = warp_sum(s);
+        const double lse = log(s) + mx;
+        for (int k = lane; k < K; k += 32) row[k] = exp(__ldcg(row + k) - lse);
+        lse_acc += lse;
+    }
+    if (lane == 0) warp_lse[warp] = lse_acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += warp_lse[w];
+        lse_partial[blockIdx.x] = s;
+    }
+}
+
+// Sum `n` doubles in a fixed order (single CTA) and write {sum, extra} to out[0], out[1].
+__global__ void reduce_fixed_kernel(const double* __restrict__ in, long long n, double extra,
+                                    double* __restrict__ out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += in[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sh[0];
+        out[1] = extra;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// M-step, first moments: grid (n_chunks, ceil(K/8)); thread d < D owns column d for 8
+// components, thread d == D accumulates n_k.  partial[(chunk*K + k)*(D+1) + {0: n, 1+d: m}].
+// ---------------------------------------------------------------------------------------
+__global__ void gmm_m1_kernel(long long N, const double* __restrict__ X, int K, int D,
+                              const double* __restrict__ resp, const double* __restrict__ centres,
+                              double* __restrict__ partial, long long frames_per_chunk) {
+    const int d = threadIdx.x;
+    const int k0 = blockIdx.y * 8;
+    const long long n_begin = (long long)blockIdx.x * frames_per_chunk;
+    const long long n_end = min(N, n_begin + frames_per_chunk);
+    double acc[8], cc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        acc[q] = 0.0;
+        cc[q] = (d < D && k0 + q < K) ? centres[(size_t)(k0 + q) * D + d] : 0.0;
+    }
+    if (d <= D) {
+        for (long long n = n_begin; n < n_end; ++n) {
+            const double x = (d < D) ? X[n * D + d] : 0.0;
+            const double* r = resp + n * K + k0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double rv = (k0 + q < K) ? r[q] : 0.0;
+                acc[q] = (d < D) ? fma(rv, x - cc[q], acc[q]) : acc[q] + rv;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (k0 + q < K) {
+                double* p = partial + ((size_t)blockIdx.x * K + (k0 + q)) * (D + 1);
+                p[(d < D) ? 1 + d : 0] = acc[q];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// M-step, second moments: grid (K, n_chunks, n_tile_pairs).  CTA = one W x W output tile
+// (W = 16*TM) of S_k over one chunk of frames; 256 threads, TM x TM accumulators each.
+// ---------------------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(256)
+gmm_m2_kernel(long long N, const double* __restrict__ X, int K, int D,
+              const double* __restrict__ resp, const double* __restrict__ centres,
+              double* __restrict__ partial, long long frames_per_chunk, int n_tiles) {
+    constexpr int W = 16 * TM;
+    constexpr int WS = W + 1;
+    __shared__ double sa[2][M_FB * WS];
+    __shared__ double sb[2][M_FB * WS];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int k = blockIdx.x;
+    // tile pair (bi <= bj) from the linear index
+    int bi = 0, bj = 0;
+    {
+        int t = blockIdx.z;
+        for (bi = 0; bi < n_tiles; ++bi) {
+            const int row = n_tiles - bi;
+            if (t < row) { bj = bi + t; break; }
+            t -= row;
+        }
+    }
+    const bool same = (bi == bj);
+    const long long n_begin = (long long)blockIdx.y * frames_per_chunk;
+    const long long n_end = min(N, n_begin + frames_per_chunk);
+    const double* ck = centres + (size_t)k * D;
+
+    double acc[TM][TM];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+
+    constexpr int PER = (M_FB * W + 255) / 256;
+    double pa[PER], pb[PER];
+    auto prefetch = [&](long long nb) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + 256 * q;
+            const int f = e / W, c = e - f * W;
+            const long long n = nb + f;
+            double va = 0.0, vb = 0.0;
+            if (e < M_FB * W && n < n_end) {
+                const double r = resp[n * K + k];
+                const int ci = bi * W + c, cj = bj * W + c;
+                const double xi = (ci < D) ? X[n * D + ci] - ck[ci] : 0.0;
+                va = r * xi;
+                vb = same ? xi : ((cj < D) ? X[n * D + cj] - ck[cj] : 0.0);
+            }
+            pa[q] = va;
+            pb[q] = vb;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + 256 * q;
+            if (e < M_FB * W) {
+                const int f = e / W, c = e - f * W;
+                sa[buf][f * WS + c] = pa[q];
+                sb[buf][f * WS + c] = pb[q];
+            }
+        }
+    };
+    if (n_begin < n_end) {
+        prefetch(n_begin);
+        stash(0);
+        __syncthreads();
+        int buf = 0;
+        for (long long nb = n_begin; nb < n_end; nb += M_FB) {
+            const bool more = nb + M_FB < n_end;
+            if (more) prefetch(nb + M_FB);
+            const double* a_base = sa[buf] + ty * TM;
+            const double* b_base = sb[buf] + tx * TM;
+#pragma unroll
+            for (int f = 0; f < M_FB; ++f) {
+                double a[TM], b[TM];
+#pragma unroll
+                for (int q = 0; q < TM; ++q) a[q] = a_base[f * WS + q];
+#pragma unroll
+                for (int q = 0; q < TM; ++q) b[q] = b_base[f * WS + q];
+#pragma unroll
+                for (int p = 0; p < TM; ++p)
+#pragma unroll
+                    for (int q = 0; q < TM; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+            }
+            if (more) stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    // partial layout: [chunk][k][D][D]
+    double* out = partial + ((size_t)blockIdx.y * K + k) * (size_t)D * D;
+#pragma unroll
+    for (int p = 0; p < TM; ++p) {
+        const int i = bi * W + ty * TM + p;
+        if (i >= D) continue;
+#pragma unroll
+        for (int q = 0; q < TM; ++q) {
+            const int j = bj * W + tx * TM + q;
+            if (j >= D) continue;
+            out[(size_t)i * D + j] = acc[p][q];
+            if (!same) out[(size_t)j * D + i] = acc[p][q];
+        }
+    }
+}
+
+// stats[k] = sum over chunks (fixed order) of the first- and second-moment partials.
+__global__ void gmm_reduce_partials_kernel(int K, int D, int chunks1, const double* __restrict__ p1,
+                                           int chunks2, const double* __restrict__ p2,
+                                           double* __restrict__ stats) {
+    const size_t sb = stats_block(D);
+    const size_t total = (size_t)K * sb;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / sb);
+        const size_t r = e - (size_t)k * sb;
+        double s = 0.0;
+        if (r < (size_t)D + 1) {
+            for (int c = 0; c < chunks1; ++c) s += p1[((size_t)c * K + k) * (D + 1) + r];
+        } else {
+            const size_t ij = r - (D + 1);
+            for (int c = 0; c < chunks2; ++c) s += p2[((size_t)c * K + k) * (size_t)D * D + ij];
+        }
+        stats[e] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Finalize: one CTA per component.  from_stats = 1: parameters from sufficient statistics;
+// from_stats = 0: only the precision Cholesky of given covariances (weights/means given).
+// Dynamic smem: D * (D + 1) doubles (covariance -> Cholesky factor in the lower triangle,
+// transposed inverse in the strict upper triangle).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_stats,
+                    const double* __restrict__ stats, const double* __restrict__ centres,
+                    double* __restrict__ weights, double* __restrict__ means,
+                    double* __restrict__ covariances, double* __restrict__ prec_chol,
+                    double* __restrict__ aux, int32_t* __restrict__ info) {
+    extern __shared__ double A[];
+    const int S = D + 1;
+    __shared__ double sh_piv;
+    __shared__ int sh_fail;
+    __shared__ double sh_red[256];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    double* cov = covariances + (size_t)k * D * D;
+    double* mu = means + (size_t)k * D;
+    double wk;
+    if (from_stats) {
+        const size_t sb = stats_block(D);
+        const double* st = stats + (size_t)k * sb;
+        const double EPS10 = 10.0 * DBL_EPSILON;
+        const double nk = st[0] + EPS10;
+        double denom;
+        if (weight_norm == 1) {
+            denom = stats[(size_t)K * sb + 1];
+        } else {
+            denom = 0.0;
+            for (int q = 0; q < K; ++q) denom += stats[(size_t)q * sb] + EPS10;
+        }
+        wk = nk / denom;
+        const double* ck = centres + (size_t)k * D;
+        for (int e = tid; e < D * D; e += 256) {
+            const int i = e / D, j = e - i * D;
+            const double di = st[1 + i] / nk, dj = st[1 + j] / nk;
+            double c = st[1 + D + e] / nk - di * dj;
+            if (i == j) c += reg_covar;
+            cov[e] = c;
+            A[i * S + j] = c;
+        }
+        for (int dd = tid; dd < D; dd += 256) mu[dd] = ck[dd] + st[1 + dd] / nk;
+        if (tid == 0) weights[k] = wk;
+    } else {
+        wk = weights[k];
+        for (int e = tid; e < D * D; e += 256) {
+            const int i = e / D, j = e - i * D;
+            A[i * S + j] = cov[e];
+        }
+    }
+    if (tid == 0) sh_fail = 0;
+    __syncthreads();
+    // left-looking Cholesky, thread i owns row i (D <= 256)
+    const int i = tid;
+    for (int j = 0; j < D; ++j) {
+        double s = 0.0;
+        if (i >= j && i < D) {
+            s = A[i * S + j];
+            for (int p = 0; p < j; ++p) s = fma(-A[i * S + p], A[j * S + p], s);
+        }
+        if (i == j) {
+            if (!(s > 0.0)) {
+                if (sh_fail == 0) sh_fail = j + 1;
+                s = 1.0;
+            }
+            sh_piv = sqrt(s);
+            A[j * S + j] = sh_piv;
+        }
+        __syncthreads();
+        if (i > j && i < D) A[i * S + j] = s / sh_piv;
+        __syncthreads();
+    }
+    // Z = C^-1 (lower); store Z^T in the strict upper triangle: A[c][i] = Z[i][c], i > c.
+    if (tid < D) {
+        const int c = tid;
+        const double zcc = 1.0 / A[c * S + c];
+        for (int r = c + 1; r < D; ++r) {
+            double s = A[r * S + c] * zcc;  // C[r][c] * z_c
+            for (int p = c + 1; p < r; ++p) s = fma(A[r * S + p], A[c * S + p], s);
+            A[c * S + r] = -s / A[r * S + r];
+        }
+    }
+    __syncthreads();
+    // prec_chol (upper) = Z^T; diagonal 1 / C[j][j]
+    double* pc = prec_chol + (size_t)k * D * D;
+    for (int e = tid; e < D * D; e += 256) {
+        const int r = e / D, c = e - r * D;
+        double v = 0.0;
+        if (c > r) v = A[r * S + c];
+        else if (c == r) v = 1.0 / A[r * S + r];
+        pc[e] = v;
+    }
+    double ld = 0.0;
+    for (int j = tid; j < D; j += 256) ld += log(1.0 / A[j * S + j]);
+    sh_red[tid] = ld;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) sh_red[tid] += sh_red[tid + o];
+        __syncthreads();
+    }
+    double* ak = aux + (size_t)k * (D + 2);
+    if (tid < D) {
+        const int j = tid;
+        double b = 0.0;
+        for (int dd = 0; dd < j; ++dd) b = fma(mu[dd], A[dd * S + j], b);
+        b = fma(mu[j], 1.0 / A[j * S + j], b);
+        ak[j] = b;
+    }
+    if (tid == 0) {
+        ak[D] = sh_red[0];
+        ak[D + 1] = log(wk);
+        info[k] = sh_fail;
+    }
+}
+
+static int m_chunks(int K) {
+    int c = (4 * 148 + K - 1) / K;
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    return c;
+}
+constexpr int M1_CHUNKS = 296;
+
+struct GmmWorkspace {
+    double* lse_partial;
+    double* p1;
+    double* p2;
+    size_t bytes;
+};
+
+static GmmWorkspace carve_gmm(long long N, int K, int D, void* base) {
+    Carver c(base);
+    GmmWorkspace w;
+    w.lse_partial = c.take<double>((size_t)((N + E_FT - 1) / E_FT) + 1);
+    w.p1 = c.take<double>((size_t)M1_CHUNKS * K * (D + 1));
+    w.p2 = c.take<double>((size_t)m_chunks(K) * K * (size_t)D * D);
+    w.bytes = align_up(c.used, 256);
+    return w;
+}
+
+template <int TN>
+static int launch_estep(long long N, const double* X, int K, int D, const double* pc,
+                        const double* aux, double* resp, double* lse_partial, int mode,
+                        int32_t* mix, cudaStream_t st) {
+    const int Dp = (D + E_KC - 1) / E_KC * E_KC;
+    const size_t smem = sizeof(double) * ((size_t)E_FT * (Dp + 1) + 2 * E_KC * 16 * TN);
+    auto kern = gmm_estep_kernel<TN>;
+    KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    const long long grid = (N + E_FT - 1) / E_FT;
+    kern<<<(unsigned)grid, 256, smem, st>>>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+int estep_fp64(long long N, const double* X, int K, int D, const double* pc, const double* aux,
+               double* resp, double* lse_partial, int mode, int32_t* mix, cudaStream_t st) {
+    if (D <= 16) return launch_estep<1>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix, st);
+    if (D <= 32) return launch_estep<2>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix, st);
+    if (D <= 48) return launch_estep<3>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix, st);
+    if (D <= 80) return launch_estep<5>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix, st);
+    if (D <= 144) return launch_estep<9>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix, st);
+    set_error("dim %d > 144 is not supported by the E-step kernels", D);
+    return KW_ERR_UNSUPPORTED;
+}
+
+template <int TM>
+static int launch_m2(long long N, const double* X, int K, int D, const double* resp,
+                     const double* centres, double* p2, int chunks, cudaStream_t st) {
+    const int W = 16 * TM;
+    const int n_tiles = (D + W - 1) / W;
+    const int n_pairs = n_tiles * (n_tiles + 1) / 2;
+    const long long fpc = (N + chunks - 1) / chunks;
+    gmm_m2_kernel<TM><<<dim3(K, chunks, n_pairs), 256, 0, st>>>(N, X, K, D, resp, centres, p2,
+                                                               fpc, n_tiles);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+int finalize_launch(int K, int D, double reg_covar, int weight_norm, int from_stats,
+                    const double* stats, const double* centres, double* weights, double* means,
+                    double* cov, double* pc, double* aux, int32_t* info, cudaStream_t st) {
+    if (D > 160) {
+        set_error("dim %d > 160 is not supported by the finalize kernel", D);
+        return KW_ERR_UNSUPPORTED;
+    }
+    const size_t smem = sizeof(double) * (size_t)D * (D + 1);
+    KW_CUDA_CHECK(cudaFuncSetAttribute(gmm_finalize_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_finalize_kernel<<<K, 256, smem, st>>>(K, D, reg_covar, weight_norm, from_stats, stats,
+                                              centres, weights, means, cov, pc, aux, info);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+}  // namespace kw
+
+using namespace kw;
+
+extern "C" size_t kw_gmm_stats_len(int K, int D) { return (size_t)K * stats_block(D) + 2; }
+
+extern "C" size_t kw_gmm_workspace_bytes(int64_t n_frames, int K, int D, int precision) {
+    (void)precision;
+    return carve_gmm(n_frames, K, D, nullptr).bytes;
+}
+
+extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const double* means_dev,
+                            const double* prec_chol_dev, const double* aux_dev, double* resp_dev,
+                            double* stats_dev, int precision, void* workspace_dev,
+                            size_t workspace_bytes, void* stream) {
+    (void)means_dev;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_estep: N, K, D must be positive");
+    if (precision != 0) {
+        set_error("GMM precision %d is not built (0 = fp64)", precision);
+        return KW_ERR_UNSUPPORTED;
+    }
+    GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    int rc = estep_fp64(N, x_dev, K, D, prec_chol_dev, aux_dev, resp_dev, w.lse_partial, 0,
+                        nullptr, st);
+    if (rc != KW_OK) return rc;
+    const long long nblk = (N + E_FT - 1) / E_FT;
+    reduce_fixed_kernel<<<1, 256, 0, st>>>(w.lse_partial, nblk, (double)N,
+                                           stats_dev + (size_t)K * stats_block(D));
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, int D,
+                                       const double* resp_dev, const double* centres_dev,
+                                       double* stats_dev, int precision, void* workspace_dev,
+                                       size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_mstep_accumulate: N, K, D must be positive");
+    if (precision != 0) {
+        set_error("GMM precision %d is not built (0 = fp64)", precision);
+        return KW_ERR_UNSUPPORTED;
+    }
+    if (D + 1 > 1024) {
+        set_error("dim %d too large", D);
+        return KW_ERR_UNSUPPORTED;
+    }
+    GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    const long long fpc1 = (N + M1_CHUNKS - 1) / M1_CHUNKS;
+    const int bd = (D + 1 + 31) / 32 * 32;
+    gmm_m1_kernel<<<dim3(M1_CHUNKS, (K + 7) / 8), bd, 0, st>>>(N, x_dev, K, D, resp_dev,
+                                                              centres_dev, w.p1, fpc1);
+    KW_CUDA_CHECK(cudaGetLastError());
+    const int chunks = m_chunks(K);
+    int rc;
+    if (D <= 16) rc = launch_m2<1>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
+    else if (D <= 32) rc = launch_m2<2>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
+    else if (D <= 48) rc = launch_m2<3>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
+    else if (D <= 80) rc = launch_m2<5>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
+    else rc = launch_m2<9>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
+    if (rc != KW_OK) return rc;
+    gmm_reduce_partials_kernel<<<296, 256, 0, st>>>(K, D, M1_CHUNKS, w.p1, chunks, w.p2,
+                                                    stats_dev);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+extern "C" int kw_gmm_mstep_finalize(int K, int D, double reg_covar, int weight_norm,
+                                     const double* stats_dev, const double* centres_dev,
+                                     double* weights_dev, double* means_dev,
+                                     double* covariances_dev, double* prec_chol_dev,
+                                     double* aux_dev, int32_t* info_dev, void* stream) {
+    KW_REQUIRE(K > 0 && D > 0, "kw_gmm_mstep_finalize: K, D must be positive");
+    return finalize_launch(K, D, reg_covar, weight_norm, 1, stats_dev, centres_dev, weights_dev,
+                           means_dev, covariances_dev, prec_chol_dev, aux_dev, info_dev,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kw_gmm_precision_cholesky(int K, int D, const double* weights_dev,
+                                         const double* means_dev, const double* covariances_dev,
+                                         double* prec_chol_dev, double* aux_dev, int32_t* info_dev,
+                                         void* stream) {
+    KW_REQUIRE(K > 0 && D > 0, "kw_gmm_precision_cholesky: K, D must be positive");
+    return finalize_launch(K, D, 0.0, 0, 0, nullptr, nullptr, const_cast<double*>(weights_dev),
+                           const_cast<double*>(means_dev), const_cast<double*>(covariances_dev),
+                           prec_chol_dev, aux_dev, info_dev, static_cast<cudaStream_t>(stream));
+}

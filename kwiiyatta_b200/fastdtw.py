@@ -1,0 +1,126 @@
+"""Drop-in for the third-party ``fastdtw`` module on the B200.
+
+The reference imports ``fastdtw`` at module scope (kwiiyatta/vocoder/align.py:3) and calls
+``fastdtw.fastdtw(x_feature, y_feature, dist=2, radius=radius)`` once (:71); its tests also
+call ``fastdtw.fastdtw(a, b, radius=1, dist=2)`` (tests/kwiiyatta/test_vocoder.py:281-286).
+This module keeps those signatures and return types ``(float, list[tuple[int, int]])`` and
+adds the batched entry points the GPU needs (``fastdtw_batch``); the single-pair functions are
+the batch-of-one case.  All arithmetic runs in kw_dtw_batch (csrc/dtw.cu).
+"""
+import numbers
+
+import numpy as np
+
+from . import _lib
+
+
+def _norm_from_dist(dist, ndim):
+    if dist is None:
+        return 1                       # fastdtw default: |a-b| (1-D) or the 1-norm (2-D)
+    if callable(dist):
+        raise NotImplementedError('callable dist is not supported on the GPU path; use 1 or 2')
+    if isinstance(dist, numbers.Number):
+        if dist <= 0:
+            raise ValueError('dist cannot be a negative integer')
+        if dist in (1, 2):
+            return int(dist)
+        raise NotImplementedError(f'dist={dist!r}: only the 1- and 2-norm are built')
+    raise TypeError(f'unsupported dist {dist!r}')
+
+
+def _prep(x):
+    x = np.asanyarray(x, dtype='float')
+    if x.ndim == 1:
+        x = x[:, None]
+    if x.ndim != 2:
+        raise ValueError('x and y must be 1-D or 2-D')
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+class DtwBatchResult:
+    """Device-resident result of a batched alignment."""
+
+    def __init__(self, cost, path, path_begin, path_len, cells, tx, ty):
+        self.cost, self.path, self.path_begin, self.path_len, self.cells = (
+            cost, path, path_begin, path_len, cells)
+        self.tx, self.ty = tx, ty
+        region = (tx.astype(np.int64) + ty.astype(np.int64))
+        self.region_off = np.concatenate(([0], np.cumsum(region)))
+
+    def to_host(self):
+        """list of (distance: float, path: (L, 2) int32 ndarray) plus total cells."""
+        cost = self.cost.cpu().numpy()
+        path = self.path.cpu().numpy()
+        begin = self.path_begin.cpu().numpy()
+        length = self.path_len.cpu().numpy()
+        out = []
+        for p in range(len(cost)):
+            s = int(self.region_off[p]) + int(begin[p])
+            out.append((float(cost[p]), path[s:s + int(length[p])]))
+        return out
+
+
+def fastdtw_batch_device(x_dev, y_dev, tx, ty, radius=1, dist=2, precision=0):
+    """Batched FastDTW on device-resident, row-concatenated float64 inputs.
+
+    x_dev (sum tx, F), y_dev (sum ty, F) CUDA tensors; tx / ty host int arrays.
+    ``radius < 0`` = exhaustive DTW.  Returns a DtwBatchResult (device tensors)."""
+    torch = _lib.require_cuda()
+    lib = _lib.lib()
+    tx = np.ascontiguousarray(tx, dtype=np.int32)
+    ty = np.ascontiguousarray(ty, dtype=np.int32)
+    n = len(tx)
+    f = x_dev.shape[1]
+    if y_dev.shape[1] != f:
+        raise ValueError('second dimension of x and y must be the same')
+    p_norm = _norm_from_dist(dist, 2)
+    dev = x_dev.device
+    ws_bytes = lib.kw_dtw_workspace_bytes(n, tx.ctypes.data, ty.ctypes.data, f, int(radius))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    total_pts = int(tx.astype(np.int64).sum() + ty.astype(np.int64).sum())
+    cost = torch.empty(n, dtype=torch.float64, device=dev)
+    path = torch.empty((total_pts, 2), dtype=torch.int32, device=dev)
+    begin = torch.empty(n, dtype=torch.int32, device=dev)
+    length = torch.empty(n, dtype=torch.int32, device=dev)
+    cells = torch.empty(n, dtype=torch.int64, device=dev)
+    rc = lib.kw_dtw_batch(n, x_dev.data_ptr(), y_dev.data_ptr(), tx.ctypes.data,
+                          ty.ctypes.data, f, int(radius), p_norm, int(precision),
+                          cost.data_ptr(), path.data_ptr(), begin.data_ptr(),
+                          length.data_ptr(), cells.data_ptr(), ws.data_ptr(), ws_bytes,
+                          _lib.stream_ptr(torch))
+    _lib.check(rc, 'kw_dtw_batch')
+    return DtwBatchResult(cost, path, begin, length, cells, tx, ty)
+
+
+def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None):
+    """``pairs``: sequence of (x, y) host arrays.  Returns a list of
+    ``(distance, path ndarray (L, 2))`` in the same order."""
+    torch = _lib.require_cuda()
+    if len(pairs) == 0:
+        return []
+    xs = [_prep(x) for x, _ in pairs]
+    ys = [_prep(y) for _, y in pairs]
+    for x, y in zip(xs, ys):
+        if x.shape[1] != y.shape[1]:
+            raise ValueError('second dimension of x and y must be the same')
+        if len(x) == 0 or len(y) == 0:
+            raise ValueError('x and y must not be empty')
+    _norm_from_dist(dist, 2)
+    dev = torch.device('cuda' if device is None else device)
+    tx = np.array([len(x) for x in xs], dtype=np.int32)
+    ty = np.array([len(y) for y in ys], dtype=np.int32)
+    x_dev = torch.from_numpy(np.concatenate(xs)).to(dev, non_blocking=True)
+    y_dev = torch.from_numpy(np.concatenate(ys)).to(dev, non_blocking=True)
+    return fastdtw_batch_device(x_dev, y_dev, tx, ty, radius, dist, precision).to_host()
+
+
+def fastdtw(x, y, radius=1, dist=None):
+    """``fastdtw.fastdtw``: approximate DTW distance and path ``[(i, j), ...]``."""
+    cost, path = fastdtw_batch([(x, y)], radius=radius, dist=dist)[0]
+    return cost, [tuple(p) for p in path.tolist()]
+
+
+def dtw(x, y, dist=None):
+    """``fastdtw.dtw``: exhaustive DTW."""
+    cost, path = fastdtw_batch([(x, y)], radius=-1, dist=dist)[0]
+    return cost, [tuple(p) for p in path.tolist()]

@@ -1,0 +1,349 @@
+"""Joint full-covariance GMM on the B200: the back-end behind kwiiyatta's converter seam.
+
+* ``GaussianMixture`` keeps the slice of ``sklearn.mixture.GaussianMixture`` the reference
+  uses (kwiiyatta/converter/gmm.py:13-26; nnmnkwii's MLPG reads ``weights_``, ``means_``,
+  ``covariances_``, ``covariance_type``): same constructor keywords, same fitted attributes,
+  same stopping rule (sklearn/mixture/_base.py fit_predict loop).
+* ``B200GMMFeatureConverter`` mirrors ``GMMFeatureConverter`` (kwiiyatta/converter/gmm.py:8-34)
+  and is what ``MelCepstrumConverter(Converter=...)`` / ``Config.create_converter(Converter=...)``
+  (kwiiyatta/converter/__init__.py:9-14, kwiiyatta/config.py:59-69) receive.
+
+Every E-step / M-step / finalisation runs in csrc/gmm.cu through the C ABI; the only
+host-side arithmetic is the scalar convergence test.  With ``torch.distributed`` initialised
+the per-iteration sufficient statistics are summed over ranks (one all-reduce per iteration);
+every rank then finalises identical parameters.
+"""
+import abc
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .delta import DELTA_WINDOWS, check_windows
+
+PRECISIONS = {'fp64': 0, 'tc': 1, 0: 0, 1: 1}
+
+
+class ConvergenceWarning(UserWarning):
+    pass
+
+
+def _as_device(x, torch, device):
+    if hasattr(x, 'data_ptr'):
+        t = x.to(device=device, dtype=torch.float64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+    return t.contiguous()
+
+
+class GaussianMixture:
+    covariance_type = 'full'
+
+    def __init__(self, n_components=1, covariance_type='full', tol=1e-3, reg_covar=1e-6,
+                 max_iter=100, n_init=1, init_params='kmeans', weights_init=None,
+                 means_init=None, precisions_init=None, random_state=None, warm_start=False,
+                 verbose=0, verbose_interval=10, precision='fp64', resp_init=None,
+                 process_group=None, device=None):
+        if covariance_type != 'full':
+            raise NotImplementedError("only covariance_type='full' is built "
+                                      '(kwiiyatta/converter/gmm.py:17-18)')
+        if n_init != 1 or warm_start:
+            raise NotImplementedError('n_init > 1 / warm_start are not built')
+        if precisions_init is not None:
+            raise NotImplementedError('precisions_init is not built; pass resp_init or '
+                                      'means_init + weights_init')
+        self.n_components = n_components
+        self.tol = tol
+        self.reg_covar = reg_covar
+        self.max_iter = max_iter
+        self.n_init = n_init
+        self.init_params = init_params
+        self.weights_init = weights_init
+        self.means_init = means_init
+        self.random_state = random_state
+        self.verbose = verbose
+        self.verbose_interval = verbose_interval
+        self.precision = PRECISIONS[precision]
+        self.resp_init = resp_init
+        self.process_group = process_group
+        self.device = device
+        self.iter_callback = None
+
+    # ------------------------------------------------------------------ device plumbing
+    def _alloc(self, torch, n, d, dev):
+        k = self.n_components
+        lib = _lib.lib()
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._weights = torch.empty(k, **f64)
+        self._means = [torch.empty((k, d), **f64), torch.empty((k, d), **f64)]
+        self._cur = 0
+        self._cov = torch.empty((k, d, d), **f64)
+        self._pc = torch.empty((k, d, d), **f64)
+        self._aux = torch.empty((k, d + 2), **f64)
+        self._info = torch.zeros(k, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(lib.kw_gmm_stats_len(k, d), **f64)
+        self._resp = torch.empty((n, k), **f64)
+        self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
+        self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=dev)
+
+    def _estep(self, torch, x):
+        n, d = x.shape
+        rc = _lib.lib().kw_gmm_estep(
+            n, x.data_ptr(), self.n_components, d, self._means[self._cur].data_ptr(),
+            self._pc.data_ptr(), self._aux.data_ptr(), self._resp.data_ptr(),
+            self._stats.data_ptr(), self.precision, self._ws.data_ptr(), self._ws_bytes,
+            _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_estep')
+
+    def _accumulate(self, torch, x, centres):
+        n, d = x.shape
+        rc = _lib.lib().kw_gmm_mstep_accumulate(
+            n, x.data_ptr(), self.n_components, d, self._resp.data_ptr(), centres.data_ptr(),
+            self._stats.data_ptr(), self.precision, self._ws.data_ptr(), self._ws_bytes,
+            _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_mstep_accumulate')
+
+    def _allreduce(self, torch):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            if dist.get_world_size(self.process_group) > 1:
+                dist.all_reduce(self._stats, group=self.process_group)
+
+    def _finalize(self, torch, centres, weight_norm):
+        k, d = centres.shape
+        new = self._means[self._cur ^ 1]
+        rc = _lib.lib().kw_gmm_mstep_finalize(
+            k, d, float(self.reg_covar), weight_norm, self._stats.data_ptr(),
+            centres.data_ptr(), self._weights.data_ptr(), new.data_ptr(),
+            self._cov.data_ptr(), self._pc.data_ptr(), self._aux.data_ptr(),
+            self._info.data_ptr(), _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_mstep_finalize')
+        self._cur ^= 1
+
+    def _check_info(self):
+        info = self._info.cpu().numpy()
+        if info.any():
+            raise ValueError(
+                'Fitting the mixture model failed because some components have ill-defined '
+                'empirical covariance (for instance caused by singleton or collapsed '
+                'samples). Try to decrease the number of components, or increase reg_covar.')
+
+    # ------------------------------------------------------------------ initialisation
+    def _initial_resp(self, torch, x):
+        n, _ = x.shape
+        k = self.n_components
+        if self.resp_init is not None:
+            r = _as_device(self.resp_init, torch, x.device)
+            if tuple(r.shape) != (n, k):
+                raise ValueError(f'resp_init must have shape {(n, k)}, got {tuple(r.shape)}')
+            return r
+        from . import kmeans
+        seed = self.random_state
+        if self.init_params == 'kmeans':
+            labels = kmeans.kmeans_labels(x, k, seed, self.process_group)
+        elif self.init_params == 'random_from_data':
+            labels = kmeans.kmeans_labels(x, k, seed, self.process_group, n_lloyd=0)
+        else:
+            raise NotImplementedError(f'init_params={self.init_params!r} is not built')
+        r = torch.zeros((n, k), dtype=torch.float64, device=x.device)
+        r[torch.arange(n, device=x.device), labels] = 1.0
+        return r
+
+    # ------------------------------------------------------------------ public API
+    def fit(self, X, y=None):
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda' if self.device is None else self.device)
+        x = _as_device(X, torch, dev)
+        if x.dim() != 2:
+            raise ValueError('Expected 2D array')
+        n, d = x.shape
+        k = self.n_components
+        if self.process_group is None and n < k:
+            raise ValueError('Expected n_samples >= n_components '
+                             f'but got n_components = {k}, n_samples = {n}')
+        self._alloc(torch, n, d, dev)
+        if self.verbose:
+            print('Initialization 0')
+        # GaussianMixture._initialize: one M-step from the initial responsibilities
+        self._resp.copy_(self._initial_resp(torch, x))
+        centre = x.sum(dim=0, keepdim=True)
+        count = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and \
+                dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(centre, group=self.process_group)
+            dist.all_reduce(count, group=self.process_group)
+        centres0 = (centre / count).expand(k, d).contiguous()
+        self._stats.zero_()
+        self._stats[-1] = float(n)
+        self._accumulate(torch, x, centres0)
+        self._allreduce(torch)
+        self._finalize(torch, centres0, weight_norm=1)
+        if self.means_init is not None or self.weights_init is not None:
+            self._override_init(torch)
+        self._check_info()
+
+        lower_bound = -np.inf
+        self.lower_bounds_ = []
+        self.converged_ = False
+        n_iter = 0
+        for n_iter in range(1, self.max_iter + 1):
+            prev = lower_bound
+            centres = self._means[self._cur]
+            self._estep(torch, x)
+            self._accumulate(torch, x, centres)
+            self._allreduce(torch)
+            tail = self._stats[-2:].cpu().numpy()
+            lower_bound = float(tail[0] / tail[1])
+            self._finalize(torch, centres, weight_norm=0)
+            self._check_info()
+            self.lower_bounds_.append(lower_bound)
+            change = lower_bound - prev
+            if self.verbose and n_iter % self.verbose_interval == 0:
+                print(f'  Iteration {n_iter}')
+            if self.iter_callback is not None:
+                self.iter_callback(self, n_iter, lower_bound)
+            if abs(change) < self.tol:
+                self.converged_ = True
+                break
+        if self.verbose:
+            print(f'Initialization converged: {self.converged_}')
+        if not self.converged_ and self.max_iter > 0:
+            warnings.warn('Best performing initialization did not converge. Try different '
+                          'init parameters, or increase max_iter, tol, or check for '
+                          'degenerate data.', ConvergenceWarning)
+        self.n_iter_ = n_iter
+        self.lower_bound_ = lower_bound
+        self._publish()
+        self._resp = None
+        self._ws = None
+        return self
+
+    def _override_init(self, torch):
+        """means_init / weights_init replace the initial M-step's values (sklearn
+        _initialize); the precision Cholesky stays that of the estimated covariances."""
+        dev = self._weights.device
+        if self.weights_init is not None:
+            self._weights.copy_(_as_device(self.weights_init, torch, dev))
+        if self.means_init is not None:
+            self._means[self._cur].copy_(_as_device(self.means_init, torch, dev))
+        k, d = self._means[self._cur].shape
+        rc = _lib.lib().kw_gmm_precision_cholesky(
+            k, d, self._weights.data_ptr(), self._means[self._cur].data_ptr(),
+            self._cov.data_ptr(), self._pc.data_ptr(), self._aux.data_ptr(),
+            self._info.data_ptr(), _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_precision_cholesky')
+
+    def _publish(self):
+        self.weights_ = self._weights.cpu().numpy()
+        self.means_ = self._means[self._cur].cpu().numpy()
+        self.covariances_ = self._cov.cpu().numpy()
+        self.precisions_cholesky_ = self._pc.cpu().numpy()
+
+    @property
+    def precisions_(self):
+        pc = self.precisions_cholesky_
+        return np.einsum('kij,klj->kil', pc, pc)
+
+    def set_parameters(self, weights, means, covariances):
+        """Load an existing model (e.g. a fitted sklearn GaussianMixture's attributes)."""
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda' if self.device is None else self.device)
+        means = np.asarray(means, dtype=np.float64)
+        k, d = means.shape
+        self.n_components = k
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._weights = _as_device(weights, torch, dev)
+        self._means = [_as_device(means, torch, dev), torch.empty((k, d), **f64)]
+        self._cur = 0
+        self._cov = _as_device(covariances, torch, dev)
+        self._pc = torch.empty((k, d, d), **f64)
+        self._aux = torch.empty((k, d + 2), **f64)
+        self._info = torch.zeros(k, dtype=torch.int32, device=dev)
+        rc = _lib.lib().kw_gmm_precision_cholesky(
+            k, d, self._weights.data_ptr(), self._means[0].data_ptr(), self._cov.data_ptr(),
+            self._pc.data_ptr(), self._aux.data_ptr(), self._info.data_ptr(),
+            _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_precision_cholesky')
+        self._check_info()
+        self._publish()
+        return self
+
+    def _posterior(self, X):
+        torch = _lib.require_cuda()
+        x = _as_device(X, torch, self._weights.device)
+        n, d = x.shape
+        k = self.n_components
+        lib = _lib.lib()
+        self._resp = torch.empty((n, k), dtype=torch.float64, device=x.device)
+        self._stats = torch.zeros(lib.kw_gmm_stats_len(k, d), dtype=torch.float64,
+                                  device=x.device)
+        self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
+        self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=x.device)
+        self._estep(torch, x)
+        resp, self._resp, self._ws = self._resp, None, None
+        return resp, float(self._stats[-2].item()) / n
+
+    def predict_proba(self, X):
+        return self._posterior(X)[0].cpu().numpy()
+
+    def predict(self, X):
+        return self._posterior(X)[0].argmax(dim=1).cpu().numpy()
+
+    def score(self, X, y=None):
+        return self._posterior(X)[1]
+
+
+class FeatureConverter(abc.ABC):
+    """kwiiyatta/converter/abc/converter.py:4-15."""
+
+    @abc.abstractmethod
+    def _train(self, dataarray, **kwargs):
+        raise NotImplementedError
+
+    def train(self, dataset, keys, **kwargs):
+        from . import dataset as ds
+        self._train(ds.make_dataset_to_array(dataset, keys), **kwargs)
+
+    @abc.abstractmethod
+    def convert(self, feature, **kwargs):
+        raise NotImplementedError
+
+
+class B200GMMFeatureConverter(FeatureConverter):
+    """Drop-in for GMMFeatureConverter (kwiiyatta/converter/gmm.py:8-34)."""
+
+    def __init__(self, components=64, max_iter=100, random_state=None, **kwargs):
+        super().__init__()
+        self.init_gmm(components, max_iter, random_state, **kwargs)
+
+    def init_gmm(self, components, max_iter=100, random_state=None, **kwargs):
+        if 'verbose' not in kwargs:
+            kwargs['verbose'] = 1
+        if 'covariance_type' not in kwargs:
+            kwargs['covariance_type'] = 'full'
+        self.gmm = GaussianMixture(n_components=components, max_iter=max_iter,
+                                   random_state=random_state, **kwargs)
+        self._paramgen = {}
+
+    def _train(self, dataarray, **kwargs):
+        self._paramgen = {}
+        self.gmm.fit(dataarray, **kwargs)
+
+    def _mlpg(self, diff):
+        from .mlpg import MLPG
+        key = bool(diff)
+        if key not in self._paramgen:
+            self._paramgen[key] = MLPG(self.gmm, windows=DELTA_WINDOWS, diff=diff)
+        return self._paramgen[key]
+
+    def convert(self, feature, mlpg=True, diff=False):
+        if not mlpg:
+            raise NotImplementedError(
+                'mlpg=False (per-frame soft-posterior mapping of a model trained without '
+                'deltas, kwiiyatta/converter/gmm.py:30-31) is not built yet')
+        return self._mlpg(diff).transform(feature)
+
+    def convert_many(self, features, diff=False):
+        """Batched ``convert`` over a list of (T_i, 72) arrays."""
+        return self._mlpg(diff).transform_many(features)

@@ -1,0 +1,89 @@
+"""Posterior + MLPG on the B200 (nnmnkwii.baseline.gmm.MLPG as used at
+kwiiyatta/converter/gmm.py:28-34)."""
+import numpy as np
+
+from . import _lib
+from .delta import DELTA_WINDOWS, check_windows
+
+
+class MLPG:
+    """``MLPG(gmm, windows, diff).transform(src)``.  ``gmm`` is anything with ``weights_``,
+    ``means_`` and ``covariances_`` (our GaussianMixture or sklearn's).  The sliced model
+    (marginal precision Cholesky, regression matrices, variance table) is prepared once
+    here; the reference rebuilds it on every convert call (kwiiyatta/converter/gmm.py:32)."""
+
+    def __init__(self, gmm, windows=None, swap=False, diff=False, precision='fp64',
+                 device=None):
+        torch = _lib.require_cuda()
+        if windows is None:
+            windows = DELTA_WINDOWS
+        check_windows(windows)
+        if swap:
+            raise NotImplementedError('swap=True is not built')
+        if getattr(gmm, 'covariance_type', 'full') != 'full':
+            raise AssertionError("covariance_type must be 'full'")
+        self.windows = windows
+        self.diff = bool(diff)
+        self.precision = {'fp64': 0, 'tc': 1, 0: 0, 1: 1}[precision]
+        dev = torch.device('cuda' if device is None else device)
+        means = np.ascontiguousarray(gmm.means_, dtype=np.float64)
+        self.num_mixtures, d = means.shape
+        self.dim_half = d // 2
+        self.static_dim = d // 2 // len(windows)
+        lib = _lib.lib()
+        k, dh = self.num_mixtures, self.dim_half
+        w = torch.from_numpy(np.ascontiguousarray(gmm.weights_, dtype=np.float64)).to(dev)
+        m = torch.from_numpy(means).to(dev)
+        c = torch.from_numpy(np.ascontiguousarray(gmm.covariances_, dtype=np.float64)).to(dev)
+        self._prepared = torch.empty(lib.kw_convert_prepared_len(k, dh), dtype=torch.float64,
+                                     device=dev)
+        info = torch.zeros(k, dtype=torch.int32, device=dev)
+        rc = lib.kw_convert_prepare(k, dh, int(self.diff), w.data_ptr(), m.data_ptr(),
+                                    c.data_ptr(), self._prepared.data_ptr(), info.data_ptr(),
+                                    _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_convert_prepare')
+        if info.cpu().numpy().any():
+            raise np.linalg.LinAlgError('source covariance of some mixture is not positive '
+                                        'definite')
+        self._dev = dev
+
+    def transform_device(self, src_dev, offsets_dev, n_utts, max_frames, return_mix=False):
+        """src_dev (sum T, dim_half) float64 CUDA tensor, offsets int64 (n_utts + 1)."""
+        torch = _lib.require_cuda()
+        lib = _lib.lib()
+        total = src_dev.shape[0]
+        out = torch.empty((total, self.static_dim), dtype=torch.float64, device=src_dev.device)
+        mix = torch.empty(total, dtype=torch.int32, device=src_dev.device) if return_mix else None
+        ws_bytes = lib.kw_convert_workspace_bytes(total, self.num_mixtures, self.dim_half,
+                                                  self.precision)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=src_dev.device)
+        rc = lib.kw_convert_batch(n_utts, offsets_dev.data_ptr(), total, int(max_frames),
+                                  src_dev.data_ptr(), self.num_mixtures, self.dim_half,
+                                  self._prepared.data_ptr(), out.data_ptr(), _lib.ptr(mix),
+                                  self.precision, ws.data_ptr(), ws_bytes,
+                                  _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_convert_batch')
+        return (out, mix) if return_mix else out
+
+    def transform_many(self, features):
+        torch = _lib.require_cuda()
+        feats = [np.ascontiguousarray(f, dtype=np.float64) for f in features]
+        for f in feats:
+            if f.ndim != 2 or f.shape[1] != self.dim_half:
+                raise ValueError(f'expected (T, {self.dim_half}) features, got {f.shape}')
+        lens = np.array([len(f) for f in feats], dtype=np.int64)
+        if lens.sum() == 0:
+            return [np.zeros((0, self.static_dim)) for _ in feats]
+        off = np.concatenate(([0], np.cumsum(lens)))
+        src = torch.from_numpy(np.concatenate(feats)).to(self._dev, non_blocking=True)
+        off_dev = torch.from_numpy(off).to(self._dev, non_blocking=True)
+        out = self.transform_device(src, off_dev, len(feats), int(lens.max())).cpu().numpy()
+        return [out[off[i]:off[i + 1]] for i in range(len(feats))]
+
+    def transform(self, src):
+        src = np.asarray(src, dtype=np.float64)
+        if src.ndim != 2:
+            raise ValueError('MLPG.transform expects a (T, dim) array')
+        if src.shape[1] == self.static_dim:
+            raise NotImplementedError('static-only (no delta) mapping is not built')
+        return self.transform_many([src])[0]

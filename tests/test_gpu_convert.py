@@ -1,0 +1,79 @@
+"""CUDA posterior + MLPG and delta features vs the oracle."""
+import numpy as np
+import pytest
+
+from kwiiyatta_b200 import delta as kdelta
+from kwiiyatta_b200 import synth
+from kwiiyatta_b200.mlpg import MLPG
+from oracle import delta_ref, mlpg_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_ABS = 1e-4   # north_star: MLPG output within 1e-4 absolute on the mcep
+
+
+class _Model:
+    covariance_type = 'full'
+
+    def __init__(self, w, m, c):
+        self.weights_, self.means_, self.covariances_ = w, m, c
+
+
+def _sources(n, frames):
+    return [delta_ref.delta_features(s) for s in
+            (synth.make_source_utterances(n, frames=frames))]
+
+
+@pytest.mark.parametrize('diff', [False, True])
+def test_transform_matches_oracle(cuda, diff):
+    w, m, c = synth.make_joint_gmm(8, seed=1)
+    src = _sources(2, 150)
+    paramgen = MLPG(_Model(w, m, c), diff=diff)
+    for s in src:
+        exp, mix, _, _ = mlpg_ref.transform(s, w, m, c, diff=diff, return_internals=True)
+        got = paramgen.transform(s)
+        assert got.shape == exp.shape == (150, 24)
+        assert np.abs(got - exp).max() <= 1e-8 < TOL_ABS
+
+
+def test_mixture_sequence_and_batching(cuda):
+    import torch
+    w, m, c = synth.make_joint_gmm(16, seed=2)
+    lens = [1, 2, 3, 17, 64, 65, 200]
+    src = [delta_ref.delta_features(synth.make_source_utterances(1, frames=max(t, 2))[0][:t])
+           for t in lens]
+    paramgen = MLPG(_Model(w, m, c))
+    outs = paramgen.transform_many(src)
+    off = np.concatenate(([0], np.cumsum(lens)))
+    _, mix = paramgen.transform_device(torch.from_numpy(np.concatenate(src)).cuda(),
+                                       torch.from_numpy(off).cuda(), len(src), max(lens),
+                                       return_mix=True)
+    mix = mix.cpu().numpy()
+    for i, s in enumerate(src):
+        exp, emix, _, _ = mlpg_ref.transform(s, w, m, c, return_internals=True)
+        assert np.array_equal(mix[off[i]:off[i + 1]], emix)
+        assert np.abs(outs[i] - exp).max() <= 1e-8
+    assert [len(o) for o in paramgen.transform_many([])] == []
+
+
+def test_dense_oracle_agrees(cuda):
+    w, m, c = synth.make_joint_gmm(4, seed=3)
+    s = _sources(1, 40)[0]
+    exp = mlpg_ref.transform(s, w, m, c, banded=False)
+    assert np.abs(MLPG(_Model(w, m, c)).transform(s) - exp).max() <= 1e-8
+
+
+def test_delta_features_exact(cuda):
+    rng = np.random.default_rng(0)
+    for t in (1, 2, 3, 50, 333):
+        x = rng.standard_normal((t, 24))
+        assert np.array_equal(kdelta.delta_features(x), delta_ref.delta_features(x))
+
+
+def test_errors(cuda):
+    w, m, c = synth.make_joint_gmm(2, seed=4)
+    paramgen = MLPG(_Model(w, m, c))
+    with pytest.raises(ValueError):
+        paramgen.transform(np.zeros((5, 71)))
+    with pytest.raises(NotImplementedError):
+        MLPG(_Model(w, m, c), windows=delta_ref.DELTA_WINDOWS[:2])

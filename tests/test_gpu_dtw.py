@@ -1,0 +1,138 @@
+"""CUDA DTW / FastDTW vs the oracle (through the C ABI via kwiiyatta_b200.fastdtw)."""
+import numpy as np
+import pytest
+
+from kwiiyatta_b200 import fastdtw as kfd
+from kwiiyatta_b200 import synth
+from kwiiyatta_b200.align import make_feature
+from oracle import dtw_c, fastdtw_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_pair(rng, tx, ty, f):
+    return rng.standard_normal((tx, f)), rng.standard_normal((ty, f))
+
+
+def _check(pairs, radius, dist=2, exact_cost=True):
+    got = kfd.fastdtw_batch(pairs, radius=radius, dist=dist)
+    for (x, y), (cost, path) in zip(pairs, got):
+        ecost, epath = dtw_c.fastdtw(x, y, radius=radius, dist=dist, use_fma=True)
+        assert path.shape == epath.shape, (x.shape, y.shape, radius)
+        assert np.array_equal(path, epath), (x.shape, y.shape, radius)
+        if exact_cost:
+            assert cost == ecost       # same summation order -> bit-exact
+        else:
+            assert abs(cost - ecost) <= 1e-12 * abs(ecost)
+
+
+@pytest.mark.parametrize('radius', [1, 2, 5, 32])
+def test_fastdtw_random_shapes(cuda, radius):
+    rng = np.random.default_rng(radius)
+    shapes = [(1, 1), (1, 7), (9, 1), (2, 2), (3, 5), (17, 33), (40, 55), (64, 64), (100, 37),
+              (129, 257), (300, 280), (513, 300), (70, 400)]
+    pairs = [_rand_pair(rng, tx, ty, 6) for tx, ty in shapes]
+    _check(pairs, radius)
+
+
+@pytest.mark.parametrize('f', [1, 2, 8, 9, 16, 25, 26, 32])
+def test_fastdtw_feature_dims(cuda, f):
+    rng = np.random.default_rng(100 + f)
+    pairs = [_rand_pair(rng, 90, 120, f), _rand_pair(rng, 300, 260, f)]
+    _check(pairs, 3)
+    _check(pairs, -1)
+
+
+def test_exhaustive_dtw_matches_python_reference(cuda):
+    rng = np.random.default_rng(7)
+    x, y = _rand_pair(rng, 45, 61, 4)
+    cost, path = kfd.dtw(x, y, dist=2)
+    ecost, epath = fastdtw_ref.dtw(x, y, dist=2, dist_mode='seq')
+    assert path == epath
+    assert abs(cost - ecost) <= 1e-13 * ecost
+    # numpy-norm rounding of the local distance (what the package itself evaluates)
+    ncost, npath = fastdtw_ref.dtw(x, y, dist=2, dist_mode='numpy')
+    assert path == npath
+    assert abs(cost - ncost) <= 1e-12 * ncost
+
+
+def test_l1_and_default_dist(cuda):
+    rng = np.random.default_rng(8)
+    pairs = [_rand_pair(rng, 80, 95, 5), _rand_pair(rng, 33, 31, 5)]
+    _check(pairs, 2, dist=1)
+    x, y = pairs[0]
+    cost, path = kfd.fastdtw(x, y, radius=2)            # dist=None -> 1-norm
+    ecost, epath = fastdtw_ref.fastdtw(x, y, radius=2, dist=None)
+    assert path == epath and abs(cost - ecost) <= 1e-12 * ecost
+    # 1-D series
+    a, b = rng.standard_normal(50), rng.standard_normal(64)
+    cost, path = kfd.fastdtw(a, b, radius=1)
+    ecost, epath = fastdtw_ref.fastdtw(a, b, radius=1, dist=None)
+    assert path == epath and abs(cost - ecost) <= 1e-12 * ecost
+
+
+def test_large_radius_equals_exhaustive(cuda):
+    rng = np.random.default_rng(9)
+    x, y = _rand_pair(rng, 150, 170, 8)
+    c1, p1 = kfd.fastdtw(x, y, radius=200, dist=2)
+    c2, p2 = kfd.dtw(x, y, dist=2)
+    assert p1 == p2 and c1 == c2
+
+
+def test_path_properties_and_cost_recomputed(cuda):
+    rng = np.random.default_rng(10)
+    x, y = _rand_pair(rng, 400, 333, 26)
+    cost, path = kfd.fastdtw_batch([(x, y)], radius=32, dist=2)[0]
+    assert tuple(path[0]) == (0, 0) and tuple(path[-1]) == (399, 332)
+    step = np.diff(path, axis=0)
+    assert ((step >= 0) & (step <= 1)).all() and (step.sum(axis=1) >= 1).all()
+    local = np.sqrt(((x[path[:, 0]] - y[path[:, 1]]) ** 2).sum(axis=1))
+    assert abs(local.sum() - cost) <= 1e-10 * cost
+
+
+def test_errors(cuda):
+    rng = np.random.default_rng(11)
+    with pytest.raises(ValueError, match='second dimension of x and y must be the same'):
+        kfd.fastdtw(rng.standard_normal((5, 3)), rng.standard_normal((5, 4)), dist=2)
+    with pytest.raises(ValueError):
+        kfd.fastdtw(rng.standard_normal((5, 3)), rng.standard_normal((5, 3)), dist=-1)
+    with pytest.raises(ValueError):
+        kfd.fastdtw(np.zeros((0, 3)), rng.standard_normal((5, 3)), dist=2)
+    assert kfd.fastdtw_batch([]) == []
+
+
+def test_synthetic_corpus_pairs_radius32(cuda):
+    """Config-1 shaped: 10 padded pairs, 26-dim DTW features, radius 32."""
+    pairs = []
+    for i in range(10):
+        a, b = synth.make_padded_pair(i)
+        pairs.append((make_feature(a, a.fs), make_feature(b, b.fs)))
+    _check(pairs, 32)
+    # cells = sum of window sizes over all levels, as the oracle counts them
+    import torch
+    tx = np.array([len(x) for x, _ in pairs], dtype=np.int32)
+    ty = np.array([len(y) for _, y in pairs], dtype=np.int32)
+    res = kfd.fastdtw_batch_device(torch.from_numpy(np.concatenate([x for x, _ in pairs])).cuda(),
+                                   torch.from_numpy(np.concatenate([y for _, y in pairs])).cuda(),
+                                   tx, ty, radius=32, dist=2)
+    cells = res.cells.cpu().numpy()
+    for p, (x, y) in enumerate(pairs):
+        assert cells[p] == dtw_c.fastdtw(x, y, 32, 2, return_cells=True)[2]
+
+
+def test_ragged_batch_and_order_independence(cuda):
+    rng = np.random.default_rng(12)
+    shapes = [(600, 500), (35, 900), (900, 40), (2, 3), (257, 255)]
+    pairs = [_rand_pair(rng, tx, ty, 26) for tx, ty in shapes]
+    a = kfd.fastdtw_batch(pairs, radius=4, dist=2)
+    b = kfd.fastdtw_batch(pairs[::-1], radius=4, dist=2)[::-1]
+    for (c1, p1), (c2, p2) in zip(a, b):
+        assert c1 == c2 and np.array_equal(p1, p2)
+    _check(pairs, 4)
+
+
+def test_long_unconstrained_pair(cuda):
+    """Config-4 shaped (scaled to what the C oracle finishes in seconds): 1536 x 1536, F=26."""
+    a, b = synth.make_pair(3, length=1536)
+    x, y = make_feature(a, a.fs), make_feature(b, b.fs)
+    _check([(x, y)], -1)

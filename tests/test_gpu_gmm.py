@@ -1,0 +1,104 @@
+"""CUDA EM vs the sklearn-pinned oracle (through the C ABI via kwiiyatta_b200.gmm)."""
+import numpy as np
+import pytest
+
+from kwiiyatta_b200.gmm import GaussianMixture
+from oracle import gmm_ref
+from util import oracle_joint_array, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# north_star: parameters and log-likelihood within 1e-5 relative; the fp64 path is held to a
+# far tighter bound so that regressions show.
+TOL_FP64 = 1e-9
+
+
+def _blobs(rng, n, d, k):
+    centres = rng.standard_normal((k, d)) * 2.0
+    lab = rng.integers(0, k, n)
+    a = rng.standard_normal((k, d, d)) * 0.3 + np.eye(d)
+    return centres[lab] + np.einsum('nij,nj->ni', a[lab], rng.standard_normal((n, d)))
+
+
+def _compare(gm, ref, tol):
+    assert gm.n_iter_ == ref['n_iter']
+    assert gm.converged_ == ref['converged']
+    assert abs(gm.lower_bound_ - ref['lower_bound']) <= tol * abs(ref['lower_bound'])
+    assert np.abs(np.array(gm.lower_bounds_) - np.array(ref['lower_bounds'])).max() \
+        <= tol * abs(ref['lower_bound'])
+    assert rel_err(gm.weights_, ref['weights']) <= tol
+    assert rel_err(gm.means_, ref['means']) <= tol
+    assert rel_err(gm.covariances_, ref['covariances']) <= tol
+    assert rel_err(gm.precisions_cholesky_, ref['precisions_cholesky']) <= tol * 100
+
+
+@pytest.mark.parametrize('n,d,k', [(3000, 12, 4), (2000, 5, 3), (1500, 33, 6), (4097, 48, 5),
+                                   (900, 72, 2), (257, 16, 1)])
+def test_em_matches_sklearn_oracle(cuda, n, d, k):
+    rng = np.random.default_rng(n + d + k)
+    x = _blobs(rng, n, d, k)
+    resp0 = gmm_ref.kmeans_like_resp(x, k, 0)
+    ref = gmm_ref.sklearn_em(x, resp0, max_iter=25)
+    gm = GaussianMixture(n_components=k, max_iter=25, resp_init=resp0).fit(x)
+    _compare(gm, ref, TOL_FP64)
+
+
+def test_em_joint_144_config1(cuda):
+    """Config-1 shaped: 10 aligned synthetic pairs -> (N, 144), 16 mixtures."""
+    x, _ = oracle_joint_array(10)
+    assert x.shape[1] == 144
+    resp0 = gmm_ref.kmeans_like_resp(x, 16, 0)
+    ref = gmm_ref.numpy_em(x, resp0, max_iter=4, tol=0.0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        gm = GaussianMixture(n_components=16, max_iter=4, tol=0.0, resp_init=resp0).fit(x)
+    _compare(gm, ref, TOL_FP64)
+
+
+def test_soft_initial_responsibilities(cuda):
+    rng = np.random.default_rng(5)
+    x = _blobs(rng, 1200, 10, 3)
+    resp0 = rng.uniform(size=(1200, 3))
+    resp0 /= resp0.sum(axis=1, keepdims=True)
+    ref = gmm_ref.sklearn_em(x, resp0, max_iter=10)
+    gm = GaussianMixture(n_components=3, max_iter=10, resp_init=resp0).fit(x)
+    _compare(gm, ref, TOL_FP64)
+
+
+def test_predict_proba_and_score(cuda):
+    rng = np.random.default_rng(6)
+    x = _blobs(rng, 1000, 9, 4)
+    resp0 = gmm_ref.kmeans_like_resp(x, 4, 1)
+    ref = gmm_ref.sklearn_em(x, resp0, max_iter=8)
+    gm = GaussianMixture(n_components=4).set_parameters(ref['weights'], ref['means'],
+                                                        ref['covariances'])
+    assert rel_err(gm.precisions_cholesky_, ref['precisions_cholesky']) <= 1e-10
+    lb, log_resp = gmm_ref.e_step(x, ref['weights'], ref['means'], ref['precisions_cholesky'])
+    assert np.abs(gm.predict_proba(x) - np.exp(log_resp)).max() <= 1e-10
+    assert abs(gm.score(x) - lb) <= 1e-10 * abs(lb)
+    assert np.array_equal(gm.predict(x), log_resp.argmax(axis=1))
+
+
+def test_ill_defined_covariance_raises(cuda):
+    x = np.zeros((50, 4))
+    x[:, 0] = np.arange(50)
+    resp0 = np.zeros((50, 2))
+    resp0[:25, 0] = 1
+    resp0[25:, 1] = 1
+    with pytest.raises(ValueError, match='ill-defined empirical covariance'):
+        GaussianMixture(n_components=2, reg_covar=0.0, resp_init=resp0).fit(x)
+
+
+def test_fewer_samples_than_components(cuda):
+    with pytest.raises(ValueError, match='n_samples >= n_components'):
+        GaussianMixture(n_components=5).fit(np.zeros((3, 2)))
+
+
+def test_kmeans_init_runs_and_is_seeded(cuda):
+    rng = np.random.default_rng(7)
+    x = _blobs(rng, 2000, 8, 4)
+    a = GaussianMixture(n_components=4, random_state=0, max_iter=20).fit(x)
+    b = GaussianMixture(n_components=4, random_state=0, max_iter=20).fit(x)
+    assert np.array_equal(a.means_, b.means_) and a.n_iter_ == b.n_iter_
+    assert np.isfinite(a.lower_bound_)
