@@ -14,6 +14,13 @@ from . import fastdtw as _fastdtw
 pad_silence_fn = None  # set to kwiiyatta.pad_silence (or synth.pad_silence) by the integrator
 
 
+def set_pad_silence(fn):
+    """Install the silence padder used by ``align`` / ``align_even`` when ``pad_silence=True``
+    (``kwiiyatta.pad_silence``, kwiiyatta/vocoder/feature.py:19-41 -- feature-producer code)."""
+    global pad_silence_fn
+    pad_silence_fn = fn
+
+
 def binalize(x, threshold, ceil, floor=0, out=None):
     """kwiiyatta/vocoder/align.py:10-17."""
     if out is None:

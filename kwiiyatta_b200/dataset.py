@@ -3,7 +3,7 @@ with one batched DTW underneath instead of a per-key Python loop."""
 import numpy as np
 
 from . import _lib
-from . import align as _align
+from . import alignment as _align
 from .delta import delta_features_device
 
 

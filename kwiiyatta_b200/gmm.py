@@ -150,7 +150,9 @@ class GaussianMixture:
         return r
 
     # ------------------------------------------------------------------ public API
-    def fit(self, X, y=None):
+    def initialize(self, X):
+        """Move the frames to the device, allocate the model and run the initial M-step
+        (GaussianMixture._initialize).  Returns the device tensor of frames."""
         torch = _lib.require_cuda()
         dev = torch.device('cuda' if self.device is None else self.device)
         x = _as_device(X, torch, dev)
@@ -182,21 +184,17 @@ class GaussianMixture:
         if self.means_init is not None or self.weights_init is not None:
             self._override_init(torch)
         self._check_info()
+        return x
 
+    def fit(self, X, y=None):
+        x = self.initialize(X)
         lower_bound = -np.inf
         self.lower_bounds_ = []
         self.converged_ = False
         n_iter = 0
         for n_iter in range(1, self.max_iter + 1):
             prev = lower_bound
-            centres = self._means[self._cur]
-            self._estep(torch, x)
-            self._accumulate(torch, x, centres)
-            self._allreduce(torch)
-            tail = self._stats[-2:].cpu().numpy()
-            lower_bound = float(tail[0] / tail[1])
-            self._finalize(torch, centres, weight_norm=0)
-            self._check_info()
+            lower_bound = self.em_iteration(x)
             self.lower_bounds_.append(lower_bound)
             change = lower_bound - prev
             if self.verbose and n_iter % self.verbose_interval == 0:
@@ -218,6 +216,19 @@ class GaussianMixture:
         self._resp = None
         self._ws = None
         return self
+
+    def em_iteration(self, x):
+        """One EM iteration on device-resident frames ``x`` (E-step, sufficient statistics,
+        all-reduce across ranks, finalisation).  Returns the lower bound of the E-step."""
+        torch = _lib.require_cuda()
+        centres = self._means[self._cur]
+        self._estep(torch, x)
+        self._accumulate(torch, x, centres)
+        self._allreduce(torch)
+        tail = self._stats[-2:].cpu().numpy()
+        self._finalize(torch, centres, weight_norm=0)
+        self._check_info()
+        return float(tail[0] / tail[1])
 
     def _override_init(self, torch):
         """means_init / weights_init replace the initial M-step's values (sklearn

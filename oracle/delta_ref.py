@@ -22,7 +22,14 @@ def delta_features(x, windows=DELTA_WINDOWS):
     out = np.empty((t, d * len(windows)), dtype=x.dtype)
     for idx, (_, _, window) in enumerate(windows):
         for k in range(d):
-            out[:, d * idx + k] = np.correlate(x[:, k], window, mode='same')
+            if t >= len(window):
+                out[:, d * idx + k] = np.correlate(x[:, k], window, mode='same')
+            else:
+                # shorter than the window: numpy's 'same' would return len(window) values and
+                # the package raises; the zero-padded definition is kept for T < 3
+                h = len(window) // 2
+                out[:, d * idx + k] = np.correlate(np.pad(x[:, k], (h, h)), window,
+                                                   mode='valid')
     return out
 
 

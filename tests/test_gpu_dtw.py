@@ -4,7 +4,7 @@ import pytest
 
 from kwiiyatta_b200 import fastdtw as kfd
 from kwiiyatta_b200 import synth
-from kwiiyatta_b200.align import make_feature
+from kwiiyatta_b200.alignment import make_feature
 from oracle import dtw_c, fastdtw_ref
 
 pytestmark = pytest.mark.gpu

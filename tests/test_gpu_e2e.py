@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 
 import kwiiyatta_b200 as kw
-from kwiiyatta_b200 import align as kalign
 from kwiiyatta_b200 import synth
 from oracle import delta_ref, gmm_ref, mlpg_ref
 from util import oracle_joint_array, rel_err
@@ -17,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_config1_chain(cuda):
     pairs = [synth.make_padded_pair(i) for i in range(10)]
     x_exp, paths = oracle_joint_array(10)
-    kalign.pad_silence_fn = lambda f, n: f   # the synthetic features are already padded
+    kw.set_pad_silence(lambda f, n: f)   # the synthetic features are already padded
     # alignment: identical paths => identical gathered frames
     aligned = kw.align_even_many(pairs, pad_silence=True, pad_len=synth.PAD_LEN)
     for (a, b), (pa, pb), p in zip(aligned, pairs, paths):
