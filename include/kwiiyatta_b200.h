@@ -94,16 +94,21 @@ int kw_delta_features(int n_utts, const int64_t* off_dev, int64_t total_frames, 
  * precision: 0 = fp64 (CUDA-core DFMA), 1 = split-fp16 tcgen05 tensor-core contractions.
  * ------------------------------------------------------------------------------------------ */
 size_t kw_gmm_stats_len(int n_components, int dim);
+/* Length (in doubles) of the responsibilities buffer: component-major, K rows of
+ * round_up(n_frames, 128) frames each; resp[k * npad + n] is r_nk.  Pad frames are never read. */
+size_t kw_gmm_resp_len(int64_t n_frames, int n_components);
 size_t kw_gmm_workspace_bytes(int64_t n_frames, int n_components, int dim, int precision);
 
-/* E-step: resp_dev (n_frames, K) responsibilities, sum of log p(x) accumulated into
+/* E-step: resp_dev (kw_gmm_resp_len doubles, component-major) responsibilities, sum of log p(x) accumulated into
  * stats[K*(1+D+D*D)] and n_frames into the next slot. */
 int kw_gmm_estep(int64_t n_frames, const double* x_dev, int n_components, int dim,
                  const double* means_dev, const double* prec_chol_dev, const double* aux_dev,
                  double* resp_dev, double* stats_dev, int precision,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
-/* M-step sufficient statistics around centres_dev (K, D) from resp_dev. */
+/* M-step sufficient statistics around centres_dev (K, D) from resp_dev.  Frames with
+ * r_nk <= 1e-16 are skipped (their total weight is below the rounding of n_k), so the cost
+ * follows the sparsity of the posterior; the summation order is fixed (bitwise reproducible). */
 int kw_gmm_mstep_accumulate(int64_t n_frames, const double* x_dev, int n_components, int dim,
                             const double* resp_dev, const double* centres_dev,
                             double* stats_dev, int precision,
@@ -131,7 +136,8 @@ int kw_gmm_precision_cholesky(int n_components, int dim, const double* weights_d
  * kw_convert_prepare slices a joint model (optionally with the diff rewrite) into the
  * `prepared` block (device, float64, length kw_convert_prepared_len):
  *   [ px_prec_chol (K,Dh,Dh) | px_aux (K,Dh+2) | A^T (K,Dh,Dh) with A = Syx Sxx^-1 |
- *     offset (K,Dh) = mu_y - A mu_x | var (K,Dh) diagonal conditional variance | scratch (K,Dh,Dh) ]
+ *     offset (K,Dh) = mu_y - A mu_x | var (K,Dh) diagonal conditional variance |
+ *     scratch (K,Dh,Dh) | mu_x (K,Dh) | mu_y (K,Dh) ]
  * kw_convert_batch converts n_utts utterances concatenated in src_dev (sum T, Dh) with int64
  * frame offsets off_dev[n_utts+1]; out_dev is (sum T, static_dim); mix_dev (sum T) int32 receives
  * the hard mixture sequence (may be NULL).

@@ -54,6 +54,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 // gmm.cu internals shared with convert.cu
 int estep_fp64(long long N, const double* X, int K, int D, const double* pc, const double* aux,
                double* resp, double* lse_partial, int mode, int32_t* mix, cudaStream_t st);
+long long resp_pad(long long n);
+void launch_reduce_fixed(const double* in, long long n, double extra, double* out, cudaStream_t st);
+// gmm_tc.cu
+size_t tc_workspace_bytes(long long N, int K, int D);
+int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
+             const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
+             void* workspace, size_t workspace_bytes, cudaStream_t st);
+int mstats_fp64(long long N, const double* X, int K, int D, const double* resp,
+                const double* centres, double* partial, double* stats, double resp_floor,
+                cudaStream_t st);
 int finalize_launch(int K, int D, double reg_covar, int weight_norm, int from_stats,
                     const double* stats, const double* centres, double* weights, double* means,
                     double* cov, double* pc, double* aux, int32_t* info, cudaStream_t st);

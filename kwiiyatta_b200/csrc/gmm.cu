@@ -19,6 +19,7 @@ namespace kw {
 
 constexpr int E_FT = 64;   // frames per CTA tile in the E-step
 constexpr int E_KC = 16;   // contraction chunk
+constexpr double RESP_FLOOR = 1e-16;  // responsibilities at or below this are skipped in the M-step
 constexpr int M_FB = 8;    // frames per smem stage in the M-step (static smem < 48 KB)
 
 __host__ __device__ static inline size_t stats_block(int D) { return 1 + (size_t)D + (size_t)D * D; }
@@ -30,7 +31,7 @@ __host__ __device__ static inline size_t stats_block(int D) { return 1 + (size_t
 // ---------------------------------------------------------------------------------------
 template <int TN>
 __global__ void __launch_bounds__(256)
-gmm_estep_kernel(long long N, const double* __restrict__ X, int K, int D,
+gmm_estep_kernel(long long N, long long Npad, const double* __restrict__ X, int K, int D,
                  const double* __restrict__ prec_chol, const double* __restrict__ aux,
                  double* __restrict__ resp, double* __restrict__ lse_partial, int mode,
                  int32_t* __restrict__ mix_out) {
@@ -40,7 +41,7 @@ gmm_estep_kernel(long long N, const double* __restrict__ X, int K, int D,
     const int XS = Dp + 1;
     double* xs = sm;                 // E_FT * XS
     double* ls = xs + E_FT * XS;     // 2 * E_KC * WT
-    __shared__ double warp_lse[8];
+    __shared__ double frame_lse[E_FT];
 
     const int tid = threadIdx.x;
     const int tr = tid >> 4, tc = tid & 15;
@@ -127,7 +128,7 @@ gmm_estep_kernel(long long N, const double* __restrict__ X, int K, int D,
                 const long long n = n0 + tr + 16 * m;
                 const double wlp = (-0.5 * ((double)D * LOG2PI + q) + cst) + lw;
                 if (mode == 0) {
-                    if (n < N) __stcg(resp + n * K + k, wlp);
+                    if (n < N) __stcg(resp + (size_t)k * Npad + n, wlp);
                 } else if (wlp > best_v[m]) {
                     best_v[m] = wlp;
                     best_k[m] = k;
@@ -146,29 +147,27 @@ gmm_estep_kernel(long long N, const double* __restrict__ X, int K, int D,
         return;
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    double lse_acc = 0.0;
-    for (int f = warp * 8; f < warp * 8 + 8; ++f) {
-        const long long n = n0 + f;
-        if (n >= N) break;
-        double* row = resp + n * K;
-        double mx = -CUDART_INF;
-        for (int k = lane; k < K; k += 32) mx = fmax(mx, __ldcg(row + k));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        double s = 0.0;
-        for (int k = lane; k < K; k += 32) s += exp(__ldcg(row + k) - mx);
-        s = warp_sum(s);
-        const double lse = log(s) + mx;
-        for (int k = lane; k < K; k += 32) row[k] = exp(__ldcg(row + k) - lse);
-        lse_acc += lse;
+    // logsumexp over components, one thread per frame (coalesced over the frame index)
+    if (tid < E_FT) {
+        const long long n = n0 + tid;
+        double lse = 0.0;
+        if (n < N) {
+            double* col = resp + n;
+            double mx = -CUDART_INF;
+            for (int k = 0; k < K; ++k) mx = fmax(mx, __ldcg(col + (size_t)k * Npad));
+            double sum = 0.0;
+            for (int k = 0; k < K; ++k) sum += exp(__ldcg(col + (size_t)k * Npad) - mx);
+            lse = log(sum) + mx;
+            for (int k = 0; k < K; ++k)
+                col[(size_t)k * Npad] = exp(__ldcg(col + (size_t)k * Npad) - lse);
+        }
+        frame_lse[tid] = lse;
     }
-    if (lane == 0) warp_lse[warp] = lse_acc;
     __syncthreads();
     if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += warp_lse[w];
-        lse_partial[blockIdx.x] = s;
+        double t = 0.0;
+        for (int f = 0; f < E_FT; ++f) t += frame_lse[f];
+        lse_partial[blockIdx.x] = t;
     }
 }
 
@@ -190,60 +189,40 @@ __global__ void reduce_fixed_kernel(const double* __restrict__ in, long long n, 
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// M-step, first moments: grid (n_chunks, ceil(K/8)); thread d < D owns column d for 8
-// components, thread d == D accumulates n_k.  partial[(chunk*K + k)*(D+1) + {0: n, 1+d: m}].
-// ---------------------------------------------------------------------------------------
-__global__ void gmm_m1_kernel(long long N, const double* __restrict__ X, int K, int D,
-                              const double* __restrict__ resp, const double* __restrict__ centres,
-                              double* __restrict__ partial, long long frames_per_chunk) {
-    const int d = threadIdx.x;
-    const int k0 = blockIdx.y * 8;
-    const long long n_begin = (long long)blockIdx.x * frames_per_chunk;
-    const long long n_end = min(N, n_begin + frames_per_chunk);
-    double acc[8], cc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        acc[q] = 0.0;
-        cc[q] = (d < D && k0 + q < K) ? centres[(size_t)(k0 + q) * D + d] : 0.0;
-    }
-    if (d <= D) {
-        for (long long n = n_begin; n < n_end; ++n) {
-            const double x = (d < D) ? X[n * D + d] : 0.0;
-            const double* r = resp + n * K + k0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const double rv = (k0 + q < K) ? r[q] : 0.0;
-                acc[q] = (d < D) ? fma(rv, x - cc[q], acc[q]) : acc[q] + rv;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (k0 + q < K) {
-                double* p = partial + ((size_t)blockIdx.x * K + (k0 + q)) * (D + 1);
-                p[(d < D) ? 1 + d : 0] = acc[q];
-            }
-        }
-    }
+void launch_reduce_fixed(const double* in, long long n, double extra, double* out,
+                         cudaStream_t st) {
+    reduce_fixed_kernel<<<1, 256, 0, st>>>(in, n, extra, out);
 }
 
 // ---------------------------------------------------------------------------------------
-// M-step, second moments: grid (K, n_chunks, n_tile_pairs).  CTA = one W x W output tile
+// M-step sufficient statistics: grid (K, n_chunks, n_tile_pairs).  CTA = one W x W output tile
 // (W = 16*TM) of S_k over one chunk of frames; 256 threads, TM x TM accumulators each.
+// Frames whose responsibility for this component is <= resp_floor are skipped: the chunk is
+// compacted in frame order (deterministic block scan), so the summation order is fixed and
+// the work follows the posterior's sparsity.  The diagonal tile CTAs also accumulate
+// m_k = sum r (x - c_k) for their rows; tile 0 accumulates n_k = sum r.
+// partial layout: [chunk][k][1 + D + D*D].
 // ---------------------------------------------------------------------------------------
+constexpr int M_SEG = 256;
+
 template <int TM>
 __global__ void __launch_bounds__(256)
-gmm_m2_kernel(long long N, const double* __restrict__ X, int K, int D,
-              const double* __restrict__ resp, const double* __restrict__ centres,
-              double* __restrict__ partial, long long frames_per_chunk, int n_tiles) {
+gmm_mstats_kernel(long long N, long long Npad, const double* __restrict__ X, int K, int D,
+                  const double* __restrict__ respT, const double* __restrict__ centres,
+                  double* __restrict__ partial, long long frames_per_chunk, int n_tiles,
+                  double resp_floor) {
     constexpr int W = 16 * TM;
     constexpr int WS = W + 1;
+    constexpr int QCAP = M_SEG + M_FB;
     __shared__ double sa[2][M_FB * WS];
     __shared__ double sb[2][M_FB * WS];
+    __shared__ int q_n[QCAP];
+    __shared__ double q_r[QCAP];
+    __shared__ int warp_cnt[8];
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
+    const int lane = tid & 31, warp = tid >> 5;
     const int k = blockIdx.x;
-    // tile pair (bi <= bj) from the linear index
     int bi = 0, bj = 0;
     {
         int t = blockIdx.z;
@@ -257,24 +236,29 @@ gmm_m2_kernel(long long N, const double* __restrict__ X, int K, int D,
     const long long n_begin = (long long)blockIdx.y * frames_per_chunk;
     const long long n_end = min(N, n_begin + frames_per_chunk);
     const double* ck = centres + (size_t)k * D;
+    const double* rk = respT + (size_t)k * Npad;
 
     double acc[TM][TM];
+    double macc[TM];
+    double nacc = 0.0;
 #pragma unroll
-    for (int a = 0; a < TM; ++a)
+    for (int a = 0; a < TM; ++a) {
+        macc[a] = 0.0;
 #pragma unroll
         for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+    }
 
     constexpr int PER = (M_FB * W + 255) / 256;
     double pa[PER], pb[PER];
-    auto prefetch = [&](long long nb) {
+    auto prefetch = [&](int q0) {   // batch of M_FB queue entries starting at q0
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const int e = tid + 256 * q;
             const int f = e / W, c = e - f * W;
-            const long long n = nb + f;
             double va = 0.0, vb = 0.0;
-            if (e < M_FB * W && n < n_end) {
-                const double r = resp[n * K + k];
+            if (e < M_FB * W) {
+                const double r = q_r[q0 + f];
+                const long long n = n_begin + q_n[q0 + f];
                 const int ci = bi * W + c, cj = bj * W + c;
                 const double xi = (ci < D) ? X[n * D + ci] - ck[ci] : 0.0;
                 va = r * xi;
@@ -295,35 +279,90 @@ gmm_m2_kernel(long long N, const double* __restrict__ X, int K, int D,
             }
         }
     };
-    if (n_begin < n_end) {
-        prefetch(n_begin);
+    // consume n_batches full batches from the front of the queue
+    auto process = [&](int n_batches) {
+        if (n_batches <= 0) return;
+        prefetch(0);
         stash(0);
         __syncthreads();
         int buf = 0;
-        for (long long nb = n_begin; nb < n_end; nb += M_FB) {
-            const bool more = nb + M_FB < n_end;
-            if (more) prefetch(nb + M_FB);
+        for (int b = 0; b < n_batches; ++b) {
+            const bool more = b + 1 < n_batches;
+            if (more) prefetch((b + 1) * M_FB);
             const double* a_base = sa[buf] + ty * TM;
             const double* b_base = sb[buf] + tx * TM;
 #pragma unroll
             for (int f = 0; f < M_FB; ++f) {
-                double a[TM], b[TM];
+                double a[TM], bb[TM];
 #pragma unroll
                 for (int q = 0; q < TM; ++q) a[q] = a_base[f * WS + q];
 #pragma unroll
-                for (int q = 0; q < TM; ++q) b[q] = b_base[f * WS + q];
+                for (int q = 0; q < TM; ++q) bb[q] = b_base[f * WS + q];
 #pragma unroll
                 for (int p = 0; p < TM; ++p)
 #pragma unroll
-                    for (int q = 0; q < TM; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+                    for (int q = 0; q < TM; ++q) acc[p][q] = fma(a[p], bb[q], acc[p][q]);
+                if (same && tx == 0) {
+#pragma unroll
+                    for (int p = 0; p < TM; ++p) macc[p] += a[p];
+                }
+                if (tid == 0) nacc += q_r[b * M_FB + f];
             }
             if (more) stash(buf ^ 1);
             __syncthreads();
             buf ^= 1;
         }
+    };
+
+    int qcount = 0;
+    for (long long seg = n_begin; seg < n_end; seg += M_SEG) {
+        const long long n = seg + tid;
+        const double r = (n < n_end) ? rk[n] : 0.0;
+        const bool keep = r > resp_floor;
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int c = warp_cnt[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        if (keep) {
+            const int pos = qcount + before + __popc(ballot & ((1u << lane) - 1u));
+            q_n[pos] = (int)(n - n_begin);
+            q_r[pos] = r;
+        }
+        qcount += total;
+        __syncthreads();
+        const int nb = qcount / M_FB;
+        process(nb);
+        const int rem = qcount - nb * M_FB;
+        int tn = 0;
+        double tr = 0.0;
+        if (nb > 0 && tid < rem) { tn = q_n[nb * M_FB + tid]; tr = q_r[nb * M_FB + tid]; }
+        __syncthreads();
+        if (nb > 0 && tid < rem) { q_n[tid] = tn; q_r[tid] = tr; }
+        qcount = rem;
+        __syncthreads();
     }
-    // partial layout: [chunk][k][D][D]
-    double* out = partial + ((size_t)blockIdx.y * K + k) * (size_t)D * D;
+    if (qcount > 0) {
+        if (tid >= qcount && tid < M_FB) { q_n[tid] = 0; q_r[tid] = 0.0; }
+        __syncthreads();
+        process(1);
+    }
+
+    double* out = partial + ((size_t)blockIdx.y * K + k) * stats_block(D);
+    if (blockIdx.z == 0 && tid == 0) out[0] = nacc;
+    if (same && tx == 0) {
+#pragma unroll
+        for (int p = 0; p < TM; ++p) {
+            const int i = bi * W + ty * TM + p;
+            if (i < D) out[1 + i] = macc[p];
+        }
+    }
+    double* so = out + 1 + D;
 #pragma unroll
     for (int p = 0; p < TM; ++p) {
         const int i = bi * W + ty * TM + p;
@@ -332,29 +371,22 @@ gmm_m2_kernel(long long N, const double* __restrict__ X, int K, int D,
         for (int q = 0; q < TM; ++q) {
             const int j = bj * W + tx * TM + q;
             if (j >= D) continue;
-            out[(size_t)i * D + j] = acc[p][q];
-            if (!same) out[(size_t)j * D + i] = acc[p][q];
+            so[(size_t)i * D + j] = acc[p][q];
+            if (!same) so[(size_t)j * D + i] = acc[p][q];
         }
     }
 }
 
-// stats[k] = sum over chunks (fixed order) of the first- and second-moment partials.
-__global__ void gmm_reduce_partials_kernel(int K, int D, int chunks1, const double* __restrict__ p1,
-                                           int chunks2, const double* __restrict__ p2,
+// stats[k] = sum over chunks (fixed order) of the partials.
+__global__ void gmm_reduce_partials_kernel(int K, int D, int chunks,
+                                           const double* __restrict__ partial,
                                            double* __restrict__ stats) {
     const size_t sb = stats_block(D);
     const size_t total = (size_t)K * sb;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(e / sb);
-        const size_t r = e - (size_t)k * sb;
         double s = 0.0;
-        if (r < (size_t)D + 1) {
-            for (int c = 0; c < chunks1; ++c) s += p1[((size_t)c * K + k) * (D + 1) + r];
-        } else {
-            const size_t ij = r - (D + 1);
-            for (int c = 0; c < chunks2; ++c) s += p2[((size_t)c * K + k) * (size_t)D * D + ij];
-        }
+        for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * total + e];
         stats[e] = s;
     }
 }
@@ -482,12 +514,12 @@ static int m_chunks(int K) {
     if (c > 64) c = 64;
     return c;
 }
-constexpr int M1_CHUNKS = 296;
+
+long long resp_pad(long long n) { return (n + 127) / 128 * 128; }
 
 struct GmmWorkspace {
     double* lse_partial;
-    double* p1;
-    double* p2;
+    double* partial;
     size_t bytes;
 };
 
@@ -495,8 +527,7 @@ static GmmWorkspace carve_gmm(long long N, int K, int D, void* base) {
     Carver c(base);
     GmmWorkspace w;
     w.lse_partial = c.take<double>((size_t)((N + E_FT - 1) / E_FT) + 1);
-    w.p1 = c.take<double>((size_t)M1_CHUNKS * K * (D + 1));
-    w.p2 = c.take<double>((size_t)m_chunks(K) * K * (size_t)D * D);
+    w.partial = c.take<double>((size_t)m_chunks(K) * K * stats_block(D));
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -511,7 +542,8 @@ static int launch_estep(long long N, const double* X, int K, int D, const double
     KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     const long long grid = (N + E_FT - 1) / E_FT;
-    kern<<<(unsigned)grid, 256, smem, st>>>(N, X, K, D, pc, aux, resp, lse_partial, mode, mix);
+    kern<<<(unsigned)grid, 256, smem, st>>>(N, resp_pad(N), X, K, D, pc, aux, resp, lse_partial,
+                                            mode, mix);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
@@ -528,14 +560,32 @@ int estep_fp64(long long N, const double* X, int K, int D, const double* pc, con
 }
 
 template <int TM>
-static int launch_m2(long long N, const double* X, int K, int D, const double* resp,
-                     const double* centres, double* p2, int chunks, cudaStream_t st) {
+static int launch_mstats(long long N, const double* X, int K, int D, const double* resp,
+                         const double* centres, double* partial, int chunks, double resp_floor,
+                         cudaStream_t st) {
     const int W = 16 * TM;
     const int n_tiles = (D + W - 1) / W;
     const int n_pairs = n_tiles * (n_tiles + 1) / 2;
-    const long long fpc = (N + chunks - 1) / chunks;
-    gmm_m2_kernel<TM><<<dim3(K, chunks, n_pairs), 256, 0, st>>>(N, X, K, D, resp, centres, p2,
-                                                               fpc, n_tiles);
+    long long fpc = (N + chunks - 1) / chunks;
+    fpc = (fpc + M_SEG - 1) / M_SEG * M_SEG;
+    gmm_mstats_kernel<TM><<<dim3(K, chunks, n_pairs), 256, 0, st>>>(
+        N, resp_pad(N), X, K, D, resp, centres, partial, fpc, n_tiles, resp_floor);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+int mstats_fp64(long long N, const double* X, int K, int D, const double* resp,
+                const double* centres, double* partial, double* stats, double resp_floor,
+                cudaStream_t st) {
+    const int chunks = m_chunks(K);
+    int rc;
+    if (D <= 16) rc = launch_mstats<1>(N, X, K, D, resp, centres, partial, chunks, resp_floor, st);
+    else if (D <= 32) rc = launch_mstats<2>(N, X, K, D, resp, centres, partial, chunks, resp_floor, st);
+    else if (D <= 48) rc = launch_mstats<3>(N, X, K, D, resp, centres, partial, chunks, resp_floor, st);
+    else if (D <= 80) rc = launch_mstats<5>(N, X, K, D, resp, centres, partial, chunks, resp_floor, st);
+    else rc = launch_mstats<9>(N, X, K, D, resp, centres, partial, chunks, resp_floor, st);
+    if (rc != KW_OK) return rc;
+    gmm_reduce_partials_kernel<<<296, 256, 0, st>>>(K, D, chunks, partial, stats);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
@@ -562,33 +612,37 @@ using namespace kw;
 
 extern "C" size_t kw_gmm_stats_len(int K, int D) { return (size_t)K * stats_block(D) + 2; }
 
+extern "C" size_t kw_gmm_resp_len(int64_t n_frames, int K) { return (size_t)K * (size_t)resp_pad(n_frames); }
+
 extern "C" size_t kw_gmm_workspace_bytes(int64_t n_frames, int K, int D, int precision) {
-    (void)precision;
-    return carve_gmm(n_frames, K, D, nullptr).bytes;
+    size_t b = carve_gmm(n_frames, K, D, nullptr).bytes;
+    if (precision == 1) b += tc_workspace_bytes(n_frames, K, D);
+    return b;
 }
 
 extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const double* means_dev,
                             const double* prec_chol_dev, const double* aux_dev, double* resp_dev,
                             double* stats_dev, int precision, void* workspace_dev,
                             size_t workspace_bytes, void* stream) {
-    (void)means_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_estep: N, K, D must be positive");
-    if (precision != 0) {
-        set_error("GMM precision %d is not built (0 = fp64)", precision);
-        return KW_ERR_UNSUPPORTED;
-    }
+    KW_REQUIRE(precision == 0 || precision == 1, "GMM precision must be 0 (fp64) or 1 (tensor)");
     GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
     if (w.bytes > workspace_bytes) {
         set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return KW_ERR_WORKSPACE;
     }
+    double* tail = stats_dev + (size_t)K * stats_block(D);
+    if (precision == 1) {
+        return estep_tc(N, x_dev, K, D, means_dev, prec_chol_dev, aux_dev, resp_dev, tail, 0,
+                        nullptr, static_cast<char*>(workspace_dev) + w.bytes,
+                        workspace_bytes - w.bytes, st);
+    }
     int rc = estep_fp64(N, x_dev, K, D, prec_chol_dev, aux_dev, resp_dev, w.lse_partial, 0,
                         nullptr, st);
     if (rc != KW_OK) return rc;
     const long long nblk = (N + E_FT - 1) / E_FT;
-    reduce_fixed_kernel<<<1, 256, 0, st>>>(w.lse_partial, nblk, (double)N,
-                                           stats_dev + (size_t)K * stats_block(D));
+    launch_reduce_fixed(w.lse_partial, nblk, (double)N, tail, st);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
@@ -599,10 +653,7 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
                                        size_t workspace_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_mstep_accumulate: N, K, D must be positive");
-    if (precision != 0) {
-        set_error("GMM precision %d is not built (0 = fp64)", precision);
-        return KW_ERR_UNSUPPORTED;
-    }
+    (void)precision;  // the statistics are accumulated in fp64 in both modes
     if (D + 1 > 1024) {
         set_error("dim %d too large", D);
         return KW_ERR_UNSUPPORTED;
@@ -612,23 +663,7 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
         set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return KW_ERR_WORKSPACE;
     }
-    const long long fpc1 = (N + M1_CHUNKS - 1) / M1_CHUNKS;
-    const int bd = (D + 1 + 31) / 32 * 32;
-    gmm_m1_kernel<<<dim3(M1_CHUNKS, (K + 7) / 8), bd, 0, st>>>(N, x_dev, K, D, resp_dev,
-                                                              centres_dev, w.p1, fpc1);
-    KW_CUDA_CHECK(cudaGetLastError());
-    const int chunks = m_chunks(K);
-    int rc;
-    if (D <= 16) rc = launch_m2<1>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
-    else if (D <= 32) rc = launch_m2<2>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
-    else if (D <= 48) rc = launch_m2<3>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
-    else if (D <= 80) rc = launch_m2<5>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
-    else rc = launch_m2<9>(N, x_dev, K, D, resp_dev, centres_dev, w.p2, chunks, st);
-    if (rc != KW_OK) return rc;
-    gmm_reduce_partials_kernel<<<296, 256, 0, st>>>(K, D, M1_CHUNKS, w.p1, chunks, w.p2,
-                                                    stats_dev);
-    KW_CUDA_CHECK(cudaGetLastError());
-    return KW_OK;
+    return mstats_fp64(N, x_dev, K, D, resp_dev, centres_dev, w.partial, stats_dev, RESP_FLOOR, st);
 }
 
 extern "C" int kw_gmm_mstep_finalize(int K, int D, double reg_covar, int weight_norm,

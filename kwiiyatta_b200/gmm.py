@@ -82,7 +82,8 @@ class GaussianMixture:
         self._aux = torch.empty((k, d + 2), **f64)
         self._info = torch.zeros(k, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(lib.kw_gmm_stats_len(k, d), **f64)
-        self._resp = torch.empty((n, k), **f64)
+        self._npad = lib.kw_gmm_resp_len(n, k) // k
+        self._resp = torch.zeros((k, self._npad), **f64)   # component-major
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=dev)
 
@@ -136,7 +137,7 @@ class GaussianMixture:
             r = _as_device(self.resp_init, torch, x.device)
             if tuple(r.shape) != (n, k):
                 raise ValueError(f'resp_init must have shape {(n, k)}, got {tuple(r.shape)}')
-            return r
+            return r.t()
         from . import kmeans
         seed = self.random_state
         if self.init_params == 'kmeans':
@@ -145,8 +146,8 @@ class GaussianMixture:
             labels = kmeans.kmeans_labels(x, k, seed, self.process_group, n_lloyd=0)
         else:
             raise NotImplementedError(f'init_params={self.init_params!r} is not built')
-        r = torch.zeros((n, k), dtype=torch.float64, device=x.device)
-        r[torch.arange(n, device=x.device), labels] = 1.0
+        r = torch.zeros((k, n), dtype=torch.float64, device=x.device)
+        r[labels, torch.arange(n, device=x.device)] = 1.0
         return r
 
     # ------------------------------------------------------------------ public API
@@ -167,7 +168,7 @@ class GaussianMixture:
         if self.verbose:
             print('Initialization 0')
         # GaussianMixture._initialize: one M-step from the initial responsibilities
-        self._resp.copy_(self._initial_resp(torch, x))
+        self._resp[:, :n].copy_(self._initial_resp(torch, x))
         centre = x.sum(dim=0, keepdim=True)
         count = torch.tensor([float(n)], dtype=torch.float64, device=dev)
         import torch.distributed as dist
@@ -286,13 +287,14 @@ class GaussianMixture:
         n, d = x.shape
         k = self.n_components
         lib = _lib.lib()
-        self._resp = torch.empty((n, k), dtype=torch.float64, device=x.device)
+        self._npad = lib.kw_gmm_resp_len(n, k) // k
+        self._resp = torch.empty((k, self._npad), dtype=torch.float64, device=x.device)
         self._stats = torch.zeros(lib.kw_gmm_stats_len(k, d), dtype=torch.float64,
                                   device=x.device)
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=x.device)
         self._estep(torch, x)
-        resp, self._resp, self._ws = self._resp, None, None
+        resp, self._resp, self._ws = self._resp[:, :n].t(), None, None
         return resp, float(self._stats[-2].item()) / n
 
     def predict_proba(self, X):

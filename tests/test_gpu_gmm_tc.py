@@ -1,0 +1,73 @@
+"""Tensor-core (split-fp16 tcgen05) E-step vs the fp64 oracle.
+
+north_star tolerance: GMM parameters and log-likelihood within 1e-5 relative."""
+import warnings
+
+import numpy as np
+import pytest
+
+from kwiiyatta_b200.gmm import GaussianMixture
+from oracle import gmm_ref
+from util import oracle_joint_array, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _blobs(rng, n, d, k):
+    centres = rng.standard_normal((k, d)) * 2.0
+    lab = rng.integers(0, k, n)
+    a = rng.standard_normal((k, d, d)) * 0.3 + np.eye(d)
+    return centres[lab] + np.einsum('nij,nj->ni', a[lab], rng.standard_normal((n, d)))
+
+
+@pytest.mark.parametrize('n,d,k', [(1000, 16, 3), (1300, 9, 4), (4097, 48, 5), (777, 72, 6),
+                                   (2000, 144, 4)])
+def test_estep_log_prob_and_posteriors(cuda, n, d, k):
+    rng = np.random.default_rng(n + d)
+    x = _blobs(rng, n, d, k)
+    resp0 = gmm_ref.kmeans_like_resp(x, k, 0)
+    ref = gmm_ref.numpy_em(x, resp0, max_iter=3, tol=0.0)
+    gm = GaussianMixture(n_components=k, precision='tc').set_parameters(
+        ref['weights'], ref['means'], ref['covariances'])
+    lb, log_resp = gmm_ref.e_step(x, ref['weights'], ref['means'], ref['precisions_cholesky'])
+    got = gm.predict_proba(x)
+    assert np.abs(got - np.exp(log_resp)).max() <= 2e-3          # per-frame posterior
+    assert abs(gm.score(x) - lb) <= TOL * abs(lb)                # mean log-likelihood
+    # per-frame weighted log-probabilities are good to ~1e-4 absolute
+    wlp = gmm_ref.weighted_log_prob(x, ref['weights'], ref['means'], ref['precisions_cholesky'])
+    top = wlp.argmax(1)
+    agree = (got.argmax(1) == top).mean()
+    assert agree >= 0.999
+
+
+@pytest.mark.parametrize('n,d,k', [(3000, 12, 4), (4097, 48, 5)])
+def test_fit_matches_oracle_within_north_star_tolerance(cuda, n, d, k):
+    rng = np.random.default_rng(n * 3 + d)
+    x = _blobs(rng, n, d, k)
+    resp0 = gmm_ref.kmeans_like_resp(x, k, 0)
+    ref = gmm_ref.sklearn_em(x, resp0, max_iter=8, tol=0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        gm = GaussianMixture(n_components=k, max_iter=8, tol=0.0, resp_init=resp0,
+                             precision='tc').fit(x)
+    assert abs(gm.lower_bound_ - ref['lower_bound']) <= TOL * abs(ref['lower_bound'])
+    assert np.abs(np.array(gm.lower_bounds_) - np.array(ref['lower_bounds'])).max() \
+        <= TOL * abs(ref['lower_bound'])
+    assert rel_err(gm.weights_, ref['weights']) <= TOL
+    assert rel_err(gm.means_, ref['means']) <= TOL
+    assert rel_err(gm.covariances_, ref['covariances']) <= TOL
+
+
+def test_fit_joint_144_config1(cuda):
+    x, _ = oracle_joint_array(10)
+    resp0 = gmm_ref.kmeans_like_resp(x, 16, 0)
+    ref = gmm_ref.numpy_em(x, resp0, max_iter=4, tol=0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        gm = GaussianMixture(n_components=16, max_iter=4, tol=0.0, resp_init=resp0,
+                             precision='tc').fit(x)
+    assert abs(gm.lower_bound_ - ref['lower_bound']) <= TOL * abs(ref['lower_bound'])
+    assert rel_err(gm.means_, ref['means']) <= TOL
+    assert rel_err(gm.covariances_, ref['covariances']) <= TOL
+    assert rel_err(gm.weights_, ref['weights']) <= TOL
