@@ -268,8 +268,9 @@ extern "C" int kw_convert_prepare(int K, int Dh, int diff, const double* weights
 }
 
 extern "C" size_t kw_convert_workspace_bytes(int64_t total_frames, int K, int Dh, int precision) {
-    (void)K; (void)precision;
-    return carve_convert(total_frames, Dh, Dh / 3, nullptr).bytes;
+    size_t b = carve_convert(total_frames, Dh, Dh / 3, nullptr).bytes;
+    if (precision == 1) b += tc_workspace_bytes(total_frames, K, Dh);
+    return b;
 }
 
 extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t total, int max_frames,
@@ -281,10 +282,7 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
     if (n_utts == 0 || total == 0) return KW_OK;
     KW_REQUIRE(n_utts > 0 && total > 0 && K > 0, "kw_convert_batch: bad sizes");
     KW_REQUIRE(Dh % 3 == 0, "dim_half %d is not static+delta+delta2 (multiple of 3)", Dh);
-    if (precision != 0) {
-        set_error("convert precision %d is not built (0 = fp64)", precision);
-        return KW_ERR_UNSUPPORTED;
-    }
+    KW_REQUIRE(precision == 0 || precision == 1, "convert precision must be 0 or 1");
     const int sd = Dh / 3;
     ConvertWorkspace w = carve_convert(total, Dh, sd, workspace_dev);
     if (w.bytes > workspace_bytes) {
@@ -293,7 +291,13 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
         return KW_ERR_WORKSPACE;
     }
     PreparedView v = view_prepared(const_cast<double*>(prepared_dev), K, Dh);
-    int rc = estep_fp64(total, src_dev, K, Dh, v.px_prec_chol, v.px_aux, nullptr, nullptr, 1,
+    int rc;
+    if (precision == 1)
+        rc = estep_tc(total, src_dev, K, Dh, v.src_means, v.px_prec_chol, v.px_aux, nullptr,
+                      nullptr, 1, w.mix, static_cast<char*>(workspace_dev) + w.bytes,
+                      workspace_bytes - w.bytes, st);
+    else
+        rc = estep_fp64(total, src_dev, K, Dh, v.px_prec_chol, v.px_aux, nullptr, nullptr, 1,
                         w.mix, st);
     if (rc != KW_OK) return rc;
     {

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(192, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
                 const float* __restrict__ sc, const double* __restrict__ cst,
-                double* __restrict__ wlpT) {
+                double* __restrict__ wlpT, int mode, int32_t* __restrict__ mix,
+                int32_t* __restrict__ cand, double near_tie) {
     extern __shared__ __align__(128) unsigned char smem[];
     const EstepSmem L = estep_smem(DP);
     __half* a_hi = reinterpret_cast<__half*>(smem + L.a);
@@ -406,6 +407,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long n = (long long)tile * TILE_M + row;
+            double v1 = -CUDART_INF, v2 = -CUDART_INF;
+            int k1 = 0, k2 = -1;
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                 float* sk = scl + (size_t)s * 2 * DP;
@@ -433,7 +436,17 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
                 const double wlp = (-0.5 * ((double)D * LOG2PI + q) + cst_s[s * 2]) + cst_s[s * 2 + 1];
-                if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
+                if (mode == 0) {
+                    if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
+                } else if (wlp > v1) {
+                    v2 = v1; k2 = k1; v1 = wlp; k1 = k;
+                } else if (wlp > v2) {
+                    v2 = wlp; k2 = k;
+                }
+            }
+            if (mode == 1 && n < N) {
+                mix[n] = k1;
+                cand[n] = (K > 1 && v1 - v2 < near_tie) ? k2 : -1;   // runner-up to re-check in fp64
             }
         }
     }
@@ -477,6 +490,43 @@ __global__ void lse_kernel(long long N, long long Npad, int K, double* __restric
     }
 }
 
+// Hard-assignment near-ties: frames whose two best components are closer than the tensor-core
+// error budget are re-evaluated for those two components in FP64 (one warp per frame), so the
+// mixture sequence equals the FP64 argmax.
+__global__ void refine_argmax_kernel(long long N, int D, const double* __restrict__ X,
+                                     const double* __restrict__ prec_chol,
+                                     const double* __restrict__ aux, int32_t* __restrict__ mix,
+                                     const int32_t* __restrict__ cand) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double LOG2PI = 1.8378770664093453;
+    for (long long n = warp; n < N; n += n_warps) {
+        const int kb = cand[n];
+        if (kb < 0) continue;
+        const int ka = mix[n];
+        double w[2];
+        for (int c = 0; c < 2; ++c) {
+            const int k = c == 0 ? ka : kb;
+            const double* Lk = prec_chol + (size_t)k * D * D;
+            const double* ak = aux + (size_t)k * (D + 2);
+            double q = 0.0;
+            for (int j = lane; j < D; j += 32) {
+                double y = 0.0;
+                for (int d = 0; d <= j; ++d) y = fma(X[n * D + d], Lk[(size_t)d * D + j], y);
+                y -= ak[j];
+                q = fma(y, y, q);
+            }
+            q = warp_sum(q);
+            w[c] = (-0.5 * ((double)D * LOG2PI + q) + ak[D]) + ak[D + 1];
+        }
+        if (lane == 0) {
+            const bool take_b = (w[1] > w[0]) || (w[1] == w[0] && kb < ka);
+            if (take_b) mix[n] = kb;
+        }
+    }
+}
+
 }  // namespace tc
 
 constexpr int TC_STAT_CHUNKS = 296;
@@ -489,6 +539,7 @@ struct TcWorkspace {
     float* sc;
     double* cst;
     double* lse_partial;
+    int32_t* cand;
     size_t bytes;
 };
 
@@ -506,6 +557,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.sc = c.take<float>((size_t)K * 2 * DP);
     w.cst = c.take<double>(2 * (size_t)K);
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
+    w.cand = c.take<int32_t>((size_t)N);
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -551,8 +603,14 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     while (cols < 2u * DP) cols <<= 1;
     const int grid = (int)std::min<long long>(n_tiles, sms);
     tc::estep_tc_kernel<<<grid, 192, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
-                                                    w.bt, w.sc, w.cst, resp);
+                                                    w.bt, w.sc, w.cst, resp, mode, mix, w.cand,
+                                                    0.05);
     KW_CUDA_CHECK(cudaGetLastError());
+    if (mode == 1) {
+        tc::refine_argmax_kernel<<<sms * 4, 256, 0, st>>>(N, D, X, pc, aux, mix, w.cand);
+        KW_CUDA_CHECK(cudaGetLastError());
+        return KW_OK;
+    }
     const unsigned lgrid = (unsigned)((N + 127) / 128);
     tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial, mode, mix);
     KW_CUDA_CHECK(cudaGetLastError());

@@ -56,6 +56,25 @@ def test_mixture_sequence_and_batching(cuda):
     assert [len(o) for o in paramgen.transform_many([])] == []
 
 
+def test_tensor_core_posterior_gives_the_same_mixture_sequence(cuda):
+    """precision='tc': tcgen05 posterior + FP64 re-check of near-ties => identical hard labels,
+    hence identical (FP64) MLPG output."""
+    import torch
+    w, m, c = synth.make_joint_gmm(32, seed=6)
+    src = _sources(6, 300)
+    paramgen = MLPG(_Model(w, m, c), precision='tc')
+    lens = [len(s) for s in src]
+    off = np.concatenate(([0], np.cumsum(lens)))
+    out, mix = paramgen.transform_device(torch.from_numpy(np.concatenate(src)).cuda(),
+                                         torch.from_numpy(off).cuda(), len(src), max(lens),
+                                         return_mix=True)
+    out, mix = out.cpu().numpy(), mix.cpu().numpy()
+    for i, s in enumerate(src):
+        exp, emix, _, _ = mlpg_ref.transform(s, w, m, c, return_internals=True)
+        assert np.array_equal(mix[off[i]:off[i + 1]], emix)
+        assert np.abs(out[off[i]:off[i + 1]] - exp).max() <= 1e-8
+
+
 def test_dense_oracle_agrees(cuda):
     w, m, c = synth.make_joint_gmm(4, seed=3)
     s = _sources(1, 40)[0]
