@@ -99,6 +99,13 @@ size_t kw_gmm_stats_len(int n_components, int dim);
 size_t kw_gmm_resp_len(int64_t n_frames, int n_components);
 size_t kw_gmm_workspace_bytes(int64_t n_frames, int n_components, int dim, int precision);
 
+/* precision 1 only (no-op otherwise): centre, scale, split into fp16 hi/lo and tile the frames
+ * into the workspace.  Call once per (x_dev, workspace) before kw_gmm_estep /
+ * kw_gmm_mstep_accumulate with precision 1; those calls read the packed frames from the SAME
+ * workspace and must be given the same n_frames, n_components and dim. */
+int kw_gmm_pack_frames(int64_t n_frames, const double* x_dev, int n_components, int dim,
+                       int precision, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* E-step: resp_dev (kw_gmm_resp_len doubles, component-major) responsibilities, sum of log p(x) accumulated into
  * stats[K*(1+D+D*D)] and n_frames into the next slot. */
 int kw_gmm_estep(int64_t n_frames, const double* x_dev, int n_components, int dim,

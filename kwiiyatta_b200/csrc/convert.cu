@@ -292,6 +292,11 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
     }
     PreparedView v = view_prepared(const_cast<double*>(prepared_dev), K, Dh);
     int rc;
+    if (precision == 1) {
+        rc = pack_frames_tc(total, src_dev, K, Dh, static_cast<char*>(workspace_dev) + w.bytes,
+                            workspace_bytes - w.bytes, st);
+        if (rc != KW_OK) return rc;
+    }
     if (precision == 1)
         rc = estep_tc(total, src_dev, K, Dh, v.src_means, v.px_prec_chol, v.px_aux, nullptr,
                       nullptr, 1, w.mix, static_cast<char*>(workspace_dev) + w.bytes,

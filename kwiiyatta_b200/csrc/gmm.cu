@@ -653,7 +653,7 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
                                        size_t workspace_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_mstep_accumulate: N, K, D must be positive");
-    (void)precision;  // the statistics are accumulated in fp64 in both modes
+    KW_REQUIRE(precision == 0 || precision == 1, "GMM precision must be 0 (fp64) or 1 (tensor)");
     if (D + 1 > 1024) {
         set_error("dim %d too large", D);
         return KW_ERR_UNSUPPORTED;
@@ -663,7 +663,25 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
         set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return KW_ERR_WORKSPACE;
     }
+    if (precision == 1)
+        return mstats_tc(N, K, D, resp_dev, centres_dev, stats_dev,
+                         static_cast<char*>(workspace_dev) + w.bytes, workspace_bytes - w.bytes,
+                         st);
     return mstats_fp64(N, x_dev, K, D, resp_dev, centres_dev, w.partial, stats_dev, RESP_FLOOR, st);
+}
+
+extern "C" int kw_gmm_pack_frames(int64_t N, const double* x_dev, int K, int D, int precision,
+                                  void* workspace_dev, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_pack_frames: N, K, D must be positive");
+    if (precision != 1) return KW_OK;
+    GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    return pack_frames_tc(N, x_dev, K, D, static_cast<char*>(workspace_dev) + w.bytes,
+                          workspace_bytes - w.bytes, st);
 }
 
 extern "C" int kw_gmm_mstep_finalize(int K, int D, double reg_covar, int weight_norm,

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -158,7 +159,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 // Packed layouts (in halves).  X tile: [part][row group 16][k group DP/8][8][8];
 // B (per component): [part][col group DP/8][k group DP/8][8][8].
-__host__ __device__ inline size_t tile_elems(int DP) { return (size_t)TILE_M * DP; }
+// The packed X tile is DPB = DP + 16 columns wide: column DP holds the constant 1 (so the M-step
+// contraction also yields sum r (x - mu)), the rest of the pad is zero.  Three parts per tile:
+// hi, lo * 2^11 (E-step) and lo unscaled (M-step).
+__host__ __device__ inline int dpb_of(int DP) { return DP + 16; }
+__host__ __device__ inline size_t tile_elems(int DP) { return (size_t)TILE_M * dpb_of(DP); }
+constexpr int X_PARTS = 3;
 __host__ __device__ inline size_t bmat_elems(int DP) { return (size_t)DP * DP; }
 
 // ------------------------------------------------------------------------------------------
@@ -220,16 +226,23 @@ __device__ __forceinline__ void split_store(double v, __half* hi_dst, __half* lo
 __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restrict__ X,
                               const double* __restrict__ xinfo, __half* __restrict__ xt) {
     const long long tile = blockIdx.x;
-    __half* hi = xt + (size_t)tile * 2 * tile_elems(DP);
-    __half* lo = hi + tile_elems(DP);
-    const int kg_n = DP / 8;
-    for (int e = threadIdx.x; e < TILE_M * DP; e += blockDim.x) {
-        const int r = e / DP, c = e - r * DP;
+    const int DPB = dpb_of(DP);
+    __half* hi = xt + (size_t)tile * X_PARTS * tile_elems(DP);
+    __half* lo_s = hi + tile_elems(DP);
+    __half* lo_u = lo_s + tile_elems(DP);
+    const int kg_n = DPB / 8;
+    for (int e = threadIdx.x; e < TILE_M * DPB; e += blockDim.x) {
+        const int r = e / DPB, c = e - r * DPB;
         const long long n = tile * TILE_M + r;
         double v = 0.0;
         if (n < N && c < D) v = (X[n * D + c] - xinfo[c]) / xinfo[DP + c];
+        if (c == DP) v = 1.0;
         const size_t o = ((size_t)(r >> 3) * kg_n + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7);
-        split_store(v, hi + o, lo + o);
+        const __half h = __double2half(v);
+        const double res = v - (double)__half2float(h);
+        hi[o] = h;
+        lo_s[o] = __double2half(res * LO_SCALE);
+        lo_u[o] = __double2half(res);
     }
 }
 
@@ -290,7 +303,7 @@ struct EstepSmem {
 __host__ __device__ inline EstepSmem estep_smem(int DP) {
     EstepSmem s;
     uint32_t o = 0;
-    s.a = o;     o += 2u * TILE_M * DP * 2;            // hi then lo
+    s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
     s.b_hi = o;  o += 2u * DP * DP * 2;                // two stages
     s.b_lo = o;  o += (uint32_t)DP * DP * 2;
     s.scl = o;   o += 2u * 2 * DP * 4;                 // two stages of [scale | bprime]
@@ -322,9 +335,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = 2u * TILE_M * DP * 2;
+    const uint32_t a_bytes = 2u * TILE_M * dpb_of(DP) * 2;
     const uint32_t b_bytes = (uint32_t)DP * DP * 2;
     const uint32_t lbo = 128, sbo = (uint32_t)(DP / 8) * 128;
+    const uint32_t sbo_a = (uint32_t)(dpb_of(DP) / 8) * 128;
     const int ksteps = DP / 16;
     const uint32_t idesc = make_idesc(TILE_M, DP);
 
@@ -356,7 +370,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     if (k == 0) {
                         mbar_wait(bars + BAR_A_EMPTY, ((uint32_t)it & 1u) ^ 1u);
                         mbar_expect_tx(bars + BAR_A_FULL, a_bytes);
-                        bulk_g2s(a_hi, xt + (size_t)tile * 2 * tile_elems(DP), a_bytes,
+                        bulk_g2s(a_hi, xt + (size_t)tile * X_PARTS * tile_elems(DP), a_bytes,
                                  bars + BAR_A_FULL);
                     }
                 }
@@ -378,19 +392,19 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     if (k == 0) mbar_wait(bars + BAR_A_FULL, (uint32_t)it & 1u);
                     tc_fence_after();
                     for (int ks = 0; ks < ksteps; ++ks)       // x_hi . l_lo
-                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo),
+                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo_a),
                                  make_desc(b_lo_addr + ks * 256, lbo, sbo), idesc, ks > 0);
                     umma_commit(bars + BAR_BLO_EMPTY);
                     mbar_wait(bars + BAR_BHI_FULL0 + s, u & 1u);
                     tc_fence_after();
                     for (int ks = 0; ks < ksteps; ++ks)       // x_lo . l_hi
-                        umma_f16(acc, make_desc(a_lo_addr + ks * 256, lbo, sbo),
+                        umma_f16(acc, make_desc(a_lo_addr + ks * 256, lbo, sbo_a),
                                  make_desc(b_hi_addr + ks * 256, lbo, sbo), idesc, 1u);
                     // acc = acc * 2^-11 + x_hi . l_hi
-                    umma_f16_scaled(acc, make_desc(a_hi_addr, lbo, sbo),
+                    umma_f16_scaled(acc, make_desc(a_hi_addr, lbo, sbo_a),
                                     make_desc(b_hi_addr, lbo, sbo), idesc);
                     for (int ks = 1; ks < ksteps; ++ks)
-                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo),
+                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo_a),
                                  make_desc(b_hi_addr + ks * 256, lbo, sbo), idesc, 1u);
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
@@ -527,6 +541,365 @@ __global__ void refine_argmax_kernel(long long N, int D, const double* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core M-step statistics.
+//
+//   S_k[i][j] = sum_n z_ni x'_nj,   z_ni = r_nk (x'_ni - mu'_ki)        (i, j < DP; x'_{n,DP} = 1)
+//
+// A = z (generated per (tile, component) by CUDA cores, fp16 hi + unscaled lo), B = x' (the
+// packed frames, shared by all components), both MN-major (the contraction runs over frames).
+// Work item = (component, chunk of 64-frame tiles); the accumulator lives in TMEM for M_FLUSH
+// tiles, is then added (fp32, round-to-nearest) into registers of the epilogue warps and written
+// as float64 partials at the end of the item.  Rows >= 128 of S come from a second, narrow MMA on
+// a shifted row window (rows DP-128 .. DP-1 x columns 128 .. DP+15).
+// ------------------------------------------------------------------------------------------
+constexpr int MT = 64;        // frames per M-step tile
+constexpr int M_FLUSH = 2;    // tiles accumulated in TMEM between flushes
+
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+    return make_idesc(M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+}
+
+struct MstepGeom {
+    int DP, DPB, DA;     // DA = feature rows of the A tile (>= 128)
+    int N1, N2;          // accumulator widths of the two MMAs (N2 = 0 when DP <= 128)
+    int a_win2;          // first feature group of MMA2's row window
+    uint32_t b_stage, a_stage;   // bytes per smem stage (hi + lo)
+    uint32_t off_b, off_a, off_rs, off_mu, off_bars, off_tmem, total;
+    int partial_len;     // doubles per work item
+};
+__host__ __device__ inline MstepGeom mstep_geom(int DP) {
+    MstepGeom g;
+    g.DP = DP;
+    g.DPB = dpb_of(DP);
+    g.DA = DP > 128 ? DP : 128;
+    g.N1 = g.DPB;
+    g.N2 = DP > 128 ? DP + 16 - 128 : 0;
+    g.a_win2 = (DP - 128) / 8;
+    g.b_stage = 2u * MT * g.DPB * 2;
+    g.a_stage = 2u * MT * g.DA * 2;
+    uint32_t o = 0;
+    g.off_b = o;    o += 2 * g.b_stage;
+    g.off_a = o;    o += 2 * g.a_stage;
+    g.off_rs = o;   o += 2 * MT * 4;
+    g.off_mu = o;   o += (uint32_t)g.DA * 4;
+    g.off_bars = o; o += 16 * 8;
+    g.off_tmem = o; o += 16;
+    g.total = o;
+    g.partial_len = 128 * g.N1 + 128 * g.N2 + 1;
+    return g;
+}
+
+enum { MB_B_FULL = 0, MB_B_EMPTY = 2, MB_A_FULL = 4, MB_A_EMPTY = 6, MB_TM_FULL = 8,
+       MB_TM_EMPTY = 10 };
+
+// mu'_k = fl32((mu_k - c) / sigma) for the generators, one CTA per component.
+__global__ void pack_centres_kernel(int K, int D, int DA, const double* __restrict__ centres,
+                                    const double* __restrict__ xinfo, int DP,
+                                    float* __restrict__ mu32) {
+    const int k = blockIdx.x;
+    for (int d = threadIdx.x; d < DA; d += blockDim.x) {
+        float v = 0.f;
+        if (d < D) v = (float)((centres[(size_t)k * D + d] - xinfo[d]) / xinfo[DP + d]);
+        mu32[(size_t)k * DA + d] = v;
+    }
+}
+
+__global__ void __launch_bounds__(448, 1)
+mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
+                 int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
+                 const float* __restrict__ mu32, double* __restrict__ partial, int swap_strides) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const MstepGeom G = mstep_geom(DP);
+    unsigned char* b_base = smem + G.off_b;
+    unsigned char* a_base = smem + G.off_a;
+    float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
+    float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = K * n_chunks;
+    const uint32_t part_b = (uint32_t)MT * G.DPB * 2;   // bytes of one part of a B stage
+    const uint32_t part_a = (uint32_t)MT * G.DA * 2;
+    const uint32_t acc_cols = (uint32_t)(G.N1 + G.N2);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + MB_B_FULL + i, 1);
+            mbar_init(bars + MB_B_EMPTY + i, 5);    // 4 generator warps + the MMA commit
+            mbar_init(bars + MB_A_FULL + i, 4);
+            mbar_init(bars + MB_A_EMPTY + i, 1);
+            mbar_init(bars + MB_TM_FULL + i, 1);
+            mbar_init(bars + MB_TM_EMPTY + i, 8);
+        }
+        fence_barrier_init();
+    }
+    // zero the A stages once (feature rows >= DP stay zero)
+    for (uint32_t i = threadIdx.x; i < 2 * G.a_stage / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(a_base)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto item_tiles = [&](int item, int& k, int& t0, int& t1) {
+        const int chunk = item / K;
+        k = item - chunk * K;
+        t0 = chunk * tiles_per_chunk;
+        t1 = min(n_mtiles, t0 + tiles_per_chunk);
+    };
+
+    if (warp == 0) {
+        // ---------------- producer: packed frames (hi, unscaled lo) ----------------
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int k, t0, t1;
+                item_tiles(item, k, t0, t1);
+                for (int t = t0; t < t1; ++t, ++g) {
+                    const uint32_t s = g & 1u, u = g >> 1;
+                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
+                    mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
+                    const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                         (size_t)(t & 1) * MT * G.DPB;
+                    unsigned char* dst = b_base + s * G.b_stage;
+                    bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
+                    bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
+                             bars + MB_B_FULL + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc_mn(128, G.N1);
+            const uint32_t idesc2 = make_idesc_mn(128, G.N2 > 0 ? G.N2 : 16);
+            // MN-major, no swizzle: SBO = stride between 8-element groups along M/N (features),
+            // LBO = stride between 8-frame groups along K.
+            uint32_t sbo = 128, lbo_a = (uint32_t)(G.DA / 8) * 128, lbo_b = (uint32_t)(G.DPB / 8) * 128;
+            uint32_t g = 0, f = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int k, t0, t1;
+                item_tiles(item, k, t0, t1);
+                for (int t = t0; t < t1; ++t, ++g) {
+                    const uint32_t s = g & 1u, u = g >> 1;
+                    const int in_group = (t - t0) % M_FLUSH;
+                    const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
+                    const uint32_t ts = f & 1u, tu = f >> 1;
+                    if (in_group == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
+                    mbar_wait(bars + MB_A_FULL + s, u & 1u);
+                    mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_base + s * G.a_stage);
+                    const uint32_t b_addr = smem_u32(b_base + s * G.b_stage);
+                    const uint32_t acc1 = tmem_base + ts * acc_cols;
+                    const uint32_t acc2 = acc1 + (uint32_t)G.N1;
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t ap = a_addr + (pass == 2 ? part_a : 0u);   // A lo in pass 2
+                        const uint32_t bp = b_addr + (pass == 1 ? part_b : 0u);   // B lo in pass 1
+                        for (int ks = 0; ks < MT / 16; ++ks) {
+                            const uint32_t accum = (in_group > 0 || pass > 0 || ks > 0) ? 1u : 0u;
+                            const uint32_t ao = ap + ks * 2 * lbo_a, bo = bp + ks * 2 * lbo_b;
+                            uint64_t da, db;
+                            if (!swap_strides) { da = make_desc(ao, lbo_a, sbo); db = make_desc(bo, lbo_b, sbo); }
+                            else               { da = make_desc(ao, sbo, lbo_a); db = make_desc(bo, sbo, lbo_b); }
+                            umma_f16(acc1, da, db, idesc1, accum);
+                            if (G.N2 > 0) {
+                                const uint32_t ao2 = ao + G.a_win2 * sbo, bo2 = bo + 16 * sbo;
+                                if (!swap_strides) { da = make_desc(ao2, lbo_a, sbo); db = make_desc(bo2, lbo_b, sbo); }
+                                else               { da = make_desc(ao2, sbo, lbo_a); db = make_desc(bo2, sbo, lbo_b); }
+                                umma_f16(acc2, da, db, idesc2, accum);
+                            }
+                        }
+                    }
+                    umma_commit(bars + MB_A_EMPTY + s);
+                    umma_commit(bars + MB_B_EMPTY + s);
+                    if (last) { umma_commit(bars + MB_TM_FULL + ts); ++f; }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- generators (warps 2..5): A = r (x' - mu') split into hi / lo ----------
+        const int gt = threadIdx.x - 64;     // 0..127
+        const int fgroups = MT / 8, kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
+        const int n_chunks16 = fgroups * kgD * 8;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int k, t0, t1;
+            item_tiles(item, k, t0, t1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            for (int d = gt; d < G.DA; d += 128) mu_s[d] = mu32[(size_t)k * G.DA + d];
+            double nacc = 0.0;
+            for (int t = t0; t < t1; ++t, ++g) {
+                const uint32_t s = g & 1u, u = g >> 1;
+                if (gt < MT) {
+                    const long long n = (long long)t * MT + gt;
+                    r_s[s * MT + gt] = (n < N) ? (float)respT[(size_t)k * Npad + n] : 0.f;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (gt == 0)
+                    for (int i = 0; i < MT; ++i) nacc += (double)r_s[s * MT + i];
+                mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
+                const unsigned char* bh = b_base + s * G.b_stage;
+                unsigned char* ah = a_base + s * G.a_stage;
+                for (int idx = gt; idx < n_chunks16; idx += 128) {
+                    const int fr = idx & 7, rest = idx >> 3;
+                    const int featg = rest % kgD, fg = rest / kgD;
+                    const uint32_t bo = ((uint32_t)(fg * kgB + featg) * 8 + fr) * 16;
+                    const uint32_t ao = ((uint32_t)(fg * kgA + featg) * 8 + fr) * 16;
+                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
+                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
+                    const float r = r_s[s * MT + fg * 8 + fr];
+                    const __half2* hp = reinterpret_cast<const __half2*>(&hv);
+                    const __half2* lp = reinterpret_cast<const __half2*>(&lv);
+                    uint4 oh, ol;
+                    __half2* ohp = reinterpret_cast<__half2*>(&oh);
+                    __half2* olp = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
+                        const float m0 = mu_s[featg * 8 + 2 * e], m1 = mu_s[featg * 8 + 2 * e + 1];
+                        const float z0 = r * ((xh.x + xl.x) - m0), z1 = r * ((xh.y + xl.y) - m1);
+                        const __half2 zh = __floats2half2_rn(z0, z1);
+                        const float2 zf = __half22float2(zh);
+                        ohp[e] = zh;
+                        olp[e] = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
+                    }
+                    *reinterpret_cast<uint4*>(ah + ao) = oh;
+                    *reinterpret_cast<uint4*>(ah + part_a + ao) = ol;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bars + MB_A_FULL + s);
+                    mbar_arrive(bars + MB_B_EMPTY + s);
+                }
+            }
+            if (gt == 0) partial[(size_t)item * G.partial_len + G.partial_len - 1] = nacc;
+        }
+    } else {
+        // ---------------- epilogue (warps 6..13): TMEM -> fp32 registers -> fp64 partials ------
+        const uint32_t quarter = (uint32_t)(warp & 3);
+        const int half = (warp - 6) >> 2;
+        const int row = (int)quarter * 32 + lane;
+        const int n16_1 = G.N1 / 16, n16_2 = G.N2 / 16;
+        const int c1_begin = half == 0 ? 0 : (n16_1 + 1) / 2;
+        const int c1_end = half == 0 ? (n16_1 + 1) / 2 : n16_1;
+        const int c2_begin = half == 0 ? 0 : (n16_2 + 1) / 2;
+        const int c2_end = half == 0 ? (n16_2 + 1) / 2 : n16_2;
+        float acc[6][16];
+        uint32_t f = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int k, t0, t1;
+            item_tiles(item, k, t0, t1);
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
+            const int n_groups = (t1 - t0 + M_FLUSH - 1) / M_FLUSH;
+            for (int h = 0; h < n_groups; ++h, ++f) {
+                const uint32_t ts = f & 1u, tu = f >> 1;
+                mbar_wait(bars + MB_TM_FULL + ts, tu & 1u);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    if (c1_begin + c < c1_end) {
+                        uint32_t v[16];
+                        tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[c][j] += __uint_as_float(v[j]);
+                    }
+                }
+                if (c2_begin < c2_end) {
+                    uint32_t v[16];
+                    tmem_ld16(tbase + (uint32_t)G.N1 + (uint32_t)c2_begin * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[5][j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + MB_TM_EMPTY + ts);
+            }
+            double* out = partial + (size_t)item * G.partial_len;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                if (c1_begin + c < c1_end) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = (double)acc[c][j];
+                }
+            }
+            if (c2_begin < c2_end) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    out[(size_t)128 * G.N1 + (size_t)row * G.N2 + c2_begin * 16 + j] =
+                        (double)acc[5][j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Partials -> the statistics vector kw_gmm_mstep_finalize expects, centred on centres[k]:
+//   n_k,  sum r (x - c_k),  sum r (x - c_k)(x - c_k)^T   (float64, fixed summation order).
+__global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
+                                      const double* __restrict__ partial,
+                                      const double* __restrict__ xinfo,
+                                      const float* __restrict__ mu32,
+                                      const double* __restrict__ centres,
+                                      double* __restrict__ stats) {
+    extern __shared__ double sh[];      // raw sums of one component: partial_len doubles
+    const MstepGeom G = mstep_geom(DP);
+    const int k = blockIdx.x;
+    for (int e = threadIdx.x; e < G.partial_len; e += blockDim.x) {
+        double t = 0.0;
+        for (int c = 0; c < n_chunks; ++c) t += partial[((size_t)c * K + k) * G.partial_len + e];
+        sh[e] = t;
+    }
+    __syncthreads();
+    const double* a1 = sh;
+    const double* a2 = sh + 128 * G.N1;
+    const double nk = sh[G.partial_len - 1];
+    auto sab = [&](int i, int j) -> double {      // needs i < 128 or j >= 128
+        if (i < 128) return a1[i * G.N1 + j];
+        return a2[(i - (DP - 128)) * G.N2 + (j - 128)];
+    };
+    auto mc = [&](int i) -> double { return sab(i, DP); };
+    const float* muk = mu32 + (size_t)k * G.DA;
+    auto sc = [&](int i, int j) -> double { return sab(i, j) - mc(i) * (double)muk[j]; };
+    const size_t sb = 1 + (size_t)D + (size_t)D * D;
+    double* st = stats + (size_t)k * sb;
+    const double* ck = centres + (size_t)k * D;
+    // e_d = effective centre - requested centre, in original units
+    auto eoff = [&](int d) -> double {
+        return (xinfo[d] + xinfo[DP + d] * (double)muk[d]) - ck[d];
+    };
+    if (threadIdx.x == 0) st[0] = nk;
+    for (int i = threadIdx.x; i < D; i += blockDim.x)
+        st[1 + i] = xinfo[DP + i] * mc(i) + nk * eoff(i);
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e - i * D;
+        const bool ok_ij = (i < 128) || (j >= 128), ok_ji = (j < 128) || (i >= 128);
+        double v;
+        if (ok_ij && ok_ji) v = 0.5 * (sc(i, j) + sc(j, i));
+        else if (ok_ij) v = sc(i, j);
+        else v = sc(j, i);
+        const double si = xinfo[DP + i], sj = xinfo[DP + j];
+        const double mi = si * mc(i), mj = sj * mc(j), ei = eoff(i), ej = eoff(j);
+        st[1 + D + e] = si * sj * v + mi * ej + ei * mj + nk * ei * ej;
+    }
+}
+
 }  // namespace tc
 
 constexpr int TC_STAT_CHUNKS = 296;
@@ -540,48 +913,87 @@ struct TcWorkspace {
     double* cst;
     double* lse_partial;
     int32_t* cand;
+    float* mu32;
+    double* mpartial;
+    int m_chunks, tiles_per_chunk, n_mtiles;
     size_t bytes;
 };
 
 static inline int tc_dp(int D) { return (D + 15) / 16 * 16; }
 
+static int device_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+// Number of frame chunks per component for the tensor-core M-step: enough items for a few full
+// waves of the persistent grid with the smallest tail.
+static int tc_m_chunks(int K, long long n_mtiles) {
+    const int sms = 148;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int c = 1; c <= 64; ++c) {
+        if ((long long)c > n_mtiles) break;
+        const long long items = (long long)K * c;
+        if (items < sms && c < 64 && (long long)(c + 1) <= n_mtiles) continue;
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = (double)items / (double)(waves * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+        if (items >= 8 * sms) break;
+    }
+    return best;
+}
+
 static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     const int DP = tc_dp(D);
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
+    const tc::MstepGeom G = tc::mstep_geom(DP);
     Carver c(base);
     TcWorkspace w;
+    w.n_mtiles = (int)(2 * n_tiles);
+    w.m_chunks = tc_m_chunks(K, w.n_mtiles);
+    w.tiles_per_chunk = (w.n_mtiles + w.m_chunks - 1) / w.m_chunks;
     w.colpartial = c.take<double>((size_t)TC_STAT_CHUNKS * 3 * D);
     w.xinfo = c.take<double>(2 * (size_t)DP);
-    w.xt = c.take<__half>((size_t)n_tiles * 2 * tc::tile_elems(DP));
+    w.xt = c.take<__half>((size_t)n_tiles * tc::X_PARTS * tc::tile_elems(DP));
     w.bt = c.take<__half>((size_t)K * 2 * tc::bmat_elems(DP));
     w.sc = c.take<float>((size_t)K * 2 * DP);
     w.cst = c.take<double>(2 * (size_t)K);
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
     w.cand = c.take<int32_t>((size_t)N);
+    w.mu32 = c.take<float>((size_t)K * G.DA);
+    w.mpartial = c.take<double>((size_t)w.m_chunks * K * G.partial_len);
     w.bytes = align_up(c.used, 256);
     return w;
 }
 
 size_t tc_workspace_bytes(long long N, int K, int D) { return carve_tc(N, K, D, nullptr).bytes; }
 
-// wlp (or resp, or argmax) through the tensor-core path.  mode 0: resp + sum of logsumexp into
-// lse_out[0] and N into lse_out[1];  mode 1: hard labels into mix (resp is scratch, K x Npad).
-int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
-             const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
-             void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    const int DP = tc_dp(D);
-    if (DP > 144) {
-        set_error("dim %d > 144 is not supported by the tensor-core E-step", D);
+static int tc_check(long long N, int K, int D, void* workspace, size_t workspace_bytes,
+                    TcWorkspace& w) {
+    if (tc_dp(D) > 144) {
+        set_error("dim %d > 144 is not supported by the tensor-core kernels", D);
         return KW_ERR_UNSUPPORTED;
     }
-    TcWorkspace w = carve_tc(N, K, D, workspace);
+    w = carve_tc(N, K, D, workspace);
     if (w.bytes > workspace_bytes) {
-        set_error("tensor-core E-step workspace too small: need %zu bytes, got %zu", w.bytes,
+        set_error("tensor-core workspace too small: need %zu bytes, got %zu", w.bytes,
                   workspace_bytes);
         return KW_ERR_WORKSPACE;
     }
+    return KW_OK;
+}
+
+// Centre, scale, split and tile the frames once per (X, workspace).
+int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+    TcWorkspace w;
+    int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
+    if (rc != KW_OK) return rc;
+    const int DP = tc_dp(D);
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
-    const long long Npad = resp_pad(N);
     const long long fpc = (N + TC_STAT_CHUNKS - 1) / TC_STAT_CHUNKS;
     tc::colstats_partial_kernel<<<TC_STAT_CHUNKS, 160, 0, st>>>(N, D, X, w.colpartial, fpc);
     KW_CUDA_CHECK(cudaGetLastError());
@@ -589,13 +1001,25 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     KW_CUDA_CHECK(cudaGetLastError());
     tc::pack_x_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(N, D, DP, X, w.xinfo, w.xt);
     KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+// wlp (or resp, or argmax) through the tensor-core path; the frames must have been packed into
+// this workspace by pack_frames_tc.  mode 0: resp + sum of logsumexp into lse_out[0] and N into
+// lse_out[1];  mode 1: hard labels into mix (FP64 re-check of near ties).
+int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
+             const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
+             void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    TcWorkspace w;
+    int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
+    if (rc != KW_OK) return rc;
+    const int DP = tc_dp(D);
+    const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
+    const long long Npad = resp_pad(N);
     tc::pack_l_kernel<<<K, 256, sizeof(double) * DP, st>>>(K, D, DP, means, pc, aux, w.xinfo,
                                                           w.bt, w.sc, w.cst);
     KW_CUDA_CHECK(cudaGetLastError());
-
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sms();
     const tc::EstepSmem L = tc::estep_smem(DP);
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -614,10 +1038,40 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     const unsigned lgrid = (unsigned)((N + 127) / 128);
     tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial, mode, mix);
     KW_CUDA_CHECK(cudaGetLastError());
-    if (mode == 0) {
-        launch_reduce_fixed(w.lse_partial, (long long)lgrid, (double)N, lse_out, st);
-        KW_CUDA_CHECK(cudaGetLastError());
+    launch_reduce_fixed(w.lse_partial, (long long)lgrid, (double)N, lse_out, st);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+// M-step statistics on the tensor cores (frames packed by pack_frames_tc).
+int mstats_tc(long long N, int K, int D, const double* resp, const double* centres, double* stats,
+              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    TcWorkspace w;
+    int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
+    if (rc != KW_OK) return rc;
+    const int DP = tc_dp(D);
+    const tc::MstepGeom G = tc::mstep_geom(DP);
+    tc::pack_centres_kernel<<<K, 160, 0, st>>>(K, D, G.DA, centres, w.xinfo, DP, w.mu32);
+    KW_CUDA_CHECK(cudaGetLastError());
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
+    const int items = K * w.m_chunks;
+    const int grid = std::min(items, device_sms());
+    static int swap_strides = -1;
+    if (swap_strides < 0) {
+        const char* e = getenv("KW_TC_MSWAP");
+        swap_strides = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
+    tc::mstats_tc_kernel<<<grid, 448, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
+                                                     w.tiles_per_chunk, w.m_chunks, K, DP, w.xt,
+                                                     resp, w.mu32, w.mpartial, swap_strides);
+    KW_CUDA_CHECK(cudaGetLastError());
+    const size_t psm = sizeof(double) * (size_t)G.partial_len;
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_post_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    tc::mstats_tc_post_kernel<<<K, 256, psm, st>>>(K, D, DP, w.m_chunks, w.mpartial, w.xinfo,
+                                                   w.mu32, centres, stats);
+    KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
 

@@ -87,6 +87,13 @@ class GaussianMixture:
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=dev)
 
+    def _pack(self, torch, x):
+        n, d = x.shape
+        rc = _lib.lib().kw_gmm_pack_frames(n, x.data_ptr(), self.n_components, d,
+                                           self.precision, self._ws.data_ptr(), self._ws_bytes,
+                                           _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_pack_frames')
+
     def _estep(self, torch, x):
         n, d = x.shape
         rc = _lib.lib().kw_gmm_estep(
@@ -165,6 +172,7 @@ class GaussianMixture:
             raise ValueError('Expected n_samples >= n_components '
                              f'but got n_components = {k}, n_samples = {n}')
         self._alloc(torch, n, d, dev)
+        self._pack(torch, x)
         if self.verbose:
             print('Initialization 0')
         # GaussianMixture._initialize: one M-step from the initial responsibilities
@@ -293,6 +301,7 @@ class GaussianMixture:
                                   device=x.device)
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=x.device)
+        self._pack(torch, x)
         self._estep(torch, x)
         resp, self._resp, self._ws = self._resp[:, :n].t(), None, None
         return resp, float(self._stats[-2].item()) / n
