@@ -141,6 +141,13 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int R> __device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R> __device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+
 // UMMA shared-memory descriptor, canonical K-major layout without swizzle:
 //   element (row r, k-col c) at  (r/8)*SBO + (c/8)*LBO + (r%8)*16 B + (c%8)*2 B.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
@@ -256,7 +263,7 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
     const int k = blockIdx.x;
     const double* L = prec_chol + (size_t)k * D * D;
     const double* mu = means + (size_t)k * D;
-    float* sck = sc + (size_t)k * 2 * DP;
+    float* sck = sc + (size_t)k * 3 * DP;
     for (int j = threadIdx.x; j < DP; j += blockDim.x) {
         double amax = 0.0, bp = 0.0;
         if (j < D) {
@@ -275,6 +282,7 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
         colinv[j] = 1.0 / scale;
         sck[j] = (float)scale;
         sck[DP + j] = (float)bp;
+        sck[2 * DP + j] = (float)(bp - (double)(float)bp);
     }
     if (threadIdx.x == 0) {
         cst[2 * k] = aux[(size_t)k * (D + 2) + D];
@@ -306,7 +314,7 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
     s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
     s.b_hi = o;  o += 2u * DP * DP * 2;                // two stages
     s.b_lo = o;  o += (uint32_t)DP * DP * 2;
-    s.scl = o;   o += 2u * 2 * DP * 4;                 // two stages of [scale | bprime]
+    s.scl = o;   o += 2u * 3 * DP * 4;                 // two stages of [scale | b' hi | b' lo]
     s.cst = o;   o += 2u * 2 * 8;
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
@@ -425,8 +433,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             int k1 = 0, k2 = -1;
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                float* sk = scl + (size_t)s * 2 * DP;
-                for (int i = et; i < 2 * DP; i += 128) sk[i] = sc[(size_t)k * 2 * DP + i];
+                float* sk = scl + (size_t)s * 3 * DP;
+                for (int i = et; i < 3 * DP; i += 128) sk[i] = sc[(size_t)k * 3 * DP + i];
                 if (et < 2) cst_s[s * 2 + et] = cst[2 * k + et];
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
@@ -441,7 +449,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float y = fmaf(__uint_as_float(v[j]), sk[c * 16 + j],
-                                             -sk[DP + c * 16 + j]);
+                                             -sk[DP + c * 16 + j]) - sk[2 * DP + c * 16 + j];
                         part = fmaf(y, y, part);
                     }
                     q += (double)part;
@@ -555,7 +563,6 @@ __global__ void refine_argmax_kernel(long long N, int D, const double* __restric
 // a shifted row window (rows DP-128 .. DP-1 x columns 128 .. DP+15).
 // ------------------------------------------------------------------------------------------
 constexpr int MT = 64;        // frames per M-step tile
-constexpr int M_FLUSH = 2;    // tiles accumulated in TMEM between flushes
 
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
     return make_idesc(M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
@@ -606,10 +613,11 @@ __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restri
     }
 }
 
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(512, 1)
 mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
-                 const float* __restrict__ mu32, double* __restrict__ partial, int swap_strides) {
+                 const float* __restrict__ mu32, double* __restrict__ partial, int swap_strides,
+                 int M_FLUSH) {
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     unsigned char* b_base = smem + G.off_b;
@@ -652,7 +660,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         t1 = min(n_mtiles, t0 + tiles_per_chunk);
     };
 
-    if (warp == 0) {
+    // warpgroup 0: producer + MMA issuer (+2 idle warps), 1: generators, 2-3: epilogue (holds the
+    // second-level accumulators, so it takes the registers the others give up)
+    if (warp < 4) {
+      reg_dec<80>();
+      if (warp == 0) {
         // ---------------- producer: packed frames (hi, unscaled lo) ----------------
         if (lane == 0) {
             uint32_t g = 0;
@@ -672,7 +684,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc_mn(128, G.N1);
@@ -721,9 +733,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 }
             }
         }
-    } else if (warp < 6) {
-        // ---------------- generators (warps 2..5): A = r (x' - mu') split into hi / lo ----------
-        const int gt = threadIdx.x - 64;     // 0..127
+      }
+    } else if (warp < 8) {
+        reg_dec<104>();
+        // ---------------- generators (warps 4..7): A = r (x' - mu') split into hi / lo ----------
+        const int gt = threadIdx.x - 128;    // 0..127
         const int fgroups = MT / 8, kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
         const int n_chunks16 = fgroups * kgD * 8;
         uint32_t g = 0;
@@ -782,9 +796,10 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             if (gt == 0) partial[(size_t)item * G.partial_len + G.partial_len - 1] = nacc;
         }
     } else {
-        // ---------------- epilogue (warps 6..13): TMEM -> fp32 registers -> fp64 partials ------
+        reg_inc<160>();
+        // ---------------- epilogue (warps 8..15): TMEM -> fp32 registers -> fp64 partials ------
         const uint32_t quarter = (uint32_t)(warp & 3);
-        const int half = (warp - 6) >> 2;
+        const int half = (warp - 8) >> 2;
         const int row = (int)quarter * 32 + lane;
         const int n16_1 = G.N1 / 16, n16_2 = G.N2 / 16;
         const int c1_begin = half == 0 ? 0 : (n16_1 + 1) / 2;
@@ -959,7 +974,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.xinfo = c.take<double>(2 * (size_t)DP);
     w.xt = c.take<__half>((size_t)n_tiles * tc::X_PARTS * tc::tile_elems(DP));
     w.bt = c.take<__half>((size_t)K * 2 * tc::bmat_elems(DP));
-    w.sc = c.take<float>((size_t)K * 2 * DP);
+    w.sc = c.take<float>((size_t)K * 3 * DP);
     w.cst = c.take<double>(2 * (size_t)K);
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
     w.cand = c.take<int32_t>((size_t)N);
@@ -1057,14 +1072,17 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
-    static int swap_strides = -1;
+    static int swap_strides = -1, m_flush = 2;
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
         swap_strides = (e != nullptr && e[0] == '1') ? 1 : 0;
+        const char* f = getenv("KW_TC_MFLUSH");   // tiles accumulated in TMEM between flushes
+        if (f != nullptr && atoi(f) > 0) m_flush = atoi(f);
     }
-    tc::mstats_tc_kernel<<<grid, 448, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
+    tc::mstats_tc_kernel<<<grid, 512, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
                                                      w.tiles_per_chunk, w.m_chunks, K, DP, w.xt,
-                                                     resp, w.mu32, w.mpartial, swap_strides);
+                                                     resp, w.mu32, w.mpartial, swap_strides,
+                                                     m_flush);
     KW_CUDA_CHECK(cudaGetLastError());
     const size_t psm = sizeof(double) * (size_t)G.partial_len;
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_post_kernel,
