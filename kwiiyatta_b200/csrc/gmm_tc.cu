@@ -590,11 +590,13 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     g.off_b = o;    o += 2 * g.b_stage;
     g.off_a = o;    o += 2 * g.a_stage;
     g.off_rs = o;   o += 2 * MT * 4;
+    o = (o + 15u) & ~15u;
     g.off_mu = o;   o += (uint32_t)g.DA * 4;
+    o = (o + 15u) & ~15u;
     g.off_bars = o; o += 16 * 8;
     g.off_tmem = o; o += 16;
     g.total = o;
-    g.partial_len = 128 * g.N1 + 128 * g.N2 + 1;
+    g.partial_len = 128 * g.N1 + 128 * g.N2;
     return g;
 }
 
@@ -613,11 +615,11 @@ __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restri
     }
 }
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
-                 const float* __restrict__ mu32, double* __restrict__ partial, int swap_strides,
-                 int M_FLUSH) {
+                 const float* __restrict__ mu32, float* __restrict__ partial,
+                 double* __restrict__ npartial, int swap_strides, int M_FLUSH) {
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     unsigned char* b_base = smem + G.off_b;
@@ -635,8 +637,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + MB_B_FULL + i, 1);
-            mbar_init(bars + MB_B_EMPTY + i, 5);    // 4 generator warps + the MMA commit
-            mbar_init(bars + MB_A_FULL + i, 4);
+            mbar_init(bars + MB_B_EMPTY + i, 9);    // 8 generator warps + the MMA commit
+            mbar_init(bars + MB_A_FULL + i, 8);
             mbar_init(bars + MB_A_EMPTY + i, 1);
             mbar_init(bars + MB_TM_FULL + i, 1);
             mbar_init(bars + MB_TM_EMPTY + i, 8);
@@ -660,10 +662,12 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         t1 = min(n_mtiles, t0 + tiles_per_chunk);
     };
 
-    // warpgroup 0: producer + MMA issuer (+2 idle warps), 1: generators, 2-3: epilogue (holds the
-    // second-level accumulators, so it takes the registers the others give up)
+    // warpgroup 0: producer + MMA issuer (+2 idle warps), 1-2: generators, 3-4: epilogue (holds
+    // the second-level accumulators, so it takes the registers the others give up).  The sum
+    // after rebalancing must not exceed the launch allocation (640 x 96): setmaxnreg.inc only
+    // draws from what the CTA's own warps released:  128*40 + 256*88 + 256*128 = 60416 <= 61440.
     if (warp < 4) {
-      reg_dec<80>();
+      reg_dec<40>();
       if (warp == 0) {
         // ---------------- producer: packed frames (hi, unscaled lo) ----------------
         if (lane == 0) {
@@ -734,18 +738,18 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             }
         }
       }
-    } else if (warp < 8) {
-        reg_dec<104>();
-        // ---------------- generators (warps 4..7): A = r (x' - mu') split into hi / lo ----------
-        const int gt = threadIdx.x - 128;    // 0..127
+    } else if (warp < 12) {
+        reg_dec<88>();
+        // ---------------- generators (warps 4..11): A = r (x' - mu') split into hi / lo ---------
+        const int gt = threadIdx.x - 128;    // 0..255
         const int fgroups = MT / 8, kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
         const int n_chunks16 = fgroups * kgD * 8;
         uint32_t g = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            for (int d = gt; d < G.DA; d += 128) mu_s[d] = mu32[(size_t)k * G.DA + d];
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            for (int d = gt; d < G.DA; d += 256) mu_s[d] = mu32[(size_t)k * G.DA + d];
             double nacc = 0.0;
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
@@ -753,21 +757,24 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const long long n = (long long)t * MT + gt;
                     r_s[s * MT + gt] = (n < N) ? (float)respT[(size_t)k * Npad + n] : 0.f;
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (gt == 0)
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (gt == 255)
                     for (int i = 0; i < MT; ++i) nacc += (double)r_s[s * MT + i];
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
-                for (int idx = gt; idx < n_chunks16; idx += 128) {
+                for (int idx = gt; idx < n_chunks16; idx += 256) {
                     const int fr = idx & 7, rest = idx >> 3;
                     const int featg = rest % kgD, fg = rest / kgD;
                     const uint32_t bo = ((uint32_t)(fg * kgB + featg) * 8 + fr) * 16;
                     const uint32_t ao = ((uint32_t)(fg * kgA + featg) * 8 + fr) * 16;
                     const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
                     const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
+                    const float4 ma = *reinterpret_cast<const float4*>(mu_s + featg * 8);
+                    const float4 mb = *reinterpret_cast<const float4*>(mu_s + featg * 8 + 4);
                     const float r = r_s[s * MT + fg * 8 + fr];
+                    const float mu8[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
                     const __half2* hp = reinterpret_cast<const __half2*>(&hv);
                     const __half2* lp = reinterpret_cast<const __half2*>(&lv);
                     uint4 oh, ol;
@@ -776,8 +783,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
-                        const float m0 = mu_s[featg * 8 + 2 * e], m1 = mu_s[featg * 8 + 2 * e + 1];
-                        const float z0 = r * ((xh.x + xl.x) - m0), z1 = r * ((xh.y + xl.y) - m1);
+                        const float z0 = r * ((xh.x + xl.x) - mu8[2 * e]);
+                        const float z1 = r * ((xh.y + xl.y) - mu8[2 * e + 1]);
                         const __half2 zh = __floats2half2_rn(z0, z1);
                         const float2 zf = __half22float2(zh);
                         ohp[e] = zh;
@@ -793,13 +800,13 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
             }
-            if (gt == 0) partial[(size_t)item * G.partial_len + G.partial_len - 1] = nacc;
+            if (gt == 255) npartial[item] = nacc;
         }
     } else {
-        reg_inc<160>();
-        // ---------------- epilogue (warps 8..15): TMEM -> fp32 registers -> fp64 partials ------
+        reg_inc<128>();
+        // ---------------- epilogue (warps 12..19): TMEM -> fp32 registers -> fp64 partials -----
         const uint32_t quarter = (uint32_t)(warp & 3);
-        const int half = (warp - 8) >> 2;
+        const int half = (warp - 12) >> 2;
         const int row = (int)quarter * 32 + lane;
         const int n16_1 = G.N1 / 16, n16_2 = G.N2 / 16;
         const int c1_begin = half == 0 ? 0 : (n16_1 + 1) / 2;
@@ -842,20 +849,19 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + MB_TM_EMPTY + ts);
             }
-            double* out = partial + (size_t)item * G.partial_len;
+            float* out = partial + (size_t)item * G.partial_len;
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
                 if (c1_begin + c < c1_end) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = (double)acc[c][j];
+                        out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = acc[c][j];
                 }
             }
             if (c2_begin < c2_end) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    out[(size_t)128 * G.N1 + (size_t)row * G.N2 + c2_begin * 16 + j] =
-                        (double)acc[5][j];
+                    out[(size_t)128 * G.N1 + (size_t)row * G.N2 + c2_begin * 16 + j] = acc[5][j];
             }
         }
     }
@@ -868,7 +874,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
 // Partials -> the statistics vector kw_gmm_mstep_finalize expects, centred on centres[k]:
 //   n_k,  sum r (x - c_k),  sum r (x - c_k)(x - c_k)^T   (float64, fixed summation order).
 __global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
-                                      const double* __restrict__ partial,
+                                      const float* __restrict__ partial,
+                                      const double* __restrict__ npartial,
                                       const double* __restrict__ xinfo,
                                       const float* __restrict__ mu32,
                                       const double* __restrict__ centres,
@@ -878,13 +885,19 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
     const int k = blockIdx.x;
     for (int e = threadIdx.x; e < G.partial_len; e += blockDim.x) {
         double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c) t += partial[((size_t)c * K + k) * G.partial_len + e];
+        for (int c = 0; c < n_chunks; ++c)
+            t += (double)partial[((size_t)c * K + k) * G.partial_len + e];
         sh[e] = t;
+    }
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int c = 0; c < n_chunks; ++c) t += npartial[(size_t)c * K + k];
+        sh[G.partial_len] = t;
     }
     __syncthreads();
     const double* a1 = sh;
     const double* a2 = sh + 128 * G.N1;
-    const double nk = sh[G.partial_len - 1];
+    const double nk = sh[G.partial_len];
     auto sab = [&](int i, int j) -> double {      // needs i < 128 or j >= 128
         if (i < 128) return a1[i * G.N1 + j];
         return a2[(i - (DP - 128)) * G.N2 + (j - 128)];
@@ -929,7 +942,8 @@ struct TcWorkspace {
     double* lse_partial;
     int32_t* cand;
     float* mu32;
-    double* mpartial;
+    float* mpartial;
+    double* npartial;
     int m_chunks, tiles_per_chunk, n_mtiles;
     size_t bytes;
 };
@@ -979,7 +993,8 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
     w.cand = c.take<int32_t>((size_t)N);
     w.mu32 = c.take<float>((size_t)K * G.DA);
-    w.mpartial = c.take<double>((size_t)w.m_chunks * K * G.partial_len);
+    w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
+    w.npartial = c.take<double>((size_t)w.m_chunks * K);
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -1079,15 +1094,16 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
         const char* f = getenv("KW_TC_MFLUSH");   // tiles accumulated in TMEM between flushes
         if (f != nullptr && atoi(f) > 0) m_flush = atoi(f);
     }
-    tc::mstats_tc_kernel<<<grid, 512, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
+    tc::mstats_tc_kernel<<<grid, 640, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
                                                      w.tiles_per_chunk, w.m_chunks, K, DP, w.xt,
-                                                     resp, w.mu32, w.mpartial, swap_strides,
+                                                     resp, w.mu32, w.mpartial, w.npartial, swap_strides,
                                                      m_flush);
     KW_CUDA_CHECK(cudaGetLastError());
-    const size_t psm = sizeof(double) * (size_t)G.partial_len;
+    const size_t psm = sizeof(double) * ((size_t)G.partial_len + 1);
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_post_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    tc::mstats_tc_post_kernel<<<K, 256, psm, st>>>(K, D, DP, w.m_chunks, w.mpartial, w.xinfo,
+    tc::mstats_tc_post_kernel<<<K, 256, psm, st>>>(K, D, DP, w.m_chunks, w.mpartial, w.npartial,
+                                                   w.xinfo,
                                                    w.mu32, centres, stats);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
