@@ -431,11 +431,28 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const long long n = (long long)tile * TILE_M + row;
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
+            // per-component epilogue constants, prefetched one component ahead
+            float pre[4];
+            double pre_c = 0.0;
+            auto fetch = [&](int k) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = et + 128 * q;
+                    pre[q] = (i < 3 * DP) ? sc[(size_t)k * 3 * DP + i] : 0.f;
+                }
+                if (et < 2) pre_c = cst[2 * k + et];
+            };
+            fetch(0);
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                 float* sk = scl + (size_t)s * 3 * DP;
-                for (int i = et; i < 3 * DP; i += 128) sk[i] = sc[(size_t)k * 3 * DP + i];
-                if (et < 2) cst_s[s * 2 + et] = cst[2 * k + et];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = et + 128 * q;
+                    if (i < 3 * DP) sk[i] = pre[q];
+                }
+                if (et < 2) cst_s[s * 2 + et] = pre_c;
+                if (k + 1 < K) fetch(k + 1);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
                 tc_fence_after();
@@ -751,15 +768,22 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (int d = gt; d < G.DA; d += 256) mu_s[d] = mu32[(size_t)k * G.DA + d];
             double nacc = 0.0;
+            auto load_r = [&](int t) -> float {
+                const long long n = (long long)t * MT + gt;
+                return (gt < MT && t < t1 && n < N) ? (float)respT[(size_t)k * Npad + n] : 0.f;
+            };
+            float r_next = load_r(t0);
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
-                if (gt < MT) {
-                    const long long n = (long long)t * MT + gt;
-                    r_s[s * MT + gt] = (n < N) ? (float)respT[(size_t)k * Npad + n] : 0.f;
+                if (gt < MT) {      // generator warps 0 and 1, all lanes
+                    r_s[s * MT + gt] = r_next;
+                    float rs = r_next;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                    nacc += (double)rs;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (gt == 255)
-                    for (int i = 0; i < MT; ++i) nacc += (double)r_s[s * MT + i];
+                r_next = load_r(t + 1);     // latency hidden behind this tile's generation
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
                 const unsigned char* bh = b_base + s * G.b_stage;
@@ -800,7 +824,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
             }
-            if (gt == 255) npartial[item] = nacc;
+            if (gt == 0 || gt == 32) npartial[(size_t)item * 2 + (gt >> 5)] = nacc;
         }
     } else {
         reg_inc<128>();
@@ -891,7 +915,8 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
     }
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c) t += npartial[(size_t)c * K + k];
+        for (int c = 0; c < n_chunks; ++c)
+            t += npartial[((size_t)c * K + k) * 2] + npartial[((size_t)c * K + k) * 2 + 1];
         sh[G.partial_len] = t;
     }
     __syncthreads();
@@ -994,7 +1019,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.cand = c.take<int32_t>((size_t)N);
     w.mu32 = c.take<float>((size_t)K * G.DA);
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
-    w.npartial = c.take<double>((size_t)w.m_chunks * K);
+    w.npartial = c.take<double>(2 * (size_t)w.m_chunks * K);
     w.bytes = align_up(c.used, 256);
     return w;
 }
