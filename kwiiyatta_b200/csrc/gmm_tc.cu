@@ -387,33 +387,51 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
-            const uint32_t b_lo_addr = smem_u32(b_lo);
+            // Descriptors are built once; an MMA's operands differ from the base only by a byte
+            // offset, i.e. an addition to the (address >> 4) field (the issuing thread is the
+            // critical path of the whole kernel, so nothing else is computed per MMA).
+            const uint64_t d_a_hi = make_desc(smem_u32(a_hi), lbo, sbo_a);
+            const uint64_t d_a_lo = make_desc(smem_u32(a_lo), lbo, sbo_a);
+            const uint64_t d_b_lo = make_desc(smem_u32(b_lo), lbo, sbo);
+            const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), lbo, sbo);
+            const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), lbo, sbo);
+            constexpr uint64_t KSTEP = 256 >> 4;      // 16 fp16 along K = two core matrices
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 for (int k = 0; k < K; ++k) {
                     const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                    const uint32_t b_hi_addr = smem_u32(b_hi0 + (size_t)s * bmat_elems(DP));
+                    const uint64_t d_b_hi = s ? d_b_hi1 : d_b_hi0;
                     const uint32_t acc = tmem_base + s * (uint32_t)DP;
                     mbar_wait(bars + BAR_TM_EMPTY0 + s, (u & 1u) ^ 1u);
                     mbar_wait(bars + BAR_BLO_FULL, g & 1u);
                     if (k == 0) mbar_wait(bars + BAR_A_FULL, (uint32_t)it & 1u);
                     tc_fence_after();
-                    for (int ks = 0; ks < ksteps; ++ks)       // x_hi . l_lo
-                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo_a),
-                                 make_desc(b_lo_addr + ks * 256, lbo, sbo), idesc, ks > 0);
+                    {
+                        uint64_t da = d_a_hi, db = d_b_lo;          // x_hi . l_lo
+                        umma_f16(acc, da, db, idesc, 0u);
+                        for (int ks = 1; ks < ksteps; ++ks) {
+                            da += KSTEP; db += KSTEP;
+                            umma_f16(acc, da, db, idesc, 1u);
+                        }
+                    }
                     umma_commit(bars + BAR_BLO_EMPTY);
                     mbar_wait(bars + BAR_BHI_FULL0 + s, u & 1u);
                     tc_fence_after();
-                    for (int ks = 0; ks < ksteps; ++ks)       // x_lo . l_hi
-                        umma_f16(acc, make_desc(a_lo_addr + ks * 256, lbo, sbo_a),
-                                 make_desc(b_hi_addr + ks * 256, lbo, sbo), idesc, 1u);
-                    // acc = acc * 2^-11 + x_hi . l_hi
-                    umma_f16_scaled(acc, make_desc(a_hi_addr, lbo, sbo_a),
-                                    make_desc(b_hi_addr, lbo, sbo), idesc);
-                    for (int ks = 1; ks < ksteps; ++ks)
-                        umma_f16(acc, make_desc(a_hi_addr + ks * 256, lbo, sbo_a),
-                                 make_desc(b_hi_addr + ks * 256, lbo, sbo), idesc, 1u);
+                    {
+                        uint64_t da = d_a_lo, db = d_b_hi;          // x_lo . l_hi
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            umma_f16(acc, da, db, idesc, 1u);
+                            da += KSTEP; db += KSTEP;
+                        }
+                    }
+                    {
+                        uint64_t da = d_a_hi, db = d_b_hi;          // acc = acc * 2^-11 + x_hi . l_hi
+                        umma_f16_scaled(acc, da, db, idesc);
+                        for (int ks = 1; ks < ksteps; ++ks) {
+                            da += KSTEP; db += KSTEP;
+                            umma_f16(acc, da, db, idesc, 1u);
+                        }
+                    }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
                 }
@@ -636,7 +654,8 @@ __global__ void __launch_bounds__(640, 1)
 mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
                  const float* __restrict__ mu32, float* __restrict__ partial,
-                 double* __restrict__ npartial, int swap_strides, int M_FLUSH) {
+                 double* __restrict__ npartial, int swap_strides, int M_FLUSH,
+                 unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     unsigned char* b_base = smem + G.off_b;
@@ -711,8 +730,24 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             const uint32_t idesc1 = make_idesc_mn(128, G.N1);
             const uint32_t idesc2 = make_idesc_mn(128, G.N2 > 0 ? G.N2 : 16);
             // MN-major, no swizzle: SBO = stride between 8-element groups along M/N (features),
-            // LBO = stride between 8-frame groups along K.
-            uint32_t sbo = 128, lbo_a = (uint32_t)(G.DA / 8) * 128, lbo_b = (uint32_t)(G.DPB / 8) * 128;
+            // LBO = stride between 8-frame groups along K.  Base descriptors per stage and part;
+            // per MMA only an offset is added to the address field.
+            const uint32_t sbo = 128, lbo_a = (uint32_t)(G.DA / 8) * 128,
+                           lbo_b = (uint32_t)(G.DPB / 8) * 128;
+            uint64_t d_a[2][2], d_b[2][2];      // [stage][0 = hi, 1 = lo]
+#pragma unroll
+            for (int st = 0; st < 2; ++st)
+#pragma unroll
+                for (int pt = 0; pt < 2; ++pt) {
+                    d_a[st][pt] = make_desc(smem_u32(a_base + st * G.a_stage + pt * part_a), lbo_a, sbo);
+                    d_b[st][pt] = make_desc(smem_u32(b_base + st * G.b_stage + pt * part_b), lbo_b, sbo);
+                }
+            const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
+            const uint64_t win_a = (uint64_t)(G.a_win2 * 128) >> 4, win_b = (16 * 128) >> 4;
+            const bool has2 = G.N2 > 0;
+            (void)swap_strides;
+            long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
+            const long long p_start = clock64();
             uint32_t g = 0, f = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int k, t0, t1;
@@ -722,36 +757,45 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const int in_group = (t - t0) % M_FLUSH;
                     const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
                     const uint32_t ts = f & 1u, tu = f >> 1;
+                    const long long c0 = clock64();
                     if (in_group == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
+                    const long long c1 = clock64();
                     mbar_wait(bars + MB_A_FULL + s, u & 1u);
+                    const long long c2 = clock64();
                     mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                    const long long c3 = clock64();
+                    p_tm += c1 - c0; p_a += c2 - c1; p_b += c3 - c2;
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_base + s * G.a_stage);
-                    const uint32_t b_addr = smem_u32(b_base + s * G.b_stage);
                     const uint32_t acc1 = tmem_base + ts * acc_cols;
                     const uint32_t acc2 = acc1 + (uint32_t)G.N1;
+                    const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
+                    const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
+#pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t ap = a_addr + (pass == 2 ? part_a : 0u);   // A lo in pass 2
-                        const uint32_t bp = b_addr + (pass == 1 ? part_b : 0u);   // B lo in pass 1
+                        uint64_t da = (pass == 2) ? a_lo_d : a_hi_d;     // A lo in pass 2
+                        uint64_t db = (pass == 1) ? b_lo_d : b_hi_d;     // B lo in pass 1
+#pragma unroll
                         for (int ks = 0; ks < MT / 16; ++ks) {
-                            const uint32_t accum = (in_group > 0 || pass > 0 || ks > 0) ? 1u : 0u;
-                            const uint32_t ao = ap + ks * 2 * lbo_a, bo = bp + ks * 2 * lbo_b;
-                            uint64_t da, db;
-                            if (!swap_strides) { da = make_desc(ao, lbo_a, sbo); db = make_desc(bo, lbo_b, sbo); }
-                            else               { da = make_desc(ao, sbo, lbo_a); db = make_desc(bo, sbo, lbo_b); }
+                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (in_group > 0 ? 1u : 0u);
                             umma_f16(acc1, da, db, idesc1, accum);
-                            if (G.N2 > 0) {
-                                const uint32_t ao2 = ao + G.a_win2 * sbo, bo2 = bo + 16 * sbo;
-                                if (!swap_strides) { da = make_desc(ao2, lbo_a, sbo); db = make_desc(bo2, lbo_b, sbo); }
-                                else               { da = make_desc(ao2, sbo, lbo_a); db = make_desc(bo2, sbo, lbo_b); }
-                                umma_f16(acc2, da, db, idesc2, accum);
-                            }
+                            if (has2) umma_f16(acc2, da + win_a, db + win_b, idesc2, accum);
+                            da += step_a;
+                            db += step_b;
                         }
                     }
                     umma_commit(bars + MB_A_EMPTY + s);
                     umma_commit(bars + MB_B_EMPTY + s);
                     if (last) { umma_commit(bars + MB_TM_FULL + ts); ++f; }
+                    p_issue += clock64() - c3;
                 }
+            }
+            if (prof != nullptr && blockIdx.x == 0) {
+                prof[0] = (unsigned long long)(clock64() - p_start);
+                prof[1] = (unsigned long long)p_tm;
+                prof[2] = (unsigned long long)p_a;
+                prof[3] = (unsigned long long)p_b;
+                prof[4] = (unsigned long long)p_issue;
+                prof[5] = g;
             }
         }
       }
@@ -761,43 +805,63 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         const int gt = threadIdx.x - 128;    // 0..255
         const int fgroups = MT / 8, kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
         const int n_chunks16 = fgroups * kgD * 8;
+        // The 16-byte chunks (8 features of one frame) this thread converts are the same for every
+        // tile: decode them once (no integer division in the tile loop).
+        constexpr int QMAX = 5;
+        uint32_t c_bo[QMAX], c_ao[QMAX];
+        int c_r[QMAX], c_mu[QMAX];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            const int idx = gt + 256 * q;
+            const int fr = idx & 7, rest = idx >> 3;
+            const int featg = rest % kgD, fg = rest / kgD;
+            c_bo[q] = ((uint32_t)(fg * kgB + featg) * 8 + fr) * 16;
+            c_ao[q] = ((uint32_t)(fg * kgA + featg) * 8 + fr) * 16;
+            c_r[q] = (idx < n_chunks16) ? fg * 8 + fr : -1;
+            c_mu[q] = featg * 8;
+        }
         uint32_t g = 0;
+        long long g_b = 0, g_a = 0, g_gen = 0;
+        const long long g_start = clock64();
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (int d = gt; d < G.DA; d += 256) mu_s[d] = mu32[(size_t)k * G.DA + d];
             double nacc = 0.0;
-            auto load_r = [&](int t) -> float {
+            auto load_r = [&](int t) -> double {
                 const long long n = (long long)t * MT + gt;
-                return (gt < MT && t < t1 && n < N) ? (float)respT[(size_t)k * Npad + n] : 0.f;
+                return (gt < MT && t < t1 && n < N) ? respT[(size_t)k * Npad + n] : 0.0;
             };
-            float r_next = load_r(t0);
+            double r_next = load_r(t0);
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
                 if (gt < MT) {      // generator warps 0 and 1, all lanes
-                    r_s[s * MT + gt] = r_next;
-                    float rs = r_next;
+                    float rs = (float)r_next;
+                    r_s[s * MT + gt] = rs;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
                     nacc += (double)rs;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                r_next = load_r(t + 1);     // latency hidden behind this tile's generation
+                r_next = load_r(t + 1);     // consumed next iteration: latency hidden
+                const long long c0 = clock64();
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                const long long c1 = clock64();
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
+                const long long c2 = clock64();
+                g_b += c1 - c0; g_a += c2 - c1;
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
-                for (int idx = gt; idx < n_chunks16; idx += 256) {
-                    const int fr = idx & 7, rest = idx >> 3;
-                    const int featg = rest % kgD, fg = rest / kgD;
-                    const uint32_t bo = ((uint32_t)(fg * kgB + featg) * 8 + fr) * 16;
-                    const uint32_t ao = ((uint32_t)(fg * kgA + featg) * 8 + fr) * 16;
-                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
-                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
-                    const float4 ma = *reinterpret_cast<const float4*>(mu_s + featg * 8);
-                    const float4 mb = *reinterpret_cast<const float4*>(mu_s + featg * 8 + 4);
-                    const float r = r_s[s * MT + fg * 8 + fr];
+                const float* rt = r_s + s * MT;
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) {
+                    if (c_r[q] < 0) continue;
+                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + c_bo[q]);
+                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + c_bo[q]);
+                    const float4 ma = *reinterpret_cast<const float4*>(mu_s + c_mu[q]);
+                    const float4 mb = *reinterpret_cast<const float4*>(mu_s + c_mu[q] + 4);
+                    const float r = rt[c_r[q]];
                     const float mu8[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
                     const __half2* hp = reinterpret_cast<const __half2*>(&hv);
                     const __half2* lp = reinterpret_cast<const __half2*>(&lv);
@@ -814,8 +878,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         ohp[e] = zh;
                         olp[e] = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
                     }
-                    *reinterpret_cast<uint4*>(ah + ao) = oh;
-                    *reinterpret_cast<uint4*>(ah + part_a + ao) = ol;
+                    *reinterpret_cast<uint4*>(ah + c_ao[q]) = oh;
+                    *reinterpret_cast<uint4*>(ah + part_a + c_ao[q]) = ol;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -823,8 +887,15 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_A_FULL + s);
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
+                g_gen += clock64() - c2;
             }
             if (gt == 0 || gt == 32) npartial[(size_t)item * 2 + (gt >> 5)] = nacc;
+        }
+        if (prof != nullptr && blockIdx.x == 0 && gt == 64) {
+            prof[8] = (unsigned long long)(clock64() - g_start);
+            prof[9] = (unsigned long long)g_b;
+            prof[10] = (unsigned long long)g_a;
+            prof[11] = (unsigned long long)g_gen;
         }
     } else {
         reg_inc<128>();
@@ -1119,10 +1190,23 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
         const char* f = getenv("KW_TC_MFLUSH");   // tiles accumulated in TMEM between flushes
         if (f != nullptr && atoi(f) > 0) m_flush = atoi(f);
     }
+    static unsigned long long* prof_dev = nullptr;
+    static int prof_on = -1;
+    if (prof_on < 0) {
+        prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
+        if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
+    }
     tc::mstats_tc_kernel<<<grid, 640, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
                                                      w.tiles_per_chunk, w.m_chunks, K, DP, w.xt,
                                                      resp, w.mu32, w.mpartial, w.npartial, swap_strides,
-                                                     m_flush);
+                                                     m_flush, prof_on ? prof_dev : nullptr);
+    if (prof_on) {
+        unsigned long long h[16];
+        cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[mstats_tc cta0] mma: total %llu wait_tmem %llu wait_a %llu wait_b %llu "
+                        "issue %llu tiles %llu | gen: total %llu wait_b %llu wait_a %llu work %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11]);
+    }
     KW_CUDA_CHECK(cudaGetLastError());
     const size_t psm = sizeof(double) * ((size_t)G.partial_len + 1);
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_post_kernel,
