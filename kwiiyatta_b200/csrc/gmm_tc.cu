@@ -172,7 +172,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __host__ __device__ inline int dpb_of(int DP) { return DP + 16; }
 __host__ __device__ inline size_t tile_elems(int DP) { return (size_t)TILE_M * dpb_of(DP); }
 constexpr int X_PARTS = 3;
-__host__ __device__ inline size_t bmat_elems(int DP) { return (size_t)DP * DP; }
+// L_k is upper triangular, so B[j][d] = L[d][j] vanishes for j < d.  B is stored per 16-wide
+// k-step: block ks holds the row groups jg >= 2*ks only, each as two adjacent 8x8 core matrices
+// (LBO = 128 B between them, SBO = 256 B between row groups).  Offsets in halves.
+__host__ __device__ inline size_t btri_off(int DP, int ks) {
+    const int ng = DP / 8;
+    return (size_t)128 * (size_t)(ng * ks - ks * (ks - 1));
+}
+__host__ __device__ inline size_t bmat_elems(int DP) { return btri_off(DP, DP / 16); }
 
 // ------------------------------------------------------------------------------------------
 // Column statistics of X: partial sums / min / max per chunk, then centre and power-of-two scale.
@@ -291,12 +298,14 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
     __syncthreads();
     __half* hi = bt + (size_t)k * 2 * bmat_elems(DP);
     __half* lo = hi + bmat_elems(DP);
-    const int kg_n = DP / 8;
     for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
         const int j = e / DP, d = e - j * DP;
+        const int ks = d >> 4, jg = j >> 3;
+        if (jg < 2 * ks) continue;             // structurally zero block: not stored
         double v = 0.0;
         if (j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * colinv[j];
-        const size_t o = ((size_t)(j >> 3) * kg_n + (d >> 3)) * 64 + (j & 7) * 8 + (d & 7);
+        const size_t o = btri_off(DP, ks) + ((size_t)(jg - 2 * ks) * 2 + ((d >> 3) & 1)) * 64 +
+                         (j & 7) * 8 + (d & 7);
         split_store(v, hi + o, lo + o);
     }
 }
@@ -306,16 +315,17 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
 // ------------------------------------------------------------------------------------------
 struct EstepSmem {
     // byte offsets into dynamic shared memory
-    uint32_t a, b_hi, b_lo, scl, cst, bars, tmem_ptr, total;
+    uint32_t a, b_hi, b_lo, scl, cst, qpart, bars, tmem_ptr, total;
 };
 __host__ __device__ inline EstepSmem estep_smem(int DP) {
     EstepSmem s;
     uint32_t o = 0;
     s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
-    s.b_hi = o;  o += 2u * DP * DP * 2;                // two stages
-    s.b_lo = o;  o += (uint32_t)DP * DP * 2;
+    s.b_hi = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
+    s.b_lo = o;  o += (uint32_t)bmat_elems(DP) * 2;
     s.scl = o;   o += 2u * 3 * DP * 4;                 // two stages of [scale | b' hi | b' lo]
     s.cst = o;   o += 2u * 2 * 8;
+    s.qpart = o; o += 2u * TILE_M * 8;
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
     s.total = o;
@@ -325,7 +335,7 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
 enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL, BAR_BLO_EMPTY, BAR_BHI_FULL0, BAR_BHI_FULL1,
        BAR_BHI_EMPTY0, BAR_BHI_EMPTY1, BAR_TM_FULL0, BAR_TM_FULL1, BAR_TM_EMPTY0, BAR_TM_EMPTY1 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
                 const float* __restrict__ sc, const double* __restrict__ cst,
@@ -339,19 +349,20 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     __half* b_lo = reinterpret_cast<__half*>(smem + L.b_lo);
     float* scl = reinterpret_cast<float*>(smem + L.scl);
     double* cst_s = reinterpret_cast<double*>(smem + L.cst);
+    double* qpart = reinterpret_cast<double*>(smem + L.qpart);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t a_bytes = 2u * TILE_M * dpb_of(DP) * 2;
-    const uint32_t b_bytes = (uint32_t)DP * DP * 2;
-    const uint32_t lbo = 128, sbo = (uint32_t)(DP / 8) * 128;
+    const uint32_t b_bytes = (uint32_t)bmat_elems(DP) * 2;
+    const uint32_t lbo = 128;
     const uint32_t sbo_a = (uint32_t)(dpb_of(DP) / 8) * 128;
     const int ksteps = DP / 16;
     const uint32_t idesc = make_idesc(TILE_M, DP);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 12; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 4u : 1u);
+        for (int i = 0; i < 12; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 8u : 1u);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
@@ -392,10 +403,13 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             // critical path of the whole kernel, so nothing else is computed per MMA).
             const uint64_t d_a_hi = make_desc(smem_u32(a_hi), lbo, sbo_a);
             const uint64_t d_a_lo = make_desc(smem_u32(a_lo), lbo, sbo_a);
-            const uint64_t d_b_lo = make_desc(smem_u32(b_lo), lbo, sbo);
-            const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), lbo, sbo);
-            const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), lbo, sbo);
-            constexpr uint64_t KSTEP = 256 >> 4;      // 16 fp16 along K = two core matrices
+            const uint64_t d_b_lo = make_desc(smem_u32(b_lo), 128, 256);
+            const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), 128, 256);
+            const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), 128, 256);
+            constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
+            // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
+            //   N = DP - 16 ks, B block at btri_off(ks), accumulator columns from 16 ks.
+            const uint32_t ng = (uint32_t)DP / 8;
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 for (int k = 0; k < K; ++k) {
@@ -408,10 +422,13 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     tc_fence_after();
                     {
                         uint64_t da = d_a_hi, db = d_b_lo;          // x_hi . l_lo
-                        umma_f16(acc, da, db, idesc, 0u);
-                        for (int ks = 1; ks < ksteps; ++ks) {
-                            da += KSTEP; db += KSTEP;
-                            umma_f16(acc, da, db, idesc, 1u);
+                        uint32_t id = idesc, cols = (uint32_t)DP;
+                        for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
+                            umma_f16(acc + 16 * ks, da, db, id, ks > 0 ? 1u : 0u);
+                            da += KSTEP;
+                            db += (uint64_t)(ng - 2 * ks) * 16;      // next block: (ng-2ks)*256 B
+                            cols -= 16;
+                            id = make_idesc(TILE_M, (int)cols);
                         }
                     }
                     umma_commit(bars + BAR_BLO_EMPTY);
@@ -419,17 +436,24 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     tc_fence_after();
                     {
                         uint64_t da = d_a_lo, db = d_b_hi;          // x_lo . l_hi
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            umma_f16(acc, da, db, idesc, 1u);
-                            da += KSTEP; db += KSTEP;
+                        uint32_t id = idesc, cols = (uint32_t)DP;
+                        for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
+                            umma_f16(acc + 16 * ks, da, db, id, 1u);
+                            da += KSTEP;
+                            db += (uint64_t)(ng - 2 * ks) * 16;
+                            cols -= 16;
+                            id = make_idesc(TILE_M, (int)cols);
                         }
                     }
                     {
                         uint64_t da = d_a_hi, db = d_b_hi;          // acc = acc * 2^-11 + x_hi . l_hi
-                        umma_f16_scaled(acc, da, db, idesc);
-                        for (int ks = 1; ks < ksteps; ++ks) {
-                            da += KSTEP; db += KSTEP;
-                            umma_f16(acc, da, db, idesc, 1u);
+                        umma_f16_scaled(acc, da, db, idesc);        // ks = 0 spans every column
+                        uint32_t cols = (uint32_t)DP;
+                        for (uint32_t ks = 1; ks < (uint32_t)ksteps; ++ks) {
+                            da += KSTEP;
+                            db += (uint64_t)(ng - 2 * (ks - 1)) * 16;
+                            cols -= 16;
+                            umma_f16(acc + 16 * ks, da, db, make_idesc(TILE_M, (int)cols), 1u);
                         }
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
@@ -439,10 +463,15 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             }
         }
     } else {
-        // ---------------- epilogue (warps 2..5) ----------------
-        const int et = threadIdx.x - 64;            // 0..127
+        // ---------------- epilogue (warps 2..9) ----------------
+        // Two warps per TMEM lane quarter: each takes half of the accumulator columns; the
+        // second half's partial q goes through shared memory to the first, which finishes.
+        const int et = threadIdx.x - 64;            // 0..255
         const uint32_t quarter = (uint32_t)(warp & 3);
+        const int half = (warp - 2) >> 2;
         const int row = (int)quarter * 32 + lane;   // TMEM lane = row of the tile
+        const int c_begin = half == 0 ? 0 : (ksteps + 1) / 2;
+        const int c_end = half == 0 ? (ksteps + 1) / 2 : ksteps;
         const double LOG2PI = 1.8378770664093453;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -450,12 +479,12 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
             // per-component epilogue constants, prefetched one component ahead
-            float pre[4];
+            float pre[2];
             double pre_c = 0.0;
             auto fetch = [&](int k) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = et + 128 * q;
+                for (int q = 0; q < 2; ++q) {
+                    const int i = et + 256 * q;
                     pre[q] = (i < 3 * DP) ? sc[(size_t)k * 3 * DP + i] : 0.f;
                 }
                 if (et < 2) pre_c = cst[2 * k + et];
@@ -465,43 +494,64 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                 float* sk = scl + (size_t)s * 3 * DP;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = et + 128 * q;
+                for (int q = 0; q < 2; ++q) {
+                    const int i = et + 256 * q;
                     if (i < 3 * DP) sk[i] = pre[q];
                 }
                 if (et < 2) cst_s[s * 2 + et] = pre_c;
                 if (k + 1 < K) fetch(k + 1);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * (uint32_t)DP;
                 double q = 0.0;
-                for (int c = 0; c < ksteps; ++c) {
-                    uint32_t v[16];
+                for (int c = c_begin; c < c_end; c += 2) {
+                    uint32_t v[32];
+                    const bool two = c + 1 < c_end;
                     tmem_ld16(taddr + c * 16, v);
+                    if (two) tmem_ld16(taddr + (c + 1) * 16, v + 16);
                     tmem_ld_wait();
-                    float part = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float y = fmaf(__uint_as_float(v[j]), sk[c * 16 + j],
-                                             -sk[DP + c * 16 + j]) - sk[2 * DP + c * 16 + j];
-                        part = fmaf(y, y, part);
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !two) break;
+                        const float* sc_p = sk + (c + h) * 16;
+                        float part = 0.f;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 cs = *reinterpret_cast<const float4*>(sc_p + 4 * j4);
+                            const float4 bh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
+                            const float4 bl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
+                            const float y0 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 0]), cs.x, -bh.x) - bl.x;
+                            const float y1 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 1]), cs.y, -bh.y) - bl.y;
+                            const float y2 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 2]), cs.z, -bh.z) - bl.z;
+                            const float y3 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 3]), cs.w, -bh.w) - bl.w;
+                            part = fmaf(y0, y0, part);
+                            part = fmaf(y1, y1, part);
+                            part = fmaf(y2, y2, part);
+                            part = fmaf(y3, y3, part);
+                        }
+                        q += (double)part;
                     }
-                    q += (double)part;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                const double wlp = (-0.5 * ((double)D * LOG2PI + q) + cst_s[s * 2]) + cst_s[s * 2 + 1];
-                if (mode == 0) {
-                    if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
-                } else if (wlp > v1) {
-                    v2 = v1; k2 = k1; v1 = wlp; k1 = k;
-                } else if (wlp > v2) {
-                    v2 = wlp; k2 = k;
+                if (half == 1) qpart[s * TILE_M + row] = q;
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (half == 0) {
+                    q += qpart[s * TILE_M + row];
+                    const double wlp =
+                        (-0.5 * ((double)D * LOG2PI + q) + cst_s[s * 2]) + cst_s[s * 2 + 1];
+                    if (mode == 0) {
+                        if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
+                    } else if (wlp > v1) {
+                        v2 = v1; k2 = k1; v1 = wlp; k1 = k;
+                    } else if (wlp > v2) {
+                        v2 = wlp; k2 = k;
+                    }
                 }
             }
-            if (mode == 1 && n < N) {
+            if (half == 0 && mode == 1 && n < N) {
                 mix[n] = k1;
                 cand[n] = (K > 1 && v1 - v2 < near_tie) ? k2 : -1;   // runner-up to re-check in fp64
             }
@@ -1152,7 +1202,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     uint32_t cols = 32;
     while (cols < 2u * DP) cols <<= 1;
     const int grid = (int)std::min<long long>(n_tiles, sms);
-    tc::estep_tc_kernel<<<grid, 192, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
+    tc::estep_tc_kernel<<<grid, 320, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
                                                     w.bt, w.sc, w.cst, resp, mode, mix, w.cand,
                                                     0.05);
     KW_CUDA_CHECK(cudaGetLastError());
