@@ -445,34 +445,51 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
     }
     if (tid == 0) sh_fail = 0;
     __syncthreads();
-    // left-looking Cholesky, thread i owns row i (D <= 256)
-    const int i = tid;
-    for (int j = 0; j < D; ++j) {
-        double s = 0.0;
-        if (i >= j && i < D) {
-            s = A[i * S + j];
-            for (int p = 0; p < j; ++p) s = fma(-A[i * S + p], A[j * S + p], s);
-        }
-        if (i == j) {
-            if (!(s > 0.0)) {
-                if (sh_fail == 0) sh_fail = j + 1;
-                s = 1.0;
+    // right-looking Cholesky over the lower triangle with all 256 threads (16 x 16 mapping of
+    // the trailing update); per element the products are subtracted in ascending column order,
+    // i.e. the same arithmetic as a left-looking sweep.
+    {
+        const int ty = tid >> 4, tx = tid & 15;
+        for (int j = 0; j < D; ++j) {
+            if (tid == 0) {
+                double s = A[j * S + j];
+                if (!(s > 0.0)) {
+                    if (sh_fail == 0) sh_fail = j + 1;
+                    s = 1.0;
+                }
+                sh_piv = sqrt(s);
+                A[j * S + j] = sh_piv;
             }
-            sh_piv = sqrt(s);
-            A[j * S + j] = sh_piv;
+            __syncthreads();
+            const double piv = sh_piv;
+            for (int i = j + 1 + tid; i < D; i += 256) A[i * S + j] = A[i * S + j] / piv;
+            __syncthreads();
+            for (int l = j + 1 + ty; l < D; l += 16) {
+                const double clj = A[l * S + j];
+                for (int i = l + tx; i < D; i += 16)
+                    A[i * S + l] = fma(-A[i * S + j], clj, A[i * S + l]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (i > j && i < D) A[i * S + j] = s / sh_piv;
-        __syncthreads();
     }
-    // Z = C^-1 (lower); store Z^T in the strict upper triangle: A[c][i] = Z[i][c], i > c.
-    if (tid < D) {
-        const int c = tid;
-        const double zcc = 1.0 / A[c * S + c];
-        for (int r = c + 1; r < D; ++r) {
-            double s = A[r * S + c] * zcc;  // C[r][c] * z_c
-            for (int p = c + 1; p < r; ++p) s = fma(A[r * S + p], A[c * S + p], s);
-            A[c * S + r] = -s / A[r * S + r];
+    // Z = C^-1 (lower); store Z^T in the strict upper triangle: A[c][r] = Z[r][c], r > c.
+    // Columns 0..111 (the long ones) are shared by two adjacent lanes that split the dot product
+    // by parity of p; columns 112.. get one thread each.
+    {
+        int c, h, nth;
+        if (tid < 224) { c = tid >> 1; h = tid & 1; nth = 2; }
+        else { c = 112 + (tid - 224); h = 0; nth = 1; }
+        const bool active = c < D;
+        const double zcc = active ? 1.0 / A[c * S + c] : 0.0;
+        for (int r = 1; r < D; ++r) {
+            double s = 0.0;
+            if (active && r > c) {
+                if (h == 0) s = A[r * S + c] * zcc;                       // p = c
+                for (int p = c + 1 + h; p < r; p += nth) s = fma(A[r * S + p], A[c * S + p], s);
+            }
+            if (tid < 224) s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (active && r > c && h == 0) A[c * S + r] = -s / A[r * S + r];
+            __syncwarp();
         }
     }
     __syncthreads();

@@ -1016,31 +1016,36 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// Partials -> the statistics vector kw_gmm_mstep_finalize expects, centred on centres[k]:
-//   n_k,  sum r (x - c_k),  sum r (x - c_k)(x - c_k)^T   (float64, fixed summation order).
-__global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
-                                      const float* __restrict__ partial,
-                                      const double* __restrict__ npartial,
+// Fixed-order sum of the per-chunk partials: raw[k][e], e < partial_len, then n_k at [partial_len].
+__global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
+                                        const float* __restrict__ partial,
+                                        const double* __restrict__ npartial,
+                                        double* __restrict__ raw) {
+    const int k = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < partial_len) {
+        double t = 0.0;
+        for (int c = 0; c < n_chunks; ++c)
+            t += (double)partial[((size_t)c * K + k) * partial_len + e];
+        raw[(size_t)k * (partial_len + 1) + e] = t;
+    } else if (e == partial_len) {
+        double t = 0.0;
+        for (int c = 0; c < n_chunks; ++c)
+            t += npartial[((size_t)c * K + k) * 2] + npartial[((size_t)c * K + k) * 2 + 1];
+        raw[(size_t)k * (partial_len + 1) + e] = t;
+    }
+}
+
+// Raw sums -> the statistics vector kw_gmm_mstep_finalize expects, centred on centres[k]:
+//   n_k,  sum r (x - c_k),  sum r (x - c_k)(x - c_k)^T   (float64).  grid (K, slices).
+__global__ void mstats_tc_post_kernel(int K, int D, int DP, const double* __restrict__ raw,
                                       const double* __restrict__ xinfo,
                                       const float* __restrict__ mu32,
                                       const double* __restrict__ centres,
                                       double* __restrict__ stats) {
-    extern __shared__ double sh[];      // raw sums of one component: partial_len doubles
     const MstepGeom G = mstep_geom(DP);
     const int k = blockIdx.x;
-    for (int e = threadIdx.x; e < G.partial_len; e += blockDim.x) {
-        double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c)
-            t += (double)partial[((size_t)c * K + k) * G.partial_len + e];
-        sh[e] = t;
-    }
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c)
-            t += npartial[((size_t)c * K + k) * 2] + npartial[((size_t)c * K + k) * 2 + 1];
-        sh[G.partial_len] = t;
-    }
-    __syncthreads();
+    const double* sh = raw + (size_t)k * (G.partial_len + 1);
     const double* a1 = sh;
     const double* a2 = sh + 128 * G.N1;
     const double nk = sh[G.partial_len];
@@ -1058,10 +1063,11 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, int n_chunks,
     auto eoff = [&](int d) -> double {
         return (xinfo[d] + xinfo[DP + d] * (double)muk[d]) - ck[d];
     };
-    if (threadIdx.x == 0) st[0] = nk;
-    for (int i = threadIdx.x; i < D; i += blockDim.x)
+    const int tid = blockIdx.y * blockDim.x + threadIdx.x, nthr = gridDim.y * blockDim.x;
+    if (tid == 0) st[0] = nk;
+    for (int i = tid; i < D; i += nthr)
         st[1 + i] = xinfo[DP + i] * mc(i) + nk * eoff(i);
-    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    for (int e = tid; e < D * D; e += nthr) {
         const int i = e / D, j = e - i * D;
         const bool ok_ij = (i < 128) || (j >= 128), ok_ji = (j < 128) || (i >= 128);
         double v;
@@ -1090,6 +1096,7 @@ struct TcWorkspace {
     float* mu32;
     float* mpartial;
     double* npartial;
+    double* mraw;
     int m_chunks, tiles_per_chunk, n_mtiles;
     size_t bytes;
 };
@@ -1141,6 +1148,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.mu32 = c.take<float>((size_t)K * G.DA);
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
     w.npartial = c.take<double>(2 * (size_t)w.m_chunks * K);
+    w.mraw = c.take<double>((size_t)K * (G.partial_len + 1));
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -1258,12 +1266,11 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
                 h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11]);
     }
     KW_CUDA_CHECK(cudaGetLastError());
-    const size_t psm = sizeof(double) * ((size_t)G.partial_len + 1);
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_post_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    tc::mstats_tc_post_kernel<<<K, 256, psm, st>>>(K, D, DP, w.m_chunks, w.mpartial, w.npartial,
-                                                   w.xinfo,
-                                                   w.mu32, centres, stats);
+    tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
+        K, G.partial_len, w.m_chunks, w.mpartial, w.npartial, w.mraw);
+    KW_CUDA_CHECK(cudaGetLastError());
+    tc::mstats_tc_post_kernel<<<dim3(K, 8), 256, 0, st>>>(K, D, DP, w.mraw, w.xinfo, w.mu32,
+                                                          centres, stats);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
