@@ -103,44 +103,105 @@ __global__ void convert_regress_kernel(int K, int Dh, int diff, const double* __
     }
 }
 
-// E[t][r] = offset[m][r] + sum_c A^T[m][c][r] x[t][c].  CTA = 8 frames; runs of equal mixture
-// share the loads of A^T.
-constexpr int C_FT = 8;
-__global__ void __launch_bounds__(128)
-convert_condmean_kernel(long long N, int Dh, const double* __restrict__ src,
-                        const int32_t* __restrict__ mix, PreparedView v,
-                        double* __restrict__ E) {
-    extern __shared__ double xs[];  // C_FT * Dh
-    __shared__ int ms[C_FT];
-    const long long n0 = (long long)blockIdx.x * C_FT;
-    for (int e = threadIdx.x; e < C_FT * Dh; e += blockDim.x) {
-        const long long n = n0 + e / Dh;
-        xs[e] = (n < N) ? src[n * Dh + (e % Dh)] : 0.0;
-    }
-    if (threadIdx.x < C_FT) ms[threadIdx.x] = (n0 + threadIdx.x < N) ? mix[n0 + threadIdx.x] : -1;
+// Conditional means E[t] = offset[m_t] + A[m_t] x[t], grouped by mixture: a counting sort of the
+// frames by hard label (histogram, scan, scatter), then one CTA per (mixture, 64 frames of it)
+// with A^T of that mixture and the frames staged in shared memory.
+constexpr int CM_FT = 64;
+
+__global__ void convert_hist_kernel(long long N, int K, const int32_t* __restrict__ mix,
+                                    int* __restrict__ counts) {
+    extern __shared__ int h[];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const int r = threadIdx.x;
-    if (r >= Dh) return;
-    int f0 = 0;
-    while (f0 < C_FT && ms[f0] >= 0) {
-        const int m = ms[f0];
-        int f1 = f0 + 1;
-        while (f1 < C_FT && ms[f1] == m) ++f1;
-        const double* at = v.at + (size_t)m * Dh * Dh;
-        double acc[C_FT];
-        const double off = v.offset[(size_t)m * Dh + r];
-#pragma unroll
-        for (int q = 0; q < C_FT; ++q) acc[q] = 0.0;
-        for (int c = 0; c < Dh; ++c) {
-            const double a = at[(size_t)c * Dh + r];
-#pragma unroll
-            for (int q = 0; q < C_FT; ++q)
-                if (f0 + q < f1) acc[q] = fma(a, xs[(f0 + q) * Dh + c], acc[q]);
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+         n += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&h[mix[n]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        if (h[i] != 0) atomicAdd(&counts[i], h[i]);
+}
+
+// offsets[m] = first slot of mixture m in the sorted order; blockstart[m] = first CTA of it.
+__global__ void convert_scan_kernel(int K, const int* __restrict__ counts, int* __restrict__ offsets,
+                                    int* __restrict__ blockstart, int* __restrict__ cursor) {
+    if (threadIdx.x == 0) {
+        int o = 0, b = 0;
+        for (int m = 0; m < K; ++m) {
+            offsets[m] = o;
+            blockstart[m] = b;
+            cursor[m] = 0;
+            o += counts[m];
+            b += (counts[m] + CM_FT - 1) / CM_FT;
         }
+        offsets[K] = o;
+        blockstart[K] = b;
+    }
+}
+
+__global__ void convert_scatter_kernel(long long N, const int32_t* __restrict__ mix,
+                                       const int* __restrict__ offsets, int* __restrict__ cursor,
+                                       int* __restrict__ order) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m = mix[n];
+    order[offsets[m] + atomicAdd(&cursor[m], 1)] = (int)n;
+}
+
+__global__ void __launch_bounds__(256)
+convert_condmean_kernel(int K, int Dh, const double* __restrict__ src,
+                        const int* __restrict__ offsets, const int* __restrict__ blockstart,
+                        const int* __restrict__ order, PreparedView v, double* __restrict__ E) {
+    extern __shared__ double sm[];
+    const int XS = Dh + 1;
+    double* as = sm;                    // Dh * Dh : A^T[c][r]
+    double* xs = as + Dh * Dh;          // CM_FT * XS
+    __shared__ int idx[CM_FT];
+    if ((int)blockIdx.x >= blockstart[K]) return;
+    int lo = 0, hi = K;                 // mixture with blockstart[m] <= blockIdx.x < blockstart[m+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blockstart[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const int m = lo;
+    const int first = offsets[m] + ((int)blockIdx.x - blockstart[m]) * CM_FT;
+    const int count = min(CM_FT, offsets[m + 1] - first);
+    const int tid = threadIdx.x;
+    if (tid < CM_FT) idx[tid] = tid < count ? order[first + tid] : -1;
+    const double* at = v.at + (size_t)m * Dh * Dh;
+    for (int e = tid; e < Dh * Dh; e += 256) as[e] = at[e];
+    __syncthreads();
+    for (int e = tid; e < CM_FT * Dh; e += 256) {
+        const int f = e / Dh, c = e - f * Dh;
+        xs[f * XS + c] = idx[f] >= 0 ? src[(size_t)idx[f] * Dh + c] : 0.0;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[4][5];
 #pragma unroll
-        for (int q = 0; q < C_FT; ++q)
-            if (f0 + q < f1) E[(n0 + f0 + q) * Dh + r] = off + acc[q];
-        f0 = f1;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) acc[a][q] = 0.0;
+    for (int c = 0; c < Dh; ++c) {
+        double a[5], x[4];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) a[q] = (tx + 16 * q < Dh) ? as[c * Dh + tx + 16 * q] : 0.0;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) x[f] = xs[(ty * 4 + f) * XS + c];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc[f][q] = fma(a[q], x[f], acc[f][q]);
+    }
+    const double* off = v.offset + (size_t)m * Dh;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const int n = idx[ty * 4 + f];
+        if (n < 0) continue;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int r = tx + 16 * q;
+            if (r < Dh) E[(size_t)n * Dh + r] = off[r] + acc[f][q];
+        }
     }
 }
 
@@ -224,15 +285,25 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, int Dh,
 
 struct ConvertWorkspace {
     int32_t* mix;
+    int* counts;      // K
+    int* offsets;     // K + 1
+    int* blockstart;  // K + 1
+    int* cursor;      // K
+    int* order;       // total
     double* E;
     double* band;
     size_t bytes;
 };
 
-static ConvertWorkspace carve_convert(long long total, int Dh, int sd, void* base) {
+static ConvertWorkspace carve_convert(long long total, int K, int Dh, int sd, void* base) {
     Carver c(base);
     ConvertWorkspace w;
     w.mix = c.take<int32_t>((size_t)total);
+    w.counts = c.take<int>((size_t)K);
+    w.offsets = c.take<int>((size_t)K + 1);
+    w.blockstart = c.take<int>((size_t)K + 1);
+    w.cursor = c.take<int>((size_t)K);
+    w.order = c.take<int>((size_t)total);
     w.E = c.take<double>((size_t)total * Dh);
     w.band = c.take<double>(4 * (size_t)total * sd);
     w.bytes = align_up(c.used, 256);
@@ -268,7 +339,7 @@ extern "C" int kw_convert_prepare(int K, int Dh, int diff, const double* weights
 }
 
 extern "C" size_t kw_convert_workspace_bytes(int64_t total_frames, int K, int Dh, int precision) {
-    size_t b = carve_convert(total_frames, Dh, Dh / 3, nullptr).bytes;
+    size_t b = carve_convert(total_frames, K, Dh, Dh / 3, nullptr).bytes;
     if (precision == 1) b += tc_workspace_bytes(total_frames, K, Dh);
     return b;
 }
@@ -284,7 +355,7 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
     KW_REQUIRE(Dh % 3 == 0, "dim_half %d is not static+delta+delta2 (multiple of 3)", Dh);
     KW_REQUIRE(precision == 0 || precision == 1, "convert precision must be 0 or 1");
     const int sd = Dh / 3;
-    ConvertWorkspace w = carve_convert(total, Dh, sd, workspace_dev);
+    ConvertWorkspace w = carve_convert(total, K, Dh, sd, workspace_dev);
     if (w.bytes > workspace_bytes) {
         set_error("convert workspace too small: need %zu bytes, got %zu", w.bytes,
                   workspace_bytes);
@@ -306,12 +377,22 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
                         w.mix, st);
     if (rc != KW_OK) return rc;
     {
-        const size_t smem = sizeof(double) * C_FT * Dh;
-        const long long grid = (total + C_FT - 1) / C_FT;
-        const int bd = (Dh + 31) / 32 * 32;
-        KW_REQUIRE(bd <= 128, "dim_half %d > 128 unsupported", Dh);
-        convert_condmean_kernel<<<(unsigned)grid, bd, smem, st>>>(total, Dh, src_dev, w.mix, v,
-                                                                 w.E);
+        KW_REQUIRE(Dh <= 80, "dim_half %d > 80 unsupported", Dh);
+        KW_REQUIRE(total < 2147483647LL, "too many frames for one conversion batch");
+        KW_CUDA_CHECK(cudaMemsetAsync(w.counts, 0, sizeof(int) * K, st));
+        convert_hist_kernel<<<296, 256, sizeof(int) * K, st>>>(total, K, w.mix, w.counts);
+        KW_CUDA_CHECK(cudaGetLastError());
+        convert_scan_kernel<<<1, 32, 0, st>>>(K, w.counts, w.offsets, w.blockstart, w.cursor);
+        KW_CUDA_CHECK(cudaGetLastError());
+        convert_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            total, w.mix, w.offsets, w.cursor, w.order);
+        KW_CUDA_CHECK(cudaGetLastError());
+        const size_t smem = sizeof(double) * ((size_t)Dh * Dh + (size_t)CM_FT * (Dh + 1));
+        KW_CUDA_CHECK(cudaFuncSetAttribute(convert_condmean_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long max_blocks = (total + CM_FT - 1) / CM_FT + K;
+        convert_condmean_kernel<<<(unsigned)max_blocks, 256, smem, st>>>(
+            K, Dh, src_dev, w.offsets, w.blockstart, w.order, v, w.E);
         KW_CUDA_CHECK(cudaGetLastError());
     }
     {
