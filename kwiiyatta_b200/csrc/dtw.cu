@@ -25,6 +25,7 @@
 #include <vector>
 
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -97,7 +98,7 @@ static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radi
         xrow += tx[p];
         yrow += ty[p];
         d.bp_off = (long long)plan.n_bp;
-        plan.n_bp += (size_t)tx[p] * (size_t)((ty[p] + 15) / 16);
+        plan.n_bp += (size_t)((tx[p] + 7) / 8) * (size_t)((ty[p] + 15) / 16) * 8;
         d.brow_off = (long long)plan.n_brow;
         plan.n_brow += 2 * (size_t)ty[p];
         d.path_off = path;
@@ -169,6 +170,13 @@ __global__ void dtw_pyramid_kernel(const PairDesc* __restrict__ descs, int level
     }
 }
 
+// Back-pointers: 2 bits per cell, 16 cells per 32-bit word; the 8 words of rows 8a..8a+7 for one
+// 16-column group form one 32-byte sector, so the backtrace (which moves to a neighbouring row
+// or column every step) stays inside one L1 sector for ~8-12 steps.  ncg = ceil(ty / 16).
+__host__ __device__ __forceinline__ size_t bp_word(int i, int j, int ncg) {
+    return ((size_t)(i >> 3) * ncg + (j >> 4)) * 8 + (size_t)(i & 7);
+}
+
 template <int P>
 __device__ __forceinline__ double dist_acc(double s, double d) {
     if (P == 2) return __fma_rn(d, d, s);
@@ -210,7 +218,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
     const int ctx = full ? 0 : d.tx[level + 1];
     const int* __restrict__ cfirst = full ? nullptr : rowj + d.rj_off[level + 1];
     const int* __restrict__ clast = full ? nullptr : cfirst + ctx;
-    const int pitchw = (ty + 15) >> 4;
+    const int tiles_x = (ty + 15) >> 4;
     uint32_t* bp_pair = bp + d.bp_off;
     double* brow_pair = brow + d.brow_off;
     const double INF = CUDART_INF;
@@ -269,8 +277,6 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
         }
         xch[NT + t] = INF;  // parity 1 is read at step 0
         uint32_t wa = 0u, wb = 0u;
-        uint32_t* bpa = bp_pair + (size_t)ia * pitchw;
-        uint32_t* bpb = bp_pair + (size_t)ib * pitchw;
         __syncthreads();
 
         for (int s = 0; s < n_steps; ++s) {
@@ -313,7 +319,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
                     if (c < best) { best = c; code = 2u; }
                     va = best;
                     wa |= code << (2 * (j & 15));
-                    if ((j & 15) == 15 || j == hia) { bpa[j >> 4] = wa; wa = 0u; }
+                    if ((j & 15) == 15 || j == hia) { bp_pair[bp_word(ia, j, tiles_x)] = wa; wa = 0u; }
                     if (ia == tx - 1 && j == ty - 1) cost[pair] = va;
                     ++my_cells;
                 }
@@ -327,7 +333,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
                     if (c < best) { best = c; code = 2u; }
                     vb = best;
                     wb |= code << (2 * (j & 15));
-                    if ((j & 15) == 15 || j == hib) { bpb[j >> 4] = wb; wb = 0u; }
+                    if ((j & 15) == 15 || j == hib) { bp_pair[bp_word(ib, j, tiles_x)] = wb; wb = 0u; }
                     if (ib == tx - 1 && j == ty - 1) cost[pair] = vb;
                     if (writes_boundary) __stcg(brow_out + j, vb);
                     ++my_cells;
@@ -348,38 +354,55 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
 }
 
 // ---------------------------------------------------------------------------------------
-// Backtrace: one thread per pair walks the 2-bit codes from (tx-1, ty-1) to the origin.
-// Level 0 writes the path (backwards, into the tail of the pair's region); levels >= 1 only
-// record first_j / last_j per row for the next finer level's window.
+// Backtrace: one warp per pair walks the 2-bit codes from (tx-1, ty-1) to the origin.  The warp
+// keeps a 2 x 2 window of back-pointer sectors (16 rows x 32 columns, one word per lane) in
+// registers and looks codes up with shuffles; global memory is touched once per window, not
+// once per step.  Level 0 writes the path (backwards, into the tail of the pair's region);
+// levels >= 1 only record first_j / last_j per row for the next finer level's window.
 // ---------------------------------------------------------------------------------------
-__global__ void dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
-                                     const uint32_t* __restrict__ bp, int* __restrict__ rowj,
-                                     int32_t* __restrict__ path, int32_t* __restrict__ path_begin,
-                                     int32_t* __restrict__ path_len) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
+                     const uint32_t* __restrict__ bp, int* __restrict__ rowj,
+                     int32_t* __restrict__ path, int32_t* __restrict__ path_begin,
+                     int32_t* __restrict__ path_len) {
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= n_pairs) return;
     const PairDesc& d = descs[pair];
     if (level >= d.nlev) return;
     const int tx = d.tx[level], ty = d.ty[level];
-    const int pitchw = (ty + 15) >> 4;
+    const int ncg = (ty + 15) >> 4;
     const uint32_t* bpp = bp + d.bp_off;
     int* first = (level > 0) ? rowj + d.rj_off[level] : nullptr;
     int* last = (level > 0) ? first + tx : nullptr;
     const int cap = d.tx[0] + d.ty[0];
     int32_t* out = path + 2 * d.path_off;
+    const int q = lane >> 3, r = lane & 7;      // window sector and row-in-sector of this lane
     int i = tx - 1, j = ty - 1, n = 0, prev_i = -1, prev_j = -1;
+    int si = -1, sj = -1;                        // anchor (bottom-right sector) of the window
+    uint32_t w = 0u;
     while (i >= 0 && j >= 0 && n < tx + ty) {
-        if (level == 0) {
-            out[2 * (cap - 1 - n)] = i;
-            out[2 * (cap - 1 - n) + 1] = j;
-        } else if (i != prev_i) {
-            last[i] = j;
-            if (prev_i >= 0) first[prev_i] = prev_j;
+        const int ci = i >> 3, cj = j >> 4;
+        if (si < 0 || si - ci > 1 || sj - cj > 1 || ci > si || cj > sj) {
+            si = ci;
+            sj = cj;
+            const int ii = si - (q & 1), jj = sj - (q >> 1);
+            w = (ii >= 0 && jj >= 0) ? __ldcg(bpp + ((size_t)ii * ncg + jj) * 8 + r) : 0u;
+        }
+        if (lane == 0) {
+            if (level == 0) {
+                out[2 * (cap - 1 - n)] = i;
+                out[2 * (cap - 1 - n) + 1] = j;
+            } else if (i != prev_i) {
+                last[i] = j;
+                if (prev_i >= 0) first[prev_i] = prev_j;
+            }
         }
         prev_i = i;
         prev_j = j;
-        const uint32_t w = __ldcg(bpp + (size_t)i * pitchw + (j >> 4));
-        const uint32_t code = (w >> (2 * (j & 15))) & 3u;
+        const int src = (((si - ci) + 2 * (sj - cj)) << 3) + (i & 7);
+        const uint32_t word = __shfl_sync(0xffffffffu, w, src);
+        const uint32_t code = (word >> (2 * (j & 15))) & 3u;
         if (code == 0u) {
             --i;
         } else if (code == 1u) {
@@ -390,10 +413,12 @@ __global__ void dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_p
         }
         ++n;
     }
-    if (level > 0 && prev_i >= 0) first[prev_i] = prev_j;
-    if (level == 0) {
-        path_begin[pair] = cap - n;
-        path_len[pair] = n;
+    if (lane == 0) {
+        if (level > 0 && prev_i >= 0) first[prev_i] = prev_j;
+        if (level == 0) {
+            path_begin[pair] = cap - n;
+            path_len[pair] = n;
+        }
     }
 }
 
@@ -480,14 +505,20 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
     }
     for (int l = plan.maxlev - 1; l >= 0; --l) {
         const int mtx = plan.level_max_tx[l];
-        const int nt = (mtx <= 64) ? 32 : (mtx <= 128 ? 64 : 128);
+        static int nt_env = -1;
+        if (nt_env < 0) {
+            const char* e = getenv("KW_DTW_NT");
+            nt_env = e != nullptr ? atoi(e) : 0;
+        }
+        int nt = (mtx <= 64) ? 32 : ((mtx <= 128 || radius >= 0) ? 64 : 128);
+        if (nt_env == 32 || nt_env == 64 || nt_env == 128) nt = std::min(nt, nt_env);
         unsigned long long* cells = reinterpret_cast<unsigned long long*>(cells_dev);
         if (p_norm == 2)
             rc = launch_dp_fp<2>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
         else
             rc = launch_dp_fp<1>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
         if (rc != KW_OK) return rc;
-        dtw_backtrace_kernel<<<(n_pairs + 31) / 32, 32, 0, st>>>(
+        dtw_backtrace_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(
             w.descs, n_pairs, l, w.bp, w.rowj, path_dev, path_begin_dev, path_len_dev);
         KW_CUDA_CHECK(cudaGetLastError());
     }
