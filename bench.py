@@ -88,6 +88,14 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
+def ctypes_device_sms(device):
+    import ctypes
+    from kwiiyatta_b200 import _lib
+    sms = ctypes.c_int(148)
+    _lib.lib().kw_device_info(device, ctypes.byref(sms), None, None, None)
+    return sms.value
+
+
 def build_dtw_inputs(first_pair, n_pairs):
     from kwiiyatta_b200 import synth
     from kwiiyatta_b200.alignment import make_feature
@@ -296,9 +304,16 @@ def run_b200(args):
         cpu = cpu_baselines(feats, x_joint, labels0, (w, m, c), src_list, em_iters=2)
 
     em_tflops = 2 * flops_half / (em_ms / K / 1e3) / 1e12
-    dominant_ms, dominant = (estep_ms, 'gmm_estep') if estep_ms >= mstep_ms else (mstep_ms, 'gmm_m2')
+    tc = args.precision == 'tc'
+    names = ('estep_tc_kernel', 'mstats_tc_kernel') if tc else ('gmm_estep_kernel', 'gmm_mstats_kernel')
+    dominant_ms, dominant = (estep_ms, names[0]) if estep_ms >= mstep_ms else (mstep_ms, names[1])
     dom_tflops = flops_half / (dominant_ms / 1e3) / 1e12
     peak = peaks['bf16_tflops_sustained']
+    # DTW: FP64-pipe issue bound: 72 FP64-pipe instructions per cell,
+    # 64 FP64 lanes per SM
+    sm_count = ctypes_device_sms(local_rank)
+    sm_hz = (clock_info['sm_max_mhz'] or 1965.0) * 1e6 if clock_info else 1965e6
+    dtw_peak = sm_count * 64 * sm_hz / 72.0
     out = {
         'metric': 'GMM-EM frames/s/iter',
         'value': em_value,
@@ -330,12 +345,15 @@ def run_b200(args):
             'note': f'B200GMMFeatureConverter._train on a pinned host (N,144) array, '
                     f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model',
         },
-        'gpu_launches': 6 * K,
+        'gpu_launches': (9 if tc else 6) * K,
         'roofline': {
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': dom_tflops / peak, 'traffic': None,
             'peak_source': f"{peaks['source']} bf16_tflops_sustained",
-            'algorithmic': '2*N*K*D^2 flop per launch (half of the 4*N*K*D^2 EM iteration)',
+            'algorithmic': '2*N*K*D^2 flop per launch (half of the 4*N*K*D^2 EM iteration); '
+                           'duration = CUDA events around the C-ABI entry that launches it',
+            'mma_passes': 3 if tc else None,
+            'frac_of_peak_over_passes': (dom_tflops / (peak / 3)) if tc else None,
             'estep_ms': estep_ms, 'mstep_accumulate_ms': mstep_ms,
             'em_iteration_tflops': em_tflops,
         },
@@ -346,6 +364,10 @@ def run_b200(args):
                 'metric': 'DTW cells/s', 'value': dtw_cells_per_s, 'unit': 'cells/s',
                 'ms_per_step': dtw_ms / K, 'cells_per_step': cells_total,
                 'nominal_cells_per_s': nominal_total * K / (dtw_ms / 1e3),
+                'roofline': {'bound': 'fp64 issue', 'achieved': dtw_cells_per_s / world,
+                             'peak': dtw_peak, 'unit': 'cells/s per GPU',
+                             'frac': dtw_cells_per_s / world / dtw_peak,
+                             'model': 'SMs x 64 FP64 lanes x f_max / 72 FP64-pipe ops per cell'},
                 'e2e': {'value': dtw_e2e, 'unit': 'cells/s',
                         'h2d_bytes_per_step': int(x_host.nbytes + y_host.nbytes),
                         'd2h_bytes_per_step': int(8 * (tx.sum() + ty.sum()) + 20 * n_pairs)},
@@ -356,6 +378,10 @@ def run_b200(args):
                 'ms_per_step': conv_ms / K, 'frames_per_step': conv_frames_total,
                 'n_components': N_MIX_CONVERT,
                 'hbm_boundary_gbs': conv_value * 768 / 1e9,
+                'roofline': {'bound': 'hbm', 'achieved': conv_value * 768 / 1e9 / world,
+                             'peak': peaks['hbm_gbs'], 'unit': 'GB/s per GPU',
+                             'frac': conv_value * 768 / 1e9 / world / peaks['hbm_gbs'],
+                             'model': '768 B/frame at the converter boundary (72 f64 in, 24 out)'},
                 'e2e': {'value': conv_e2e, 'unit': 'frames/s',
                         'h2d_bytes_per_step': int(n_utts * UTT_FRAMES * 72 * 8),
                         'd2h_bytes_per_step': int(n_utts * UTT_FRAMES * 24 * 8)},
@@ -508,7 +534,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default='fp64', choices=['fp64', 'tc'])
+    ap.add_argument('--precision', default='tc', choices=['fp64', 'tc'],
+                    help='tc = split-fp16 tcgen05 contractions (default), fp64 = CUDA-core DFMA')
     ap.add_argument('--pairs', type=int, default=N_PAIRS, help='pairs per GPU')
     ap.add_argument('--utts', type=int, default=N_UTTS, help='conversion utterances per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
