@@ -50,7 +50,9 @@ int kw_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
  * all x sequences, shape (sum tx, feat_dim); y_dev likewise.  tx_host / ty_host are HOST arrays.
  *   radius  >= 1 : FastDTW with that radius;  radius < 0 : exhaustive DTW (fastdtw.dtw).
  *   p_norm  : 1 or 2 -- local distance (sum |d|) or sqrt(sum d^2)  (dist=1 / dist=2).
- *   precision : 0 = fp64 exact (paths bit-exact to the oracle), 1 = fp32 accumulate.
+ *   precision : 0 = fp64 exact (paths bit-exact to the oracle), 1 = fp32 local distances
+ *               (direct differences and sqrt in fp32, DP sums in fp64; path cost within 1e-6
+ *               relative of the fp64 result, paths may differ on near-ties).
  * Outputs (device):
  *   cost_dev[n_pairs]            accumulated distance D[tx][ty];
  *   path_dev                     int32 (i, j) pairs; pair p owns the region of (tx[p]+ty[p]) points

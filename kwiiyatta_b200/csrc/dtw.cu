@@ -187,11 +187,25 @@ __device__ __forceinline__ double dist_fin(double s) {
     if (P == 2) return __dsqrt_rn(s);
     return s;
 }
+// fp32 local-distance mode (precision = 1): differences, squares and the square root in fp32,
+// the DP sums stay fp64 (so the path cost carries only the rounding of the local distances).
+template <int P>
+__device__ __forceinline__ float dist_acc(float s, float d) {
+    if (P == 2) return __fmaf_rn(d, d, s);
+    return __fadd_rn(s, fabsf(d));
+}
+template <int P>
+__device__ __forceinline__ double dist_fin(float s) {
+    if (P == 2) return (double)__fsqrt_rn(s);
+    return (double)s;
+}
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 
 // ---------------------------------------------------------------------------------------
 // Windowed DP for one resolution level.
 // ---------------------------------------------------------------------------------------
-template <int FP, int NT, int P>
+template <int FP, int NT, int P, typename T>
 __global__ void __launch_bounds__(NT)
 dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
               int radius, int F, const double* __restrict__ xpyr,
@@ -202,9 +216,9 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
     constexpr int RING = 2 * NT;
     constexpr int RS = RING + 1;
     extern __shared__ double smem[];
-    double* ys = smem;             // FP * RS, k-major ring of y columns
-    double* xch = ys + FP * RS;    // 2 * NT: lower-row D values, double-buffered by step parity
+    double* xch = smem;            // 2 * NT: lower-row D values, double-buffered by step parity
     double* brs = xch + 2 * NT;    // RING: previous strip's last row, staged with the y ring
+    T* ys = reinterpret_cast<T*>(brs + RING);   // FP * RS, k-major ring of y columns
     __shared__ unsigned long long cell_count;
 
     const int pair = order[blockIdx.x];
@@ -239,7 +253,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
 
     if (t == 0) cell_count = 0ull;
     // zero the padded feature rows of the ring once
-    for (int e = t; e < (FP - F) * RS; e += NT) ys[F * RS + e] = 0.0;
+    for (int e = t; e < (FP - F) * RS; e += NT) ys[F * RS + e] = (T)0;
 
     unsigned int my_cells = 0;
     int strip = 0;
@@ -248,11 +262,11 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
         int loa = INT_MAX, hia = INT_MIN, lob = INT_MAX, hib = INT_MIN;
         if (ia < tx) window(ia, loa, hia);
         if (ib < tx) window(ib, lob, hib);
-        double xa[FP], xb[FP];
+        T xa[FP], xb[FP];
 #pragma unroll
         for (int k = 0; k < FP; ++k) {
-            xa[k] = (k < F && ia < tx) ? xT[(size_t)k * tx + ia] : 0.0;
-            xb[k] = (k < F && ib < tx) ? xT[(size_t)k * tx + ib] : 0.0;
+            xa[k] = (T)((k < F && ia < tx) ? xT[(size_t)k * tx + ia] : 0.0);
+            xb[k] = (T)((k < F && ib < tx) ? xT[(size_t)k * tx + ib] : 0.0);
         }
         // strip-wide quantities (uniform across the CTA)
         int jstart, dummy;
@@ -285,7 +299,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
                 for (int e = t; e < F * CH; e += NT) {
                     const int k = e / CH, jj = e - k * CH;
                     const int j = jbase + jj;
-                    if (j < ty) ys[k * RS + (j & (RING - 1))] = yT[(size_t)k * ty + j];
+                    if (j < ty) ys[k * RS + (j & (RING - 1))] = (T)yT[(size_t)k * ty + j];
                 }
                 {
                     const int j = jbase + t;
@@ -301,13 +315,13 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
             const bool act_b = (j >= lob) && (j <= hib);
             double va = INF, vb = INF;
             if (act_a || act_b) {
-                double sa = 0.0, sb = 0.0;
-                const double* yp = ys + (j & (RING - 1));
+                T sa = (T)0, sb = (T)0;
+                const T* yp = ys + (j & (RING - 1));
 #pragma unroll
                 for (int k = 0; k < FP; ++k) {
-                    const double yv = yp[k * RS];
-                    sa = dist_acc<P>(sa, __dsub_rn(xa[k], yv));
-                    sb = dist_acc<P>(sb, __dsub_rn(xb[k], yv));
+                    const T yv = yp[k * RS];
+                    sa = dist_acc<P>(sa, sub_rn(xa[k], yv));
+                    sb = dist_acc<P>(sb, sub_rn(xb[k], yv));
                 }
                 if (act_a) {
                     const double dt = dist_fin<P>(sa);
@@ -422,12 +436,12 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
     }
 }
 
-template <int FP, int NT, int P>
+template <int FP, int NT, int P, typename T>
 static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
                      double* cost, unsigned long long* cells, cudaStream_t st) {
     constexpr int RS = 2 * NT + 1;
-    const size_t smem = sizeof(double) * ((size_t)FP * RS + 2 * NT + 2 * NT);
-    auto kern = dtw_dp_kernel<FP, NT, P>;
+    const size_t smem = sizeof(double) * (2 * NT + 2 * NT) + sizeof(T) * (size_t)FP * RS;
+    auto kern = dtw_dp_kernel<FP, NT, P, T>;
     KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     kern<<<n_pairs, NT, smem, st>>>(w.descs, w.order, level, radius, F, w.xpyr, w.ypyr, w.rowj,
@@ -436,21 +450,21 @@ static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, 
     return KW_OK;
 }
 
-template <int FP, int P>
+template <int FP, int P, typename T>
 static int launch_dp_nt(int nt, int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
                         double* cost, unsigned long long* cells, cudaStream_t st) {
-    if (nt == 32) return launch_dp<FP, 32, P>(n_pairs, w, level, radius, F, cost, cells, st);
-    if (nt == 64) return launch_dp<FP, 64, P>(n_pairs, w, level, radius, F, cost, cells, st);
-    return launch_dp<FP, 128, P>(n_pairs, w, level, radius, F, cost, cells, st);
+    if (nt == 32) return launch_dp<FP, 32, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
+    if (nt == 64) return launch_dp<FP, 64, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
+    return launch_dp<FP, 128, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
 }
 
-template <int P>
+template <int P, typename T>
 static int launch_dp_fp(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
                         double* cost, unsigned long long* cells, cudaStream_t st) {
-    if (F <= 8) return launch_dp_nt<8, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    if (F <= 16) return launch_dp_nt<16, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    if (F <= 26) return launch_dp_nt<26, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    return launch_dp_nt<32, P>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    if (F <= 8) return launch_dp_nt<8, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    if (F <= 16) return launch_dp_nt<16, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    if (F <= 26) return launch_dp_nt<26, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+    return launch_dp_nt<32, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
 }
 
 }  // namespace kw
@@ -480,10 +494,8 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
         set_error("feat_dim %d > 32 is not supported by the sm_100a DTW kernels", feat_dim);
         return KW_ERR_UNSUPPORTED;
     }
-    if (precision != 0) {
-        set_error("DTW precision %d is not built (0 = fp64 exact)", precision);
-        return KW_ERR_UNSUPPORTED;
-    }
+    KW_REQUIRE(precision == 0 || precision == 1,
+               "DTW precision must be 0 (fp64 exact) or 1 (fp32 local distances)");
     DtwPlan plan;
     int rc = make_plan(n_pairs, tx_host, ty_host, radius, feat_dim, plan);
     if (rc != KW_OK) return rc;
@@ -513,10 +525,17 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
         int nt = (mtx <= 64) ? 32 : ((mtx <= 128 || radius >= 0) ? 64 : 128);
         if (nt_env == 32 || nt_env == 64 || nt_env == 128) nt = std::min(nt, nt_env);
         unsigned long long* cells = reinterpret_cast<unsigned long long*>(cells_dev);
-        if (p_norm == 2)
-            rc = launch_dp_fp<2>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
-        else
-            rc = launch_dp_fp<1>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        if (precision == 0) {
+            if (p_norm == 2)
+                rc = launch_dp_fp<2, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+            else
+                rc = launch_dp_fp<1, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        } else {
+            if (p_norm == 2)
+                rc = launch_dp_fp<2, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+            else
+                rc = launch_dp_fp<1, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        }
         if (rc != KW_OK) return rc;
         dtw_backtrace_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(
             w.descs, n_pairs, l, w.bp, w.rowj, path_dev, path_begin_dev, path_len_dev);

@@ -136,3 +136,23 @@ def test_long_unconstrained_pair(cuda):
     a, b = synth.make_pair(3, length=1536)
     x, y = make_feature(a, a.fs), make_feature(b, b.fs)
     _check([(x, y)], -1)
+
+
+def test_fp32_distance_mode_cost_within_1e6(cuda):
+    """north_star: the fp32 mode is reported separately, path cost within 1e-6 relative."""
+    pairs = []
+    for i in range(6):
+        a, b = synth.make_padded_pair(20 + i)
+        pairs.append((make_feature(a, a.fs), make_feature(b, b.fs)))
+    exact = kfd.fastdtw_batch(pairs, radius=32, dist=2, precision=0)
+    fast = kfd.fastdtw_batch(pairs, radius=32, dist=2, precision=1)
+    same = 0
+    for (x, y), (c0, p0), (c1, p1) in zip(pairs, exact, fast):
+        assert abs(c1 - c0) <= 1e-6 * c0
+        # the fp32 path is a valid warping path whose fp64 cost is (near-)optimal as well
+        step = np.diff(p1, axis=0)
+        assert ((step >= 0) & (step <= 1)).all() and (step.sum(axis=1) >= 1).all()
+        local = np.sqrt(((x[p1[:, 0]] - y[p1[:, 1]]) ** 2).sum(axis=1))
+        assert abs(local.sum() - c0) <= 1e-6 * c0
+        same += int(p0.shape == p1.shape and np.array_equal(p0, p1))
+    assert same >= 4       # identical paths except on near-ties
