@@ -162,6 +162,14 @@ int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t total_frames, i
                      const double* prepared_dev, double* out_dev, int32_t* mix_dev,
                      int precision, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Soft-posterior mapping without MLPG (nnmnkwii MLPGBase.transform; the mlpg=False branch of
+ * kwiiyatta/converter/gmm.py:30-31): out (total, dim_half) = sum_m p(m|x) (mu_y + S_yx S_xx^-1 (x - mu_x)).
+ * `prepared_dev` comes from kw_convert_prepare with the same dim_half. */
+size_t kw_convert_soft_workspace_bytes(int64_t total_frames, int n_components, int dim_half);
+int kw_convert_soft_batch(int64_t total_frames, const double* src_dev, int n_components,
+                          int dim_half, const double* prepared_dev, double* out_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

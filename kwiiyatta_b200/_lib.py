@@ -35,6 +35,8 @@ SIGNATURES = {
     'kw_gmm_precision_cholesky': (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'kw_convert_prepared_len': (_sz, [_i, _i]),
     'kw_convert_prepare': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'kw_convert_soft_workspace_bytes': (_sz, [_i64, _i, _i]),
+    'kw_convert_soft_batch': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'kw_convert_workspace_bytes': (_sz, [_i64, _i, _i, _i]),
     'kw_convert_batch': (_i, [_i, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz,
                               _vp]),

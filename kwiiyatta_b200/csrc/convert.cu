@@ -205,6 +205,58 @@ convert_condmean_kernel(int K, int Dh, const double* __restrict__ src,
     }
 }
 
+// Soft-posterior mapping (nnmnkwii MLPGBase.transform, the mlpg=False branch of
+// kwiiyatta/converter/gmm.py:30-31):  y_t = sum_m p(m | x_t) (offset[m] + A[m] x_t).
+// CTA = 32 frames; thread r owns output dimension r for all 32 frames; mixtures whose posterior is
+// below 1e-14 for every frame of the tile are skipped.
+constexpr int SOFT_FT = 32;
+__global__ void __launch_bounds__(96)
+convert_soft_kernel(long long N, long long Npad, int K, int Dh, const double* __restrict__ src,
+                    const double* __restrict__ respT, PreparedView v, double* __restrict__ out) {
+    extern __shared__ double xs[];          // SOFT_FT * Dh frames, then SOFT_FT responsibilities
+    double* rs = xs + SOFT_FT * Dh;
+    __shared__ int any_active;
+    const long long n0 = (long long)blockIdx.x * SOFT_FT;
+    for (int e = threadIdx.x; e < SOFT_FT * Dh; e += blockDim.x) {
+        const long long n = n0 + e / Dh;
+        xs[e] = (n < N) ? src[n * Dh + (e % Dh)] : 0.0;
+    }
+    const int r = threadIdx.x;
+    double acc[SOFT_FT];
+#pragma unroll
+    for (int f = 0; f < SOFT_FT; ++f) acc[f] = 0.0;
+    for (int m = 0; m < K; ++m) {
+        __syncthreads();
+        if (threadIdx.x == 0) any_active = 0;
+        __syncthreads();
+        if (threadIdx.x < SOFT_FT) {
+            const long long n = n0 + threadIdx.x;
+            const double p = (n < N) ? respT[(size_t)m * Npad + n] : 0.0;
+            rs[threadIdx.x] = p;
+            if (p > 1e-14) any_active = 1;
+        }
+        __syncthreads();
+        if (!any_active || r >= Dh) continue;
+        const double* at = v.at + (size_t)m * Dh * Dh;
+        const double off = v.offset[(size_t)m * Dh + r];
+        double e[SOFT_FT];
+#pragma unroll
+        for (int f = 0; f < SOFT_FT; ++f) e[f] = off;
+        for (int c = 0; c < Dh; ++c) {
+            const double a = at[(size_t)c * Dh + r];
+#pragma unroll
+            for (int f = 0; f < SOFT_FT; ++f) e[f] = fma(a, xs[f * Dh + c], e[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < SOFT_FT; ++f) acc[f] = fma(rs[f], e[f], acc[f]);
+    }
+    if (r < Dh) {
+#pragma unroll
+        for (int f = 0; f < SOFT_FT; ++f)
+            if (n0 + f < N) out[(n0 + f) * Dh + r] = acc[f];
+    }
+}
+
 // MLPG: one thread per (utterance, static dim).  Banded Cholesky (bandwidth 2) with the
 // factor and the forward solution kept in a global workspace laid out [frame][static dim].
 struct Windows {
@@ -334,6 +386,37 @@ extern "C" int kw_convert_prepare(int K, int Dh, int diff, const double* weights
     KW_CUDA_CHECK(cudaFuncSetAttribute(convert_regress_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     convert_regress_kernel<<<K, 256, smem, st>>>(K, Dh, diff, covariances_dev, v);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+extern "C" size_t kw_convert_soft_workspace_bytes(int64_t total_frames, int K, int Dh) {
+    Carver c(nullptr);
+    c.take<double>((size_t)K * (size_t)resp_pad(total_frames));
+    c.take<double>((size_t)((total_frames + 63) / 64) + 1);
+    return align_up(c.used, 256);
+}
+
+extern "C" int kw_convert_soft_batch(int64_t total, const double* src_dev, int K, int Dh,
+                                     const double* prepared_dev, double* out_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total == 0) return KW_OK;
+    KW_REQUIRE(total > 0 && K > 0 && Dh > 0, "kw_convert_soft_batch: bad sizes");
+    KW_REQUIRE(Dh <= 96, "dim_half %d > 96 unsupported", Dh);
+    if (kw_convert_soft_workspace_bytes(total, K, Dh) > workspace_bytes) {
+        set_error("soft conversion workspace too small");
+        return KW_ERR_WORKSPACE;
+    }
+    Carver c(workspace_dev);
+    double* resp = c.take<double>((size_t)K * (size_t)resp_pad(total));
+    double* lse = c.take<double>((size_t)((total + 63) / 64) + 1);
+    PreparedView v = view_prepared(const_cast<double*>(prepared_dev), K, Dh);
+    int rc = estep_fp64(total, src_dev, K, Dh, v.px_prec_chol, v.px_aux, resp, lse, 0, nullptr, st);
+    if (rc != KW_OK) return rc;
+    const size_t smem = sizeof(double) * ((size_t)SOFT_FT * Dh + SOFT_FT);
+    convert_soft_kernel<<<(unsigned)((total + SOFT_FT - 1) / SOFT_FT), 96, smem, st>>>(
+        total, resp_pad(total), K, Dh, src_dev, resp, v, out_dev);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }

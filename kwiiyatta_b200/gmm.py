@@ -352,19 +352,17 @@ class B200GMMFeatureConverter(FeatureConverter):
         self._paramgen = {}
         self.gmm.fit(dataarray, **kwargs)
 
-    def _mlpg(self, diff):
+    def _mlpg(self, diff, mlpg=True):
         from .mlpg import MLPG
-        key = bool(diff)
+        key = (bool(diff), bool(mlpg))
         if key not in self._paramgen:
-            self._paramgen[key] = MLPG(self.gmm, windows=DELTA_WINDOWS, diff=diff)
+            windows = DELTA_WINDOWS if mlpg else DELTA_WINDOWS[0:1]   # gmm.py:29-31
+            self._paramgen[key] = MLPG(self.gmm, windows=windows, diff=diff,
+                                       precision=self.gmm.precision)
         return self._paramgen[key]
 
     def convert(self, feature, mlpg=True, diff=False):
-        if not mlpg:
-            raise NotImplementedError(
-                'mlpg=False (per-frame soft-posterior mapping of a model trained without '
-                'deltas, kwiiyatta/converter/gmm.py:30-31) is not built yet')
-        return self._mlpg(diff).transform(feature)
+        return self._mlpg(diff, mlpg).transform(feature)
 
     def convert_many(self, features, diff=False):
         """Batched ``convert`` over a list of (T_i, 72) arrays."""

@@ -17,7 +17,11 @@ class MLPG:
         torch = _lib.require_cuda()
         if windows is None:
             windows = DELTA_WINDOWS
-        check_windows(windows)
+        if len(windows) > 1:
+            check_windows(windows)
+        elif not (windows[0][0] == 0 and windows[0][1] == 0 and
+                  np.array_equal(windows[0][2], [1.0])):
+            raise NotImplementedError('a single window must be the static window (0, 0, [1.0])')
         if swap:
             raise NotImplementedError('swap=True is not built')
         if getattr(gmm, 'covariance_type', 'full') != 'full':
@@ -80,10 +84,31 @@ class MLPG:
         out = self.transform_device(src, off_dev, len(feats), int(lens.max())).cpu().numpy()
         return [out[off[i]:off[i + 1]] for i in range(len(feats))]
 
+    def transform_soft(self, src):
+        """MLPGBase.transform: per-frame soft-posterior conditional mean, (T, dim_half)."""
+        torch = _lib.require_cuda()
+        lib = _lib.lib()
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        if src.ndim != 2 or src.shape[1] != self.dim_half:
+            raise ValueError(f'expected (T, {self.dim_half}) features, got {src.shape}')
+        total = len(src)
+        if total == 0:
+            return np.zeros((0, self.dim_half))
+        x = torch.from_numpy(src).to(self._dev)
+        out = torch.empty((total, self.dim_half), dtype=torch.float64, device=self._dev)
+        ws_bytes = lib.kw_convert_soft_workspace_bytes(total, self.num_mixtures, self.dim_half)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self._dev)
+        rc = lib.kw_convert_soft_batch(total, x.data_ptr(), self.num_mixtures, self.dim_half,
+                                       self._prepared.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                       ws_bytes, _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_convert_soft_batch')
+        return out.cpu().numpy()
+
     def transform(self, src):
         src = np.asarray(src, dtype=np.float64)
         if src.ndim != 2:
             raise ValueError('MLPG.transform expects a (T, dim) array')
         if src.shape[1] == self.static_dim:
-            raise NotImplementedError('static-only (no delta) mapping is not built')
+            # nnmnkwii: feature_dim == static_dim -> MLPGBase.transform (no trajectory smoothing)
+            return self.transform_soft(src)
         return self.transform_many([src])[0]

@@ -89,6 +89,18 @@ def test_delta_features_exact(cuda):
         assert np.array_equal(kdelta.delta_features(x), delta_ref.delta_features(x))
 
 
+@pytest.mark.parametrize('diff', [False, True])
+def test_soft_posterior_mapping_without_mlpg(cuda, diff):
+    """mlpg=False (kwiiyatta/converter/gmm.py:30-31): windows[0:1] -> per-frame soft mapping."""
+    w, m, c = synth.make_joint_gmm(6, dim_half=24, seed=8, static_dim=24)
+    rng = np.random.default_rng(8)
+    src = rng.standard_normal((77, 24)) * (1.0 / (1.0 + np.arange(24)))
+    exp = mlpg_ref.transform_frames_soft(src, w, m, c, diff=diff)
+    got = MLPG(_Model(w, m, c), windows=delta_ref.DELTA_WINDOWS[0:1], diff=diff).transform(src)
+    assert got.shape == exp.shape == (77, 24)
+    assert np.abs(got - exp).max() <= 1e-9
+
+
 def test_errors(cuda):
     w, m, c = synth.make_joint_gmm(2, seed=4)
     paramgen = MLPG(_Model(w, m, c))
@@ -96,3 +108,5 @@ def test_errors(cuda):
         paramgen.transform(np.zeros((5, 71)))
     with pytest.raises(NotImplementedError):
         MLPG(_Model(w, m, c), windows=delta_ref.DELTA_WINDOWS[:2])
+    with pytest.raises(ValueError):
+        MLPG(_Model(w, m, c)).transform(np.zeros((5, 71)))

@@ -127,8 +127,6 @@ def test_converter_plugin_surface():
     assert conv.gmm.tol == 1e-3 and conv.gmm.reg_covar == 1e-6
     with pytest.raises(NotImplementedError):
         kw.GaussianMixture(covariance_type='diag')
-    with pytest.raises(NotImplementedError):
-        conv.convert(np.zeros((3, 72)), mlpg=False)
 
 
 def test_synthetic_corpus_is_seeded_and_tie_free():
