@@ -105,10 +105,12 @@ __device__ __forceinline__ void tc_fence_after() {
 // D[tmem] (+)= A[smem] * B[smem]; accumulate = 0 overwrites D.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                          uint32_t idesc, uint32_t accumulate) {
+    // executed by the whole (converged) MMA warp; one elected lane issues
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -116,16 +118,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void umma_f16_scaled(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                                 uint32_t idesc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -396,8 +402,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer (whole warp converged, one elected lane issues) --------
+        {
             // Descriptors are built once; an MMA's operands differ from the base only by a byte
             // offset, i.e. an addition to the (address >> 4) field (the issuing thread is the
             // critical path of the whole kernel, so nothing else is computed per MMA).
@@ -775,8 +781,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             }
         }
       } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer (whole warp converged, one elected lane issues) --------
+        {
             const uint32_t idesc1 = make_idesc_mn(128, G.N1);
             const uint32_t idesc2 = make_idesc_mn(128, G.N2 > 0 ? G.N2 : 16);
             // MN-major, no swizzle: SBO = stride between 8-element groups along M/N (features),
@@ -839,7 +845,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     p_issue += clock64() - c3;
                 }
             }
-            if (prof != nullptr && blockIdx.x == 0) {
+            if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
                 prof[0] = (unsigned long long)(clock64() - p_start);
                 prof[1] = (unsigned long long)p_tm;
                 prof[2] = (unsigned long long)p_a;
