@@ -331,7 +331,7 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
     s.b_lo = o;  o += (uint32_t)bmat_elems(DP) * 2;
     s.scl = o;   o += 2u * 3 * DP * 4;                 // two stages of [scale | b' hi | b' lo]
     s.cst = o;   o += 2u * 2 * 8;
-    s.qpart = o; o += 2u * TILE_M * 8;
+    s.qpart = o; o += 3u * 2 * TILE_M * 8;
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
     s.total = o;
@@ -341,12 +341,13 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
 enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL, BAR_BLO_EMPTY, BAR_BHI_FULL0, BAR_BHI_FULL1,
        BAR_BHI_EMPTY0, BAR_BHI_EMPTY1, BAR_TM_FULL0, BAR_TM_FULL1, BAR_TM_EMPTY0, BAR_TM_EMPTY1 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
                 const float* __restrict__ sc, const double* __restrict__ cst,
                 double* __restrict__ wlpT, int mode, int32_t* __restrict__ mix,
-                int32_t* __restrict__ cand, double near_tie) {
+                int32_t* __restrict__ cand, double near_tie,
+                unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const EstepSmem L = estep_smem(DP);
     __half* a_hi = reinterpret_cast<__half*>(smem + L.a);
@@ -368,7 +369,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     const uint32_t idesc = make_idesc(TILE_M, DP);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 12; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 8u : 1u);
+        for (int i = 0; i < 12; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 16u : 1u);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
@@ -413,6 +414,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), 128, 256);
             const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), 128, 256);
             constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
+            long long p_tm = 0, p_blo = 0, p_bhi = 0, p_issue = 0;
+            const long long p_start = clock64();
             // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
             //   N = DP - 16 ks, B block at btri_off(ks), accumulator columns from 16 ks.
             const uint32_t ng = (uint32_t)DP / 8;
@@ -422,9 +425,13 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                     const uint64_t d_b_hi = s ? d_b_hi1 : d_b_hi0;
                     const uint32_t acc = tmem_base + s * (uint32_t)DP;
+                    const long long c0 = clock64();
                     mbar_wait(bars + BAR_TM_EMPTY0 + s, (u & 1u) ^ 1u);
+                    const long long c1 = clock64();
                     mbar_wait(bars + BAR_BLO_FULL, g & 1u);
                     if (k == 0) mbar_wait(bars + BAR_A_FULL, (uint32_t)it & 1u);
+                    const long long c2 = clock64();
+                    p_tm += c1 - c0; p_blo += c2 - c1;
                     tc_fence_after();
                     {
                         uint64_t da = d_a_hi, db = d_b_lo;          // x_hi . l_lo
@@ -438,7 +445,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         }
                     }
                     umma_commit(bars + BAR_BLO_EMPTY);
+                    const long long c3 = clock64();
                     mbar_wait(bars + BAR_BHI_FULL0 + s, u & 1u);
+                    const long long c4 = clock64();
+                    p_bhi += c4 - c3; p_issue += c3 - c2;
                     tc_fence_after();
                     {
                         uint64_t da = d_a_lo, db = d_b_hi;          // x_lo . l_hi
@@ -464,88 +474,91 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
+                    p_issue += clock64() - c4;
                 }
                 umma_commit(bars + BAR_A_EMPTY);
             }
+            if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
+                prof[0] = (unsigned long long)(clock64() - p_start);
+                prof[1] = (unsigned long long)p_tm;
+                prof[2] = (unsigned long long)p_blo;
+                prof[3] = (unsigned long long)p_bhi;
+                prof[4] = (unsigned long long)p_issue;
+            }
         }
     } else {
-        // ---------------- epilogue (warps 2..9) ----------------
-        // Two warps per TMEM lane quarter: each takes half of the accumulator columns; the
-        // second half's partial q goes through shared memory to the first, which finishes.
-        const int et = threadIdx.x - 64;            // 0..255
+        // ---------------- epilogue (warps 2..17) ----------------
+        // Four warps per TMEM lane quarter, each takes a quarter of the accumulator columns; the
+        // partial q of parts 1..3 goes through shared memory to part 0, which finishes.  (The
+        // epilogue, not the MMA, bounds this kernel: more warps = more latency hiding.)
+        const int et = threadIdx.x - 64;            // 0..511
         const uint32_t quarter = (uint32_t)(warp & 3);
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;           // 0..3
         const int row = (int)quarter * 32 + lane;   // TMEM lane = row of the tile
-        const int c_begin = half == 0 ? 0 : (ksteps + 1) / 2;
-        const int c_end = half == 0 ? (ksteps + 1) / 2 : ksteps;
+        const int c_begin = (ksteps * part) / 4, c_end = (ksteps * (part + 1)) / 4;
         const double LOG2PI = 1.8378770664093453;
+        long long q_bar = 0, q_wait = 0, q_work = 0;
+        const long long q_start = clock64();
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long n = (long long)tile * TILE_M + row;
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
             // per-component epilogue constants, prefetched one component ahead
-            float pre[2];
+            float pre = 0.f;
             double pre_c = 0.0;
             auto fetch = [&](int k) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = et + 256 * q;
-                    pre[q] = (i < 3 * DP) ? sc[(size_t)k * 3 * DP + i] : 0.f;
-                }
+                pre = (et < 3 * DP) ? sc[(size_t)k * 3 * DP + et] : 0.f;
                 if (et < 2) pre_c = cst[2 * k + et];
             };
             fetch(0);
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                 float* sk = scl + (size_t)s * 3 * DP;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = et + 256 * q;
-                    if (i < 3 * DP) sk[i] = pre[q];
-                }
+                if (et < 3 * DP) sk[et] = pre;
                 if (et < 2) cst_s[s * 2 + et] = pre_c;
                 if (k + 1 < K) fetch(k + 1);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const long long e0 = clock64();
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                const long long e1 = clock64();
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
+                const long long e2 = clock64();
+                q_bar += e1 - e0; q_wait += e2 - e1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * (uint32_t)DP;
                 double q = 0.0;
-                for (int c = c_begin; c < c_end; c += 2) {
-                    uint32_t v[32];
-                    const bool two = c + 1 < c_end;
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t v[16];
                     tmem_ld16(taddr + c * 16, v);
-                    if (two) tmem_ld16(taddr + (c + 1) * 16, v + 16);
                     tmem_ld_wait();
+                    const float* sc_p = sk + c * 16;
+                    float part_q = 0.f;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !two) break;
-                        const float* sc_p = sk + (c + h) * 16;
-                        float part = 0.f;
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 cs = *reinterpret_cast<const float4*>(sc_p + 4 * j4);
-                            const float4 bh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
-                            const float4 bl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
-                            const float y0 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 0]), cs.x, -bh.x) - bl.x;
-                            const float y1 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 1]), cs.y, -bh.y) - bl.y;
-                            const float y2 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 2]), cs.z, -bh.z) - bl.z;
-                            const float y3 = fmaf(__uint_as_float(v[16 * h + 4 * j4 + 3]), cs.w, -bh.w) - bl.w;
-                            part = fmaf(y0, y0, part);
-                            part = fmaf(y1, y1, part);
-                            part = fmaf(y2, y2, part);
-                            part = fmaf(y3, y3, part);
-                        }
-                        q += (double)part;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 cs = *reinterpret_cast<const float4*>(sc_p + 4 * j4);
+                        const float4 bh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
+                        const float4 bl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
+                        const float y0 = fmaf(__uint_as_float(v[4 * j4 + 0]), cs.x, -bh.x) - bl.x;
+                        const float y1 = fmaf(__uint_as_float(v[4 * j4 + 1]), cs.y, -bh.y) - bl.y;
+                        const float y2 = fmaf(__uint_as_float(v[4 * j4 + 2]), cs.z, -bh.z) - bl.z;
+                        const float y3 = fmaf(__uint_as_float(v[4 * j4 + 3]), cs.w, -bh.w) - bl.w;
+                        part_q = fmaf(y0, y0, part_q);
+                        part_q = fmaf(y1, y1, part_q);
+                        part_q = fmaf(y2, y2, part_q);
+                        part_q = fmaf(y3, y3, part_q);
                     }
+                    q += (double)part_q;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                if (half == 1) qpart[s * TILE_M + row] = q;
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                if (half == 0) {
-                    q += qpart[s * TILE_M + row];
+                if (part > 0) qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
+                const long long e3 = clock64();
+                asm volatile("bar.sync 3, 512;" ::: "memory");
+                q_work += e3 - e2; q_bar += clock64() - e3;
+                if (part == 0) {
+                    q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
+                         qpart[(2 * 2 + s) * TILE_M + row];
                     const double wlp =
                         (-0.5 * ((double)D * LOG2PI + q) + cst_s[s * 2]) + cst_s[s * 2 + 1];
                     if (mode == 0) {
@@ -557,10 +570,17 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     }
                 }
             }
-            if (half == 0 && mode == 1 && n < N) {
+            if (part == 0 && mode == 1 && n < N) {
                 mix[n] = k1;
                 cand[n] = (K > 1 && v1 - v2 < near_tie) ? k2 : -1;   // runner-up to re-check in fp64
             }
+        }
+        if (prof != nullptr && blockIdx.x == 0 && (et == 0 || et == 511)) {
+            unsigned long long* pp = prof + (et == 0 ? 8 : 12);
+            pp[0] = (unsigned long long)(clock64() - q_start);
+            pp[1] = (unsigned long long)q_bar;
+            pp[2] = (unsigned long long)q_wait;
+            pp[3] = (unsigned long long)q_work;
         }
     }
     tc_fence_before();
@@ -1216,9 +1236,23 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     uint32_t cols = 32;
     while (cols < 2u * DP) cols <<= 1;
     const int grid = (int)std::min<long long>(n_tiles, sms);
-    tc::estep_tc_kernel<<<grid, 320, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
+    static unsigned long long* prof_dev = nullptr;
+    static int prof_on = -1;
+    if (prof_on < 0) {
+        prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
+        if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
+    }
+    tc::estep_tc_kernel<<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
                                                     w.bt, w.sc, w.cst, resp, mode, mix, w.cand,
-                                                    0.05);
+                                                    0.05, prof_on ? prof_dev : nullptr);
+    if (prof_on) {
+        unsigned long long h[16];
+        cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[estep_tc cta0] mma: total %llu wait_tmem %llu wait_blo(+a) %llu wait_bhi %llu "
+                        "issue %llu | epi(part0): total %llu barriers %llu wait_tmfull %llu work %llu | "
+                        "epi(part3): barriers %llu wait %llu work %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[13], h[14], h[15]);
+    }
     KW_CUDA_CHECK(cudaGetLastError());
     if (mode == 1) {
         tc::refine_argmax_kernel<<<sms * 4, 256, 0, st>>>(N, D, X, pc, aux, mix, w.cand);
