@@ -115,6 +115,14 @@ int kw_gmm_estep(int64_t n_frames, const double* x_dev, int n_components, int di
                  double* resp_dev, double* stats_dev, int precision,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Hard assignment argmax_k of the weighted log-probability (sklearn predict; with identity
+ * precisions and equal weights this is the k-means assignment step).  labels_dev[n_frames] int32.
+ * With precision 1 near-ties are re-evaluated in fp64, so the labels equal the fp64 argmax. */
+int kw_gmm_hard_labels(int64_t n_frames, const double* x_dev, int n_components, int dim,
+                       const double* means_dev, const double* prec_chol_dev, const double* aux_dev,
+                       int32_t* labels_dev, int precision,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* M-step sufficient statistics around centres_dev (K, D) from resp_dev.  Frames with
  * r_nk <= 1e-16 are skipped (their total weight is below the rounding of n_k), so the cost
  * follows the sparsity of the posterior; the summation order is fixed (bitwise reproducible). */

@@ -664,6 +664,25 @@ extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const 
     return KW_OK;
 }
 
+extern "C" int kw_gmm_hard_labels(int64_t N, const double* x_dev, int K, int D,
+                                  const double* means_dev, const double* prec_chol_dev,
+                                  const double* aux_dev, int32_t* labels_dev, int precision,
+                                  void* workspace_dev, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_hard_labels: N, K, D must be positive");
+    KW_REQUIRE(precision == 0 || precision == 1, "GMM precision must be 0 (fp64) or 1 (tensor)");
+    GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    if (precision == 1)
+        return estep_tc(N, x_dev, K, D, means_dev, prec_chol_dev, aux_dev, nullptr, nullptr, 1,
+                        labels_dev, static_cast<char*>(workspace_dev) + w.bytes,
+                        workspace_bytes - w.bytes, st);
+    return estep_fp64(N, x_dev, K, D, prec_chol_dev, aux_dev, nullptr, nullptr, 1, labels_dev, st);
+}
+
 extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, int D,
                                        const double* resp_dev, const double* centres_dev,
                                        double* stats_dev, int precision, void* workspace_dev,

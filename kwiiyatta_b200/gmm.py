@@ -148,9 +148,11 @@ class GaussianMixture:
         from . import kmeans
         seed = self.random_state
         if self.init_params == 'kmeans':
-            labels = kmeans.kmeans_labels(x, k, seed, self.process_group)
+            labels = kmeans.kmeans_labels(x, k, seed, self.process_group,
+                                          precision=self.precision)
         elif self.init_params == 'random_from_data':
-            labels = kmeans.kmeans_labels(x, k, seed, self.process_group, n_lloyd=0)
+            labels = kmeans.kmeans_labels(x, k, seed, self.process_group, n_lloyd=0,
+                                          precision=self.precision)
         else:
             raise NotImplementedError(f'init_params={self.init_params!r} is not built')
         r = torch.zeros((k, n), dtype=torch.float64, device=x.device)

@@ -1,18 +1,23 @@
 """K-means initial labels for the EM (sklearn ``init_params='kmeans'``,
-sklearn/mixture/_base.py:119-128).
+sklearn/mixture/_base.py:119-128) -- SURVEY.md section 8f rank 1.
 
-Scope note: this is the step *before* the hot path.  It runs on
-the GPU with stock torch tensor ops (k-means++ seeding, Lloyd passes), not hand-written
-kernels, and is not bit-compatible with any sklearn KMeans version (their seeding consumes the
-RNG differently across versions).  Parity tests inject ``resp_init`` instead."""
+Lloyd passes run on this library's own kernels: the assignment step is ``kw_gmm_hard_labels``
+with identity precisions and equal weights (argmin of the squared distance; tcgen05 contraction
+with fp64 re-check of near-ties when ``precision='tc'``), the centre update is the first-moment
+part of ``kw_gmm_mstep_accumulate`` on one-hot responsibilities, all-reduced across ranks.  Only
+the k-means++ seeding (K sequential D^2-weighted draws) uses stock torch ops.  The result is not
+bit-compatible with any sklearn KMeans version (their seeding consumes the RNG differently
+across versions); parity tests inject ``resp_init`` instead."""
 import numpy as np
+
+from . import _lib
 
 
 def _dist2(x, c):
     return (x * x).sum(1, keepdim=True) - 2.0 * (x @ c.t()) + (c * c).sum(1)[None, :]
 
 
-def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30):
+def _seed_centres(x, k, seed, group):
     import torch
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -23,33 +28,72 @@ def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30):
     if rank == 0:
         if n < k:
             raise ValueError(f'need at least {k} frames on rank 0 to seed k-means, got {n}')
-        first = int(rs.randint(n))
-        centres[0] = x[first]
+        centres[0] = x[int(rs.randint(n))]
         closest = _dist2(x, centres[0:1]).squeeze(1).clamp_min_(0.0)
         for j in range(1, k):
             probs = (closest / closest.sum()).cpu().numpy()
-            idx = int(np.searchsorted(np.cumsum(probs), rs.random_sample()))
-            idx = min(idx, n - 1)
+            idx = min(int(np.searchsorted(np.cumsum(probs), rs.random_sample())), n - 1)
             centres[j] = x[idx]
-            closest = torch.minimum(closest, _dist2(x, centres[j:j + 1]).squeeze(1).clamp_min_(0.0))
+            closest = torch.minimum(closest,
+                                    _dist2(x, centres[j:j + 1]).squeeze(1).clamp_min_(0.0))
     if multi:
         dist.broadcast(centres, src=dist.get_global_rank(group, 0) if group is not None else 0,
                        group=group)
-    labels = _dist2(x, centres).argmin(1)
-    for _ in range(n_lloyd):
-        sums = torch.zeros((k, d), dtype=x.dtype, device=x.device)
-        sums.index_add_(0, labels, x)
-        counts = torch.bincount(labels, minlength=k).to(x.dtype)
-        if multi:
-            dist.all_reduce(sums, group=group)
-            dist.all_reduce(counts, group=group)
-        nz = counts > 0
-        centres[nz] = sums[nz] / counts[nz][:, None]
-        new = _dist2(x, centres).argmin(1)
-        changed = (new != labels).sum().to(torch.float64)
-        if multi:
-            dist.all_reduce(changed, group=group)
-        labels = new
-        if changed.item() == 0:
+    return centres
+
+
+def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30, precision=0):
+    """Hard labels (int64 CUDA tensor) of the device-resident frames ``x`` (N, D) float64."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.lib()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    n, d = x.shape
+    x = x.contiguous()
+    centres = _seed_centres(x, k, seed, group).contiguous()
+    f64 = dict(dtype=torch.float64, device=x.device)
+    eye = torch.eye(d, **f64).expand(k, d, d).contiguous()      # prec_chol = I
+    aux = torch.zeros((k, d + 2), **f64)                         # [b = mu, log|L| = 0, log w = 0]
+    labels = torch.empty(n, dtype=torch.int32, device=x.device)
+    ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, precision)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+    npad = lib.kw_gmm_resp_len(n, k) // k
+    resp = torch.zeros((k, npad), **f64)
+    stats = torch.zeros(lib.kw_gmm_stats_len(k, d), **f64)
+    sb = 1 + d + d * d
+    stream = _lib.stream_ptr(torch)
+    _lib.check(lib.kw_gmm_pack_frames(n, x.data_ptr(), k, d, precision, ws.data_ptr(), ws_bytes,
+                                      stream), 'kw_gmm_pack_frames')
+    rows = torch.arange(n, device=x.device)
+    prev = None
+    for it in range(max(n_lloyd, 0) + 1):
+        aux[:, :d] = centres
+        _lib.check(lib.kw_gmm_hard_labels(n, x.data_ptr(), k, d, centres.data_ptr(),
+                                          eye.data_ptr(), aux.data_ptr(), labels.data_ptr(),
+                                          precision, ws.data_ptr(), ws_bytes, stream),
+                   'kw_gmm_hard_labels')
+        lab = labels.long()
+        if it == n_lloyd:
             break
-    return labels
+        if prev is not None:
+            changed = (lab != prev).sum().to(torch.float64)
+            if multi:
+                dist.all_reduce(changed, group=group)
+            if changed.item() == 0:
+                break
+        prev = lab
+        resp.zero_()
+        resp[lab, rows] = 1.0
+        _lib.check(lib.kw_gmm_mstep_accumulate(n, x.data_ptr(), k, d, resp.data_ptr(),
+                                               centres.data_ptr(), stats.data_ptr(), precision,
+                                               ws.data_ptr(), ws_bytes, stream),
+                   'kw_gmm_mstep_accumulate')
+        if multi:
+            dist.all_reduce(stats, group=group)
+        blocks = stats[:k * sb].view(k, sb)
+        counts = blocks[:, 0]
+        nz = counts > 0
+        centres = centres.clone()
+        centres[nz] = centres[nz] + blocks[nz, 1:1 + d] / counts[nz][:, None]
+        centres = centres.contiguous()
+    return labels.long()

@@ -102,3 +102,21 @@ def test_kmeans_init_runs_and_is_seeded(cuda):
     b = GaussianMixture(n_components=4, random_state=0, max_iter=20).fit(x)
     assert np.array_equal(a.means_, b.means_) and a.n_iter_ == b.n_iter_
     assert np.isfinite(a.lower_bound_)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'tc'])
+def test_kmeans_labels_are_a_lloyd_fixed_point(cuda, precision):
+    """kmeans.py runs Lloyd on the library's own kernels: at exit every frame is assigned to its
+    nearest centre (means of the clusters)."""
+    import torch
+    from kwiiyatta_b200 import kmeans
+    rng = np.random.default_rng(11)
+    x = _blobs(rng, 3000, 20, 5)
+    xd = torch.from_numpy(x).cuda()
+    lab = kmeans.kmeans_labels(xd, 5, seed=3, n_lloyd=50,
+                               precision=1 if precision == 'tc' else 0).cpu().numpy()
+    assert lab.shape == (3000,) and set(np.unique(lab)) <= set(range(5))
+    centres = np.stack([x[lab == j].mean(0) if (lab == j).any() else np.full(20, 1e9)
+                        for j in range(5)])
+    d2 = ((x[:, None, :] - centres[None]) ** 2).sum(-1)
+    assert (d2.argmin(1) == lab).mean() >= 0.999
