@@ -360,7 +360,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so the compiler knows the role branches are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t a_bytes = 2u * TILE_M * dpb_of(DP) * 2;
     const uint32_t b_bytes = (uint32_t)bmat_elems(DP) * 2;
     const uint32_t lbo = 128;
@@ -740,7 +741,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so the compiler knows the role branches are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n_items = K * n_chunks;
     const uint32_t part_b = (uint32_t)MT * G.DPB * 2;   // bytes of one part of a B stage
     const uint32_t part_a = (uint32_t)MT * G.DA * 2;
