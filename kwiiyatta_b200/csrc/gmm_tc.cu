@@ -125,6 +125,36 @@ __device__ __forceinline__ void umma_f16_scaled(uint32_t d_tmem, uint64_t a_desc
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
         : "memory");
 }
+// Variants with the A operand in tensor memory (lanes = rows, 8 columns per 16 fp16 of K).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_scaled(uint32_t d_tmem, uint32_t a_tmem,
+                                                   uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+// smem (canonical K-major tile, 128 rows x 32 bytes) -> TMEM (128 lanes x 8 columns)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t s_desc) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "@q tcgen05.cp.cta_group::1.128x256b [%0], %1;\n\t}"
+        ::"r"(taddr), "l"(s_desc)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
@@ -294,8 +324,8 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
         }
         colinv[j] = 1.0 / scale;
         sck[j] = (float)scale;
-        sck[DP + j] = (float)bp;
-        sck[2 * DP + j] = (float)(bp - (double)(float)bp);
+        sck[DP + j] = -(float)bp;                                  // -b' (hi)
+        sck[2 * DP + j] = -(float)(bp - (double)(float)bp);        // -b' (lo)
     }
     if (threadIdx.x == 0) {
         cst[2 * k] = aux[(size_t)k * (D + 2) + D];
@@ -417,6 +447,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
             long long p_tm = 0, p_blo = 0, p_bhi = 0, p_issue = 0;
             const long long p_start = clock64();
+            const uint32_t ta_hi = tmem_base + 2u * (uint32_t)DP;       // A (hi) after the accumulators
+            const uint32_t ta_lo = ta_hi + (uint32_t)DP / 2;
             // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
             //   N = DP - 16 ks, B block at btri_off(ks), accumulator columns from 16 ks.
             const uint32_t ng = (uint32_t)DP / 8;
@@ -426,20 +458,30 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                     const uint64_t d_b_hi = s ? d_b_hi1 : d_b_hi0;
                     const uint32_t acc = tmem_base + s * (uint32_t)DP;
+                    if (k == 0) {
+                        // stage the frame tile (hi and scaled lo) in tensor memory once per tile:
+                        // every MMA of the tile then reads A from TMEM and shared-memory bandwidth
+                        // is left to the L_k blocks.  cp and mma execute in issue order.
+                        mbar_wait(bars + BAR_A_FULL, (uint32_t)it & 1u);
+                        tc_fence_after();
+                        for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
+                            tmem_cp_128x256b(ta_hi + 8 * ks, d_a_hi + ks * KSTEP);
+                            tmem_cp_128x256b(ta_lo + 8 * ks, d_a_lo + ks * KSTEP);
+                        }
+                        umma_commit(bars + BAR_A_EMPTY);
+                    }
                     const long long c0 = clock64();
                     mbar_wait(bars + BAR_TM_EMPTY0 + s, (u & 1u) ^ 1u);
                     const long long c1 = clock64();
                     mbar_wait(bars + BAR_BLO_FULL, g & 1u);
-                    if (k == 0) mbar_wait(bars + BAR_A_FULL, (uint32_t)it & 1u);
                     const long long c2 = clock64();
                     p_tm += c1 - c0; p_blo += c2 - c1;
                     tc_fence_after();
                     {
-                        uint64_t da = d_a_hi, db = d_b_lo;          // x_hi . l_lo
+                        uint64_t db = d_b_lo;          // x_hi . l_lo
                         uint32_t id = idesc, cols = (uint32_t)DP;
                         for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
-                            umma_f16(acc + 16 * ks, da, db, id, ks > 0 ? 1u : 0u);
-                            da += KSTEP;
+                            umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db, id, ks > 0 ? 1u : 0u);
                             db += (uint64_t)(ng - 2 * ks) * 16;      // next block: (ng-2ks)*256 B
                             cols -= 16;
                             id = make_idesc(TILE_M, (int)cols);
@@ -452,32 +494,30 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     p_bhi += c4 - c3; p_issue += c3 - c2;
                     tc_fence_after();
                     {
-                        uint64_t da = d_a_lo, db = d_b_hi;          // x_lo . l_hi
+                        uint64_t db = d_b_hi;          // x_lo . l_hi
                         uint32_t id = idesc, cols = (uint32_t)DP;
                         for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
-                            umma_f16(acc + 16 * ks, da, db, id, 1u);
-                            da += KSTEP;
+                            umma_f16_ts(acc + 16 * ks, ta_lo + 8 * ks, db, id, 1u);
                             db += (uint64_t)(ng - 2 * ks) * 16;
                             cols -= 16;
                             id = make_idesc(TILE_M, (int)cols);
                         }
                     }
                     {
-                        uint64_t da = d_a_hi, db = d_b_hi;          // acc = acc * 2^-11 + x_hi . l_hi
-                        umma_f16_scaled(acc, da, db, idesc);        // ks = 0 spans every column
+                        uint64_t db = d_b_hi;          // acc = acc * 2^-11 + x_hi . l_hi
+                        umma_f16_ts_scaled(acc, ta_hi, db, idesc);  // ks = 0 spans every column
                         uint32_t cols = (uint32_t)DP;
                         for (uint32_t ks = 1; ks < (uint32_t)ksteps; ++ks) {
-                            da += KSTEP;
                             db += (uint64_t)(ng - 2 * (ks - 1)) * 16;
                             cols -= 16;
-                            umma_f16(acc + 16 * ks, da, db, make_idesc(TILE_M, (int)cols), 1u);
+                            umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db,
+                                        make_idesc(TILE_M, (int)cols), 1u);
                         }
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
                     p_issue += clock64() - c4;
                 }
-                umma_commit(bars + BAR_A_EMPTY);
             }
             if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
                 prof[0] = (unsigned long long)(clock64() - p_start);
@@ -528,27 +568,35 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * (uint32_t)DP;
                 double q = 0.0;
-                for (int c = c_begin; c < c_end; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + c * 16, v);
-                    tmem_ld_wait();
-                    const float* sc_p = sk + c * 16;
-                    float part_q = 0.f;
+                // all TMEM loads of this thread's (at most 3) chunks are issued before one wait
+                uint32_t v[3][16];
+#pragma unroll
+                for (int h = 0; h < 3; ++h)
+                    if (c_begin + h < c_end) tmem_ld16(taddr + (c_begin + h) * 16, v[h]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    if (c_begin + h >= c_end) break;
+                    const float* sc_p = sk + (c_begin + h) * 16;
+                    // packed fp32x2: y = acc * 2^t - b'_hi - b'_lo,  part += y * y
+                    float2 p2 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 cs = *reinterpret_cast<const float4*>(sc_p + 4 * j4);
-                        const float4 bh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
-                        const float4 bl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
-                        const float y0 = fmaf(__uint_as_float(v[4 * j4 + 0]), cs.x, -bh.x) - bl.x;
-                        const float y1 = fmaf(__uint_as_float(v[4 * j4 + 1]), cs.y, -bh.y) - bl.y;
-                        const float y2 = fmaf(__uint_as_float(v[4 * j4 + 2]), cs.z, -bh.z) - bl.z;
-                        const float y3 = fmaf(__uint_as_float(v[4 * j4 + 3]), cs.w, -bh.w) - bl.w;
-                        part_q = fmaf(y0, y0, part_q);
-                        part_q = fmaf(y1, y1, part_q);
-                        part_q = fmaf(y2, y2, part_q);
-                        part_q = fmaf(y3, y3, part_q);
+                        const float4 nbh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
+                        const float4 nbl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
+                        float2 ya = __ffma2_rn(make_float2(__uint_as_float(v[h][4 * j4 + 0]),
+                                                           __uint_as_float(v[h][4 * j4 + 1])),
+                                               make_float2(cs.x, cs.y), make_float2(nbh.x, nbh.y));
+                        float2 yb = __ffma2_rn(make_float2(__uint_as_float(v[h][4 * j4 + 2]),
+                                                           __uint_as_float(v[h][4 * j4 + 3])),
+                                               make_float2(cs.z, cs.w), make_float2(nbh.z, nbh.w));
+                        ya = __fadd2_rn(ya, make_float2(nbl.x, nbl.y));
+                        yb = __fadd2_rn(yb, make_float2(nbl.z, nbl.w));
+                        p2 = __ffma2_rn(ya, ya, p2);
+                        p2 = __ffma2_rn(yb, yb, p2);
                     }
-                    q += (double)part_q;
+                    q += (double)(p2.x + p2.y);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1008,7 +1056,13 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[c][j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; j += 2) {
+                            const float2 t = __fadd2_rn(
+                                make_float2(acc[c][j], acc[c][j + 1]),
+                                make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                            acc[c][j] = t.x;
+                            acc[c][j + 1] = t.y;
+                        }
                     }
                 }
                 if (c2_begin < c2_end) {
@@ -1016,7 +1070,13 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     tmem_ld16(tbase + (uint32_t)G.N1 + (uint32_t)c2_begin * 16, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[5][j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; j += 2) {
+                        const float2 t = __fadd2_rn(
+                            make_float2(acc[5][j], acc[5][j + 1]),
+                            make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                        acc[5][j] = t.x;
+                        acc[5][j + 1] = t.y;
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1236,7 +1296,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     uint32_t cols = 32;
-    while (cols < 2u * DP) cols <<= 1;
+    while (cols < 3u * DP) cols <<= 1;      // two accumulator stages + the frame tile (hi, lo)
     const int grid = (int)std::min<long long>(n_tiles, sms);
     static unsigned long long* prof_dev = nullptr;
     static int prof_on = -1;
