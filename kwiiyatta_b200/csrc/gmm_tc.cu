@@ -733,7 +733,7 @@ struct MstepGeom {
     int N1, N2;          // accumulator widths of the two MMAs (N2 = 0 when DP <= 128)
     int a_win2;          // first feature group of MMA2's row window
     uint32_t b_stage, a_stage;   // bytes per smem stage (hi + lo)
-    uint32_t off_b, off_a, off_rs, off_mu, off_bars, off_tmem, total;
+    uint32_t off_b, off_a, off_rs, off_mu, off_flags, off_bars, off_tmem, total;
     int partial_len;     // doubles per work item
 };
 __host__ __device__ inline MstepGeom mstep_geom(int DP) {
@@ -753,6 +753,7 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     o = (o + 15u) & ~15u;
     g.off_mu = o;   o += (uint32_t)g.DA * 4;
     o = (o + 15u) & ~15u;
+    g.off_flags = o; o += 64;    // rmax[2][2] (float), tile_skip[2], group_empty[2] (int)
     g.off_bars = o; o += 16 * 8;
     g.off_tmem = o; o += 16;
     g.total = o;
@@ -787,6 +788,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     unsigned char* a_base = smem + G.off_a;
     float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
     float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
+    volatile float* rmax_s = reinterpret_cast<volatile float*>(smem + G.off_flags);       // [2]
+    volatile int* tile_skip = reinterpret_cast<volatile int*>(smem + G.off_flags + 16);  // [2 stages]
+    volatile int* group_empty = reinterpret_cast<volatile int*>(smem + G.off_flags + 32); // [2 stages]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
     // warp index through a shuffle so the compiler knows the role branches are warp-uniform
@@ -874,6 +878,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             (void)swap_strides;
             long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
             const long long p_start = clock64();
+            bool group_has_data = false;
             uint32_t g = 0, f = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int k, t0, t1;
@@ -894,24 +899,36 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     tc_fence_after();
                     const uint32_t acc1 = tmem_base + ts * acc_cols;
                     const uint32_t acc2 = acc1 + (uint32_t)G.N1;
+                    if (in_group == 0) group_has_data = false;
+                    const bool skip = tile_skip[s] != 0;     // written by the generators (a_full)
                     const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
                     const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
+                    if (!skip) {
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         uint64_t da = (pass == 2) ? a_lo_d : a_hi_d;     // A lo in pass 2
                         uint64_t db = (pass == 1) ? b_lo_d : b_hi_d;     // B lo in pass 1
 #pragma unroll
                         for (int ks = 0; ks < MT / 16; ++ks) {
-                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (in_group > 0 ? 1u : 0u);
+                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (group_has_data ? 1u : 0u);
                             umma_f16(acc1, da, db, idesc1, accum);
                             if (has2) umma_f16(acc2, da + win_a, db + win_b, idesc2, accum);
                             da += step_a;
                             db += step_b;
                         }
                     }
+                    group_has_data = true;
+                    }
                     umma_commit(bars + MB_A_EMPTY + s);
                     umma_commit(bars + MB_B_EMPTY + s);
-                    if (last) { umma_commit(bars + MB_TM_FULL + ts); ++f; }
+                    if (last) {
+                        // tell the epilogue whether this flush group accumulated anything
+                        if (lane == 0) group_empty[ts] = group_has_data ? 0 : 1;
+                        __threadfence_block();
+                        __syncwarp();
+                        umma_commit(bars + MB_TM_FULL + ts);
+                        ++f;
+                    }
                     p_issue += clock64() - c3;
                 }
             }
@@ -963,13 +980,21 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
                 if (gt < MT) {      // generator warps 0 and 1, all lanes
-                    float rs = (float)r_next;
-                    r_s[s * MT + gt] = rs;
+                    float rm = (float)r_next;
+                    double rs = (double)rm;        // n_k sums the fp32 weights the MMAs see
+                    r_s[s * MT + gt] = rm;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-                    nacc += (double)rs;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                        rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+                    }
+                    nacc += rs;
+                    if (lane == 0) rmax_s[s * 2 + (gt >> 5)] = rm;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
+                // a tile whose responsibilities for this component are all <= 1e-16 contributes
+                // nothing representable: no operand generation, no MMAs
+                const bool skip = fmaxf(rmax_s[s * 2], rmax_s[s * 2 + 1]) <= 1e-16f;
                 r_next = load_r(t + 1);     // consumed next iteration: latency hidden
                 const long long c0 = clock64();
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
@@ -977,12 +1002,13 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
                 const long long c2 = clock64();
                 g_b += c1 - c0; g_a += c2 - c1;
+                if (gt == 0) tile_skip[s] = skip ? 1 : 0;   // the MMA warp is done with this stage
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
                 const float* rt = r_s + s * MT;
 #pragma unroll
                 for (int q = 0; q < QMAX; ++q) {
-                    if (c_r[q] < 0) continue;
+                    if (c_r[q] < 0 || skip) continue;
                     const uint4 hv = *reinterpret_cast<const uint4*>(bh + c_bo[q]);
                     const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + c_bo[q]);
                     const float4 ma = *reinterpret_cast<const float4*>(mu_s + c_mu[q]);
@@ -1048,10 +1074,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 const uint32_t ts = f & 1u, tu = f >> 1;
                 mbar_wait(bars + MB_TM_FULL + ts, tu & 1u);
                 tc_fence_after();
+                const bool empty = group_empty[ts] != 0;
                 const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    if (c1_begin + c < c1_end) {
+                    if (!empty && c1_begin + c < c1_end) {
                         uint32_t v[16];
                         tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
                         tmem_ld_wait();
@@ -1065,7 +1092,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         }
                     }
                 }
-                if (c2_begin < c2_end) {
+                if (!empty && c2_begin < c2_end) {
                     uint32_t v[16];
                     tmem_ld16(tbase + (uint32_t)G.N1 + (uint32_t)c2_begin * 16, v);
                     tmem_ld_wait();
