@@ -358,7 +358,7 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
     uint32_t o = 0;
     s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
     s.b_hi = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
-    s.b_lo = o;  o += (uint32_t)bmat_elems(DP) * 2;
+    s.b_lo = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
     s.scl = o;   o += 2u * 3 * DP * 4;                 // two stages of [scale | b' hi | b' lo]
     s.cst = o;   o += 2u * 2 * 8;
     s.qpart = o; o += 3u * 2 * TILE_M * 8;
@@ -368,7 +368,8 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
     return s;
 }
 
-enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL, BAR_BLO_EMPTY, BAR_BHI_FULL0, BAR_BHI_FULL1,
+enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL0, BAR_BLO_FULL1, BAR_BLO_EMPTY0, BAR_BLO_EMPTY1,
+       BAR_BHI_FULL0, BAR_BHI_FULL1,
        BAR_BHI_EMPTY0, BAR_BHI_EMPTY1, BAR_TM_FULL0, BAR_TM_FULL1, BAR_TM_EMPTY0, BAR_TM_EMPTY1 };
 
 __global__ void __launch_bounds__(576, 1)
@@ -400,7 +401,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     const uint32_t idesc = make_idesc(TILE_M, DP);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 12; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 16u : 1u);
+        for (int i = 0; i < 14; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 16u : 1u);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
@@ -417,9 +418,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 for (int k = 0; k < K; ++k) {
                     const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
                     const __half* bk = bt + (size_t)k * 2 * bmat_elems(DP);
-                    mbar_wait(bars + BAR_BLO_EMPTY, (g & 1u) ^ 1u);
-                    mbar_expect_tx(bars + BAR_BLO_FULL, b_bytes);
-                    bulk_g2s(b_lo, bk + bmat_elems(DP), b_bytes, bars + BAR_BLO_FULL);
+                    mbar_wait(bars + BAR_BLO_EMPTY0 + s, (u & 1u) ^ 1u);
+                    mbar_expect_tx(bars + BAR_BLO_FULL0 + s, b_bytes);
+                    bulk_g2s(b_lo + (size_t)s * bmat_elems(DP), bk + bmat_elems(DP), b_bytes,
+                             bars + BAR_BLO_FULL0 + s);
                     mbar_wait(bars + BAR_BHI_EMPTY0 + s, (u & 1u) ^ 1u);
                     mbar_expect_tx(bars + BAR_BHI_FULL0 + s, b_bytes);
                     bulk_g2s(b_hi0 + (size_t)s * bmat_elems(DP), bk, b_bytes,
@@ -441,7 +443,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             // critical path of the whole kernel, so nothing else is computed per MMA).
             const uint64_t d_a_hi = make_desc(smem_u32(a_hi), lbo, sbo_a);
             const uint64_t d_a_lo = make_desc(smem_u32(a_lo), lbo, sbo_a);
-            const uint64_t d_b_lo = make_desc(smem_u32(b_lo), 128, 256);
+            const uint64_t d_b_lo0 = make_desc(smem_u32(b_lo), 128, 256);
+            const uint64_t d_b_lo1 = make_desc(smem_u32(b_lo + bmat_elems(DP)), 128, 256);
             const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), 128, 256);
             const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), 128, 256);
             constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
@@ -473,12 +476,12 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     const long long c0 = clock64();
                     mbar_wait(bars + BAR_TM_EMPTY0 + s, (u & 1u) ^ 1u);
                     const long long c1 = clock64();
-                    mbar_wait(bars + BAR_BLO_FULL, g & 1u);
+                    mbar_wait(bars + BAR_BLO_FULL0 + s, u & 1u);
                     const long long c2 = clock64();
                     p_tm += c1 - c0; p_blo += c2 - c1;
                     tc_fence_after();
                     {
-                        uint64_t db = d_b_lo;          // x_hi . l_lo
+                        uint64_t db = s ? d_b_lo1 : d_b_lo0;          // x_hi . l_lo
                         uint32_t id = idesc, cols = (uint32_t)DP;
                         for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
                             umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db, id, ks > 0 ? 1u : 0u);
@@ -487,7 +490,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             id = make_idesc(TILE_M, (int)cols);
                         }
                     }
-                    umma_commit(bars + BAR_BLO_EMPTY);
+                    umma_commit(bars + BAR_BLO_EMPTY0 + s);
                     const long long c3 = clock64();
                     mbar_wait(bars + BAR_BHI_FULL0 + s, u & 1u);
                     const long long c4 = clock64();
