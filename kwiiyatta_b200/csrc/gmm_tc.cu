@@ -63,6 +63,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Cycle counter for the optional role profiles; compiled out of the production kernels (reading
+// the clock serialises the issuing warp).
+template <bool PROF> __device__ __forceinline__ long long tick() {
+    if constexpr (PROF) return clock64();
+    return 0;
+}
 // Bounded wait: a protocol bug must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -372,6 +378,7 @@ enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL0, BAR_BLO_FULL1, BAR_BLO_EMPTY0
        BAR_BHI_FULL0, BAR_BHI_FULL1,
        BAR_BHI_EMPTY0, BAR_BHI_EMPTY1, BAR_TM_FULL0, BAR_TM_FULL1, BAR_TM_EMPTY0, BAR_TM_EMPTY1 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(576, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
@@ -449,7 +456,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), 128, 256);
             constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
             long long p_tm = 0, p_blo = 0, p_bhi = 0, p_issue = 0;
-            const long long p_start = clock64();
+            const long long p_start = tick<PROF>();
             const uint32_t ta_hi = tmem_base + 2u * (uint32_t)DP;       // A (hi) after the accumulators
             const uint32_t ta_lo = ta_hi + (uint32_t)DP / 2;
             // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
@@ -473,11 +480,11 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         }
                         umma_commit(bars + BAR_A_EMPTY);
                     }
-                    const long long c0 = clock64();
+                    const long long c0 = tick<PROF>();
                     mbar_wait(bars + BAR_TM_EMPTY0 + s, (u & 1u) ^ 1u);
-                    const long long c1 = clock64();
+                    const long long c1 = tick<PROF>();
                     mbar_wait(bars + BAR_BLO_FULL0 + s, u & 1u);
-                    const long long c2 = clock64();
+                    const long long c2 = tick<PROF>();
                     p_tm += c1 - c0; p_blo += c2 - c1;
                     tc_fence_after();
                     {
@@ -491,9 +498,9 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         }
                     }
                     umma_commit(bars + BAR_BLO_EMPTY0 + s);
-                    const long long c3 = clock64();
+                    const long long c3 = tick<PROF>();
                     mbar_wait(bars + BAR_BHI_FULL0 + s, u & 1u);
-                    const long long c4 = clock64();
+                    const long long c4 = tick<PROF>();
                     p_bhi += c4 - c3; p_issue += c3 - c2;
                     tc_fence_after();
                     {
@@ -519,11 +526,11 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
-                    p_issue += clock64() - c4;
+                    p_issue += tick<PROF>() - c4;
                 }
             }
             if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
-                prof[0] = (unsigned long long)(clock64() - p_start);
+                prof[0] = (unsigned long long)(tick<PROF>() - p_start);
                 prof[1] = (unsigned long long)p_tm;
                 prof[2] = (unsigned long long)p_blo;
                 prof[3] = (unsigned long long)p_bhi;
@@ -542,7 +549,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
         const int c_begin = (ksteps * part) / 4, c_end = (ksteps * (part + 1)) / 4;
         const double LOG2PI = 1.8378770664093453;
         long long q_bar = 0, q_wait = 0, q_work = 0;
-        const long long q_start = clock64();
+        const long long q_start = tick<PROF>();
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long n = (long long)tile * TILE_M + row;
@@ -562,11 +569,11 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 if (et < 3 * DP) sk[et] = pre;
                 if (et < 2) cst_s[s * 2 + et] = pre_c;
                 if (k + 1 < K) fetch(k + 1);
-                const long long e0 = clock64();
+                const long long e0 = tick<PROF>();
                 asm volatile("bar.sync 1, 512;" ::: "memory");
-                const long long e1 = clock64();
+                const long long e1 = tick<PROF>();
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
-                const long long e2 = clock64();
+                const long long e2 = tick<PROF>();
                 q_bar += e1 - e0; q_wait += e2 - e1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * (uint32_t)DP;
@@ -605,9 +612,9 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
                 if (part > 0) qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
-                const long long e3 = clock64();
+                const long long e3 = tick<PROF>();
                 asm volatile("bar.sync 3, 512;" ::: "memory");
-                q_work += e3 - e2; q_bar += clock64() - e3;
+                q_work += e3 - e2; q_bar += tick<PROF>() - e3;
                 if (part == 0) {
                     q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
                          qpart[(2 * 2 + s) * TILE_M + row];
@@ -629,7 +636,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
         }
         if (prof != nullptr && blockIdx.x == 0 && (et == 0 || et == 511)) {
             unsigned long long* pp = prof + (et == 0 ? 8 : 12);
-            pp[0] = (unsigned long long)(clock64() - q_start);
+            pp[0] = (unsigned long long)(tick<PROF>() - q_start);
             pp[1] = (unsigned long long)q_bar;
             pp[2] = (unsigned long long)q_wait;
             pp[3] = (unsigned long long)q_work;
@@ -779,6 +786,7 @@ __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restri
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(640, 1)
 mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
@@ -880,7 +888,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             const bool has2 = G.N2 > 0;
             (void)swap_strides;
             long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
-            const long long p_start = clock64();
+            const long long p_start = tick<PROF>();
             bool group_has_data = false;
             uint32_t g = 0, f = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -891,19 +899,19 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const int in_group = (t - t0) % M_FLUSH;
                     const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
                     const uint32_t ts = f & 1u, tu = f >> 1;
-                    const long long c0 = clock64();
+                    const long long c0 = tick<PROF>();
                     if (in_group == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
-                    const long long c1 = clock64();
+                    const long long c1 = tick<PROF>();
                     mbar_wait(bars + MB_A_FULL + s, u & 1u);
-                    const long long c2 = clock64();
+                    const long long c2 = tick<PROF>();
                     mbar_wait(bars + MB_B_FULL + s, u & 1u);
-                    const long long c3 = clock64();
+                    const long long c3 = tick<PROF>();
                     p_tm += c1 - c0; p_a += c2 - c1; p_b += c3 - c2;
                     tc_fence_after();
                     const uint32_t acc1 = tmem_base + ts * acc_cols;
                     const uint32_t acc2 = acc1 + (uint32_t)G.N1;
                     if (in_group == 0) group_has_data = false;
-                    const bool skip = tile_skip[s] != 0;     // written by the generators (a_full)
+                    const bool skip = tile_skip[s] != 0 || swap_strides == 1;   // (1 = timing experiment: no MMAs)
                     const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
                     const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
                     if (!skip) {
@@ -932,11 +940,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         umma_commit(bars + MB_TM_FULL + ts);
                         ++f;
                     }
-                    p_issue += clock64() - c3;
+                    p_issue += tick<PROF>() - c3;
                 }
             }
             if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
-                prof[0] = (unsigned long long)(clock64() - p_start);
+                prof[0] = (unsigned long long)(tick<PROF>() - p_start);
                 prof[1] = (unsigned long long)p_tm;
                 prof[2] = (unsigned long long)p_a;
                 prof[3] = (unsigned long long)p_b;
@@ -949,75 +957,75 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         reg_dec<88>();
         // ---------------- generators (warps 4..11): A = r (x' - mu') split into hi / lo ---------
         const int gt = threadIdx.x - 128;    // 0..255
-        const int fgroups = MT / 8, kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
-        const int n_chunks16 = fgroups * kgD * 8;
-        // The 16-byte chunks (8 features of one frame) this thread converts are the same for every
-        // tile: decode them once (no integer division in the tile loop).
-        constexpr int QMAX = 5;
-        uint32_t c_bo[QMAX], c_ao[QMAX];
-        int c_r[QMAX], c_mu[QMAX];
+        const int kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
+        // Chunk = 16 bytes = 8 features of one frame.  A thread keeps the SAME feature group for
+        // all its chunks, so mu' of that group lives in registers:
+        //   main: feature group gt/16 (0..15), frame-in-group gt&7, frame groups 4*((gt>>3)&1)+q;
+        //   extra (feature groups 16, 17 when DP > 128): threads < 128 take one more chunk.
+        const int fr = gt & 7;
+        const int featg_a = gt >> 4, fg_a0 = ((gt >> 3) & 1) * 4;
+        const bool on_a = featg_a < kgD;
+        const int featg_b = 16 + (gt >> 6), fg_b = (gt >> 3) & 7;
+        const bool on_b = gt < 128 && featg_b < kgD;
+        uint32_t a_bo[4], a_ao[4];
 #pragma unroll
-        for (int q = 0; q < QMAX; ++q) {
-            const int idx = gt + 256 * q;
-            const int fr = idx & 7, rest = idx >> 3;
-            const int featg = rest % kgD, fg = rest / kgD;
-            c_bo[q] = ((uint32_t)(fg * kgB + featg) * 8 + fr) * 16;
-            c_ao[q] = ((uint32_t)(fg * kgA + featg) * 8 + fr) * 16;
-            c_r[q] = (idx < n_chunks16) ? fg * 8 + fr : -1;
-            c_mu[q] = featg * 8;
+        for (int q = 0; q < 4; ++q) {
+            a_bo[q] = ((uint32_t)((fg_a0 + q) * kgB + featg_a) * 8 + fr) * 16;
+            a_ao[q] = ((uint32_t)((fg_a0 + q) * kgA + featg_a) * 8 + fr) * 16;
         }
+        const uint32_t b_bo = ((uint32_t)(fg_b * kgB + featg_b) * 8 + fr) * 16;
+        const uint32_t b_ao = ((uint32_t)(fg_b * kgA + featg_b) * 8 + fr) * 16;
         uint32_t g = 0;
-        long long g_b = 0, g_a = 0, g_gen = 0;
-        const long long g_start = clock64();
+        long long g_b = 0, g_a = 0, g_gen = 0, g_pub = 0, g_bar = 0;
+        const long long g_start = tick<PROF>();
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            for (int d = gt; d < G.DA; d += 256) mu_s[d] = mu32[(size_t)k * G.DA + d];
-            double nacc = 0.0;
+            float mu_a[8], mu_b[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                mu_a[e] = on_a ? mu32[(size_t)k * G.DA + featg_a * 8 + e] : 0.f;
+                mu_b[e] = on_b ? mu32[(size_t)k * G.DA + featg_b * 8 + e] : 0.f;
+            }
+            double nacc = 0.0;          // per-thread sum of this thread's frame weights (gt < MT)
             auto load_r = [&](int t) -> double {
                 const long long n = (long long)t * MT + gt;
                 return (gt < MT && t < t1 && n < N) ? respT[(size_t)k * Npad + n] : 0.0;
             };
-            double r_next = load_r(t0);
+            // publish the weights of a tile (fp32, as the MMAs will see them) and their maximum
+            auto publish_r = [&](double rv, uint32_t st) {
+                if (gt < MT) {      // generator warps 0 and 1, all lanes
+                    const float rf = (float)rv;
+                    r_s[st * MT + gt] = rf;
+                    nacc += (double)rf;
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(rf, 0.f)));
+                    if (lane == 0) rmax_s[st * 2 + (gt >> 5)] = __uint_as_float(mx);
+                }
+            };
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // previous item fully consumed
+            publish_r(load_r(t0), g & 1u);
+            double r_ahead = load_r(t0 + 1);      // weights are fetched two tiles ahead of use
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
-                if (gt < MT) {      // generator warps 0 and 1, all lanes
-                    float rm = (float)r_next;
-                    double rs = (double)rm;        // n_k sums the fp32 weights the MMAs see
-                    r_s[s * MT + gt] = rm;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        rs += __shfl_xor_sync(0xffffffffu, rs, o);
-                        rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
-                    }
-                    nacc += rs;
-                    if (lane == 0) rmax_s[s * 2 + (gt >> 5)] = rm;
-                }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
                 // a tile whose responsibilities for this component are all <= 1e-16 contributes
                 // nothing representable: no operand generation, no MMAs
                 const bool skip = fmaxf(rmax_s[s * 2], rmax_s[s * 2 + 1]) <= 1e-16f;
-                r_next = load_r(t + 1);     // consumed next iteration: latency hidden
-                const long long c0 = clock64();
+                const double r_next = r_ahead;         // loaded one tile ago
+                r_ahead = load_r(t + 2);
+                const long long c0 = tick<PROF>();
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
-                const long long c1 = clock64();
+                const long long c1 = tick<PROF>();
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
-                const long long c2 = clock64();
+                const long long c2 = tick<PROF>();
                 g_b += c1 - c0; g_a += c2 - c1;
                 if (gt == 0) tile_skip[s] = skip ? 1 : 0;   // the MMA warp is done with this stage
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
                 const float* rt = r_s + s * MT;
-#pragma unroll
-                for (int q = 0; q < QMAX; ++q) {
-                    if (c_r[q] < 0 || skip) continue;
-                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + c_bo[q]);
-                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + c_bo[q]);
-                    const float4 ma = *reinterpret_cast<const float4*>(mu_s + c_mu[q]);
-                    const float4 mb = *reinterpret_cast<const float4*>(mu_s + c_mu[q] + 4);
-                    const float r = rt[c_r[q]];
-                    const float mu8[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+                auto convert = [&](uint32_t bo, uint32_t ao, float r, const float* mu8) {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
+                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
                     const __half2* hp = reinterpret_cast<const __half2*>(&hv);
                     const __half2* lp = reinterpret_cast<const __half2*>(&lv);
                     uint4 oh, ol;
@@ -1033,8 +1041,16 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         ohp[e] = zh;
                         olp[e] = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
                     }
-                    *reinterpret_cast<uint4*>(ah + c_ao[q]) = oh;
-                    *reinterpret_cast<uint4*>(ah + part_a + c_ao[q]) = ol;
+                    *reinterpret_cast<uint4*>(ah + ao) = oh;
+                    *reinterpret_cast<uint4*>(ah + part_a + ao) = ol;
+                };
+                if (!skip && swap_strides != 2) {   // (2 = timing experiment: no generation)
+                    if (on_a) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            convert(a_bo[q], a_ao[q], rt[(fg_a0 + q) * 8 + fr], mu_a);
+                    }
+                    if (on_b) convert(b_bo, b_ao, rt[fg_b * 8 + fr], mu_b);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -1042,15 +1058,29 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_A_FULL + s);
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
-                g_gen += clock64() - c2;
+                const long long c3 = tick<PROF>();
+                g_gen += c3 - c2;
+                publish_r(r_next, s ^ 1u);                        // weights of the next tile
+                const long long c4 = tick<PROF>();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                g_pub += c4 - c3; g_bar += tick<PROF>() - c4;
+            }
+            // n_k of this item: fixed-order reduction of the per-thread sums (two warps)
+            if (gt < MT) {
+                double rs = nacc;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                nacc = rs;
             }
             if (gt == 0 || gt == 32) npartial[(size_t)item * 2 + (gt >> 5)] = nacc;
         }
         if (prof != nullptr && blockIdx.x == 0 && gt == 64) {
-            prof[8] = (unsigned long long)(clock64() - g_start);
+            prof[8] = (unsigned long long)(tick<PROF>() - g_start);
             prof[9] = (unsigned long long)g_b;
             prof[10] = (unsigned long long)g_a;
             prof[11] = (unsigned long long)g_gen;
+            prof[12] = (unsigned long long)g_pub;
+            prof[13] = (unsigned long long)g_bar;
         }
     } else {
         reg_inc<128>();
@@ -1323,7 +1353,9 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     KW_CUDA_CHECK(cudaGetLastError());
     const int sms = device_sms();
     const tc::EstepSmem L = tc::estep_smem(DP);
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel,
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     uint32_t cols = 32;
     while (cols < 3u * DP) cols <<= 1;      // two accumulator stages + the frame tile (hi, lo)
@@ -1334,9 +1366,14 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
         prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
         if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
     }
-    tc::estep_tc_kernel<<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt,
-                                                    w.bt, w.sc, w.cst, resp, mode, mix, w.cand,
-                                                    0.05, prof_on ? prof_dev : nullptr);
+    if (prof_on)
+        tc::estep_tc_kernel<true><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
+                                                              w.xt, w.bt, w.sc, w.cst, resp, mode,
+                                                              mix, w.cand, 0.05, prof_dev);
+    else
+        tc::estep_tc_kernel<false><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
+                                                               w.xt, w.bt, w.sc, w.cst, resp, mode,
+                                                               mix, w.cand, 0.05, nullptr);
     if (prof_on) {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1369,14 +1406,16 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
     const tc::MstepGeom G = tc::mstep_geom(DP);
     tc::pack_centres_kernel<<<K, 160, 0, st>>>(K, D, G.DA, centres, w.xinfo, DP, w.mu32);
     KW_CUDA_CHECK(cudaGetLastError());
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel,
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
     static int swap_strides = -1, m_flush = 2;
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
-        swap_strides = (e != nullptr && e[0] == '1') ? 1 : 0;
+        swap_strides = e != nullptr ? atoi(e) : 0;
         const char* f = getenv("KW_TC_MFLUSH");   // tiles accumulated in TMEM between flushes
         if (f != nullptr && atoi(f) > 0) m_flush = atoi(f);
     }
@@ -1386,16 +1425,20 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
         prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
         if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
     }
-    tc::mstats_tc_kernel<<<grid, 640, G.total, st>>>(N, resp_pad(N), w.n_mtiles,
-                                                     w.tiles_per_chunk, w.m_chunks, K, DP, w.xt,
-                                                     resp, w.mu32, w.mpartial, w.npartial, swap_strides,
-                                                     m_flush, prof_on ? prof_dev : nullptr);
+    if (prof_on)
+        tc::mstats_tc_kernel<true><<<grid, 640, G.total, st>>>(
+            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
+            w.mpartial, w.npartial, swap_strides, m_flush, prof_dev);
+    else
+        tc::mstats_tc_kernel<false><<<grid, 640, G.total, st>>>(
+            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
+            w.mpartial, w.npartial, swap_strides, m_flush, nullptr);
     if (prof_on) {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[mstats_tc cta0] mma: total %llu wait_tmem %llu wait_a %llu wait_b %llu "
-                        "issue %llu tiles %llu | gen: total %llu wait_b %llu wait_a %llu work %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11]);
+                        "issue %llu tiles %llu | gen: total %llu wait_b %llu wait_a %llu work %llu publish %llu barrier %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13]);
     }
     KW_CUDA_CHECK(cudaGetLastError());
     tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
