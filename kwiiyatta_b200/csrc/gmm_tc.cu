@@ -183,6 +183,21 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ldmatrix (transposed 8x8 b16 tiles) and the legacy warp-level MMA, for the M-step corner block
+__device__ __forceinline__ void ldsm4_t(uint32_t addr, uint32_t* r) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm2_t(uint32_t addr, uint32_t* r) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, const uint32_t* b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                 "{%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 template <int R> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
 }
@@ -743,8 +758,9 @@ struct MstepGeom {
     int N1, N2;          // accumulator widths of the two MMAs (N2 = 0 when DP <= 128)
     int a_win2;          // first feature group of MMA2's row window
     uint32_t b_stage, a_stage;   // bytes per smem stage (hi + lo)
-    uint32_t off_b, off_a, off_rs, off_mu, off_flags, off_bars, off_tmem, total;
+    uint32_t off_b, off_a, off_rs, off_mu, off_flags, off_bars, off_tmem, off_corner, total;
     int partial_len;     // doubles per work item
+    bool corner;         // DP == 144: the 16 x 17 block outside MMA1 goes to a mma.sync warp
 };
 __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     MstepGeom g;
@@ -766,8 +782,10 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     g.off_flags = o; o += 64;    // rmax[2][2] (float), tile_skip[2], group_empty[2] (int)
     g.off_bars = o; o += 16 * 8;
     g.off_tmem = o; o += 16;
+    g.off_corner = o; o += 2 * 12 * 32 * 4;  // second-level sums of the two corner warps
     g.total = o;
     g.partial_len = 128 * g.N1 + 128 * g.N2;
+    g.corner = (DP == 144);
     return g;
 }
 
@@ -814,9 +832,10 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + MB_B_FULL + i, 1);
-            mbar_init(bars + MB_B_EMPTY + i, 9);    // 8 generator warps + the MMA commit
+            // 8 generator warps + the MMA commit (+ the corner warps)
+            mbar_init(bars + MB_B_EMPTY + i, 9 + (G.corner ? 2 : 0));
             mbar_init(bars + MB_A_FULL + i, 8);
-            mbar_init(bars + MB_A_EMPTY + i, 1);
+            mbar_init(bars + MB_A_EMPTY + i, 1 + (G.corner ? 2 : 0));
             mbar_init(bars + MB_TM_FULL + i, 1);
             mbar_init(bars + MB_TM_EMPTY + i, 8);
         }
@@ -885,7 +904,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 }
             const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
             const uint64_t win_a = (uint64_t)(G.a_win2 * 128) >> 4, win_b = (16 * 128) >> 4;
-            const bool has2 = G.N2 > 0;
+            const bool has2 = G.N2 > 0 && !G.corner;
             (void)swap_strides;
             long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
             const long long p_start = tick<PROF>();
@@ -951,6 +970,110 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 prof[4] = (unsigned long long)p_issue;
                 prof[5] = g;
             }
+        }
+      } else if (G.corner) {
+        // ---------------- corner warps 2, 3: features 128..143 x columns 128..151 -----------
+        // MMA1 covers feature rows 0..127; what is left of the symmetric block is 16 rows x 17
+        // columns, far too small for a tcgen05 instruction (its dispatch alone costs as much
+        // as an N = 160 one).  Two warps (each takes half of a tile's frames) compute it with
+        // m16n8k16 mma.sync straight from the operand tiles the tcgen05 MMAs use: A (MN-major,
+        // hi / lo) and the packed frames B; the 8 x 8 core matrices are ldmatrix.trans tiles
+        // as they lie.
+        const int cw = warp - 2;
+        float* cacc = reinterpret_cast<float*>(smem + G.off_corner) + cw * 12 * 32;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
+        const int kgA = G.DA / 8, kgB = G.DPB / 8;
+        const uint32_t mi = (uint32_t)lane >> 3, rr = (uint32_t)lane & 7u;
+        // per-lane row addresses inside a stage for k-step 0 (frame groups 0, 1)
+        const uint32_t la = (((mi >> 1) * kgA + 16 + (mi & 1u)) * 8 + rr) * 16;
+        const uint32_t lb = (((mi & 1u) * kgB + 16 + (mi >> 1)) * 8 + rr) * 16;
+        const uint32_t lb2 = (((mi & 1u) * kgB + 18) * 8 + rr) * 16;
+        const uint32_t ka = 2u * kgA * 128, kb = 2u * kgB * 128;     // bytes per k-step
+        const uint32_t a_s0 = smem_u32(a_base), b_s0 = smem_u32(b_base);
+        float acc[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+        uint32_t g = 0;
+        long long c_wait = 0, c_work = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int k, t0, t1;
+            item_tiles(item, k, t0, t1);
+            for (int t = t0; t < t1; ++t, ++g) {
+                const uint32_t s = g & 1u, u = g >> 1;
+                const int in_group = (t - t0) % M_FLUSH;
+                const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
+                const long long c0 = tick<PROF>();
+                mbar_wait(bars + MB_A_FULL + s, u & 1u);
+                mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                const long long c1 = tick<PROF>();
+                c_wait += c1 - c0;
+                if (tile_skip[s] == 0 && swap_strides != 1) {
+                    const uint32_t ab = a_s0 + s * G.a_stage + la, bb = b_s0 + s * G.b_stage;
+#pragma unroll
+                    for (int kq = 0; kq < MT / 32; ++kq) {
+                        const int ks = cw * (MT / 32) + kq;
+                        uint32_t ah[4], al[4], bh[6], bl[4];
+                        ldsm4_t(ab + ks * ka, ah);
+                        ldsm4_t(ab + part_a + ks * ka, al);
+                        ldsm4_t(bb + lb + ks * kb, bh);
+                        ldsm2_t(bb + lb2 + ks * kb, bh + 4);
+                        ldsm4_t(bb + part_b + lb + ks * kb, bl);
+#pragma unroll
+                        for (int nb = 0; nb < 3; ++nb) {
+                            mma16816(acc + 4 * nb, al, bh + 2 * nb);
+                            // (the ones column of block 2 has no lo part)
+                            if (nb < 2) mma16816(acc + 4 * nb, ah, bl + 2 * nb);
+                            mma16816(acc + 4 * nb, ah, bh + 2 * nb);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bars + MB_A_EMPTY + s);
+                    mbar_arrive(bars + MB_B_EMPTY + s);
+                }
+                if (last) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        cacc[i * 32 + lane] += acc[i];
+                        acc[i] = 0.f;
+                    }
+                }
+                c_work += tick<PROF>() - c1;
+            }
+            // rows 112..127 of the second accumulator block of this item's partial: warp 2 adds
+            // warp 3's half and writes
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+            if (cw == 1) {
+                asm volatile("bar.sync 3, 64;" ::: "memory");    // warp 2 has read our sums
+#pragma unroll
+                for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
+                continue;
+            }
+            float* out = partial + (size_t)item * G.partial_len + (size_t)128 * G.N1;
+            const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (nb < 3) {
+                        v.x = cacc[(4 * nb + 2 * h) * 32 + lane] +
+                              cacc[(12 + 4 * nb + 2 * h) * 32 + lane];
+                        v.y = cacc[(4 * nb + 2 * h + 1) * 32 + lane] +
+                              cacc[(12 + 4 * nb + 2 * h + 1) * 32 + lane];
+                        cacc[(4 * nb + 2 * h) * 32 + lane] = 0.f;
+                        cacc[(4 * nb + 2 * h + 1) * 32 + lane] = 0.f;
+                    }
+                    *reinterpret_cast<float2*>(out + (size_t)(112 + gq + 8 * h) * G.N2 + nb * 8 +
+                                               2 * tq) = v;
+                }
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+        }
+        if (prof != nullptr && blockIdx.x == 0 && lane == 0 && cw == 0) {
+            prof[6] = (unsigned long long)c_wait;
+            prof[7] = (unsigned long long)c_work;
         }
       }
     } else if (warp < 12) {
@@ -1125,7 +1248,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         }
                     }
                 }
-                if (!empty && c2_begin < c2_end) {
+                if (!empty && c2_begin < c2_end && !G.corner) {
                     uint32_t v[16];
                     tmem_ld16(tbase + (uint32_t)G.N1 + (uint32_t)c2_begin * 16, v);
                     tmem_ld_wait();
@@ -1151,7 +1274,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = acc[c][j];
                 }
             }
-            if (c2_begin < c2_end) {
+            if (c2_begin < c2_end && !(G.corner && row >= 112)) {   // corner rows: the corner warp
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     out[(size_t)128 * G.N1 + (size_t)row * G.N2 + c2_begin * 16 + j] = acc[5][j];
@@ -1437,8 +1560,8 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[mstats_tc cta0] mma: total %llu wait_tmem %llu wait_a %llu wait_b %llu "
-                        "issue %llu tiles %llu | gen: total %llu wait_b %llu wait_a %llu work %llu publish %llu barrier %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13]);
+                        "issue %llu tiles %llu | corner: wait %llu work %llu | gen: total %llu wait_b %llu wait_a %llu work %llu publish %llu barrier %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
     }
     KW_CUDA_CHECK(cudaGetLastError());
     tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
