@@ -392,22 +392,38 @@ __global__ void gmm_reduce_partials_kernel(int K, int D, int chunks,
 }
 
 // ---------------------------------------------------------------------------------------
-// Finalize: one CTA per component.  from_stats = 1: parameters from sufficient statistics;
-// from_stats = 0: only the precision Cholesky of given covariances (weights/means given).
-// Dynamic smem: D * (D + 1) doubles (covariance -> Cholesky factor in the lower triangle,
-// transposed inverse in the strict upper triangle).
+// Finalize: one CTA (512 threads) per component.  from_stats = 1: parameters from sufficient
+// statistics; from_stats = 0: only the precision Cholesky of given covariances (weights/means
+// given).  Everything stays in shared memory: covariance -> Cholesky factor L in the lower
+// triangle -> Z = L^-1 stored transposed in the strict upper triangle (= the precision
+// Cholesky factor sklearn keeps).  Both factorisations are blocked by FIN_NB columns so the
+// bulk of the flops are register-tiled panel products and the number of block-wide barriers
+// is ~2 per column instead of 3 plus a serial triangular sweep.
+// Dynamic smem: D * S doubles (S = D | 1), FIN_NB + 1 doubles per column of scratch, 3 D
+// doubles of diagonals / means.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int FIN_NB = 16;
+constexpr int FIN_THREADS = 512;
+
+static size_t finalize_smem_bytes(int D) {
+    const size_t S = (size_t)D | 1;
+    return sizeof(double) * ((size_t)D * S + (size_t)D * (FIN_NB + 1) + 3 * (size_t)D);
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
 gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_stats,
                     const double* __restrict__ stats, const double* __restrict__ centres,
                     double* __restrict__ weights, double* __restrict__ means,
                     double* __restrict__ covariances, double* __restrict__ prec_chol,
                     double* __restrict__ aux, int32_t* __restrict__ info) {
     extern __shared__ double A[];
-    const int S = D + 1;
-    __shared__ double sh_piv;
+    const int S = D | 1;
+    double* T = A + (size_t)D * S;            // [column][FIN_NB + 1] scratch of the inverse
+    double* dg = T + (size_t)D * (FIN_NB + 1);   // L[j][j]
+    double* zd = dg + D;                      // 1 / L[j][j]
+    double* dm = zd + D;                      // first moments / n_k
     __shared__ int sh_fail;
-    __shared__ double sh_red[256];
+    __shared__ double sh_red[FIN_THREADS / 32];
     const int k = blockIdx.x, tid = threadIdx.x;
     double* cov = covariances + (size_t)k * D * D;
     double* mu = means + (size_t)k * D;
@@ -426,100 +442,198 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
         }
         wk = nk / denom;
         const double* ck = centres + (size_t)k * D;
-        for (int e = tid; e < D * D; e += 256) {
-            const int i = e / D, j = e - i * D;
-            const double di = st[1 + i] / nk, dj = st[1 + j] / nk;
-            double c = st[1 + D + e] / nk - di * dj;
-            if (i == j) c += reg_covar;
-            cov[e] = c;
-            A[i * S + j] = c;
+        for (int dd = tid; dd < D; dd += FIN_THREADS) {
+            const double m = st[1 + dd] / nk;
+            dm[dd] = m;
+            mu[dd] = ck[dd] + m;
         }
-        for (int dd = tid; dd < D; dd += 256) mu[dd] = ck[dd] + st[1 + dd] / nk;
         if (tid == 0) weights[k] = wk;
+        __syncthreads();
+        for (int i = tid >> 5; i < D; i += FIN_THREADS / 32) {
+            const double di = dm[i];
+            for (int j = tid & 31; j < D; j += 32) {
+                double c = st[1 + D + (size_t)i * D + j] / nk - di * dm[j];
+                if (i == j) c += reg_covar;
+                cov[(size_t)i * D + j] = c;
+                A[i * S + j] = c;
+            }
+        }
     } else {
         wk = weights[k];
-        for (int e = tid; e < D * D; e += 256) {
-            const int i = e / D, j = e - i * D;
-            A[i * S + j] = cov[e];
-        }
+        for (int i = tid >> 5; i < D; i += FIN_THREADS / 32)
+            for (int j = tid & 31; j < D; j += 32) A[i * S + j] = cov[(size_t)i * D + j];
     }
     if (tid == 0) sh_fail = 0;
     __syncthreads();
-    // right-looking Cholesky over the lower triangle with all 256 threads (16 x 16 mapping of
-    // the trailing update); per element the products are subtracted in ascending column order,
-    // i.e. the same arithmetic as a left-looking sweep.
-    {
-        const int ty = tid >> 4, tx = tid & 15;
-        for (int j = 0; j < D; ++j) {
-            if (tid == 0) {
-                double s = A[j * S + j];
-                if (!(s > 0.0)) {
-                    if (sh_fail == 0) sh_fail = j + 1;
-                    s = 1.0;
+
+    // ---- Cholesky, left-looking by panels of FIN_NB columns --------------------------------
+    // Per element the products are subtracted in ascending column order (the arithmetic of an
+    // unblocked left-looking sweep).
+    for (int J = 0; J < D; J += FIN_NB) {
+        const int nb = min(FIN_NB, D - J);
+        if (J > 0) {
+            // panel -= L[:, :J] L[J:J+nb, :J]^T; a thread owns 2 rows x 4 columns
+            const int R = D - J, Rh = (R + 1) >> 1;
+            for (int u = tid; u < Rh * 4; u += FIN_THREADS) {
+                const int cg = u / Rh, ip = u - cg * Rh;
+                const int c0 = 4 * cg;
+                if (c0 >= nb) continue;
+                const int i0 = J + ip, i1 = i0 + Rh;
+                const bool two = i1 < D;
+                const double* r0 = A + i0 * S;
+                const double* r1 = A + (two ? i1 : i0) * S;
+                const double* q0 = A + (J + c0) * S;
+                const double* q1 = A + (J + min(c0 + 1, nb - 1)) * S;
+                const double* q2 = A + (J + min(c0 + 2, nb - 1)) * S;
+                const double* q3 = A + (J + min(c0 + 3, nb - 1)) * S;
+                double a00 = r0[J + c0], a01 = r0[J + min(c0 + 1, nb - 1)],
+                       a02 = r0[J + min(c0 + 2, nb - 1)], a03 = r0[J + min(c0 + 3, nb - 1)];
+                double a10 = r1[J + c0], a11 = r1[J + min(c0 + 1, nb - 1)],
+                       a12 = r1[J + min(c0 + 2, nb - 1)], a13 = r1[J + min(c0 + 3, nb - 1)];
+                for (int p = 0; p < J; ++p) {
+                    const double l0 = -r0[p], l1 = -r1[p];
+                    const double b0 = q0[p], b1 = q1[p], b2 = q2[p], b3 = q3[p];
+                    a00 = fma(l0, b0, a00); a01 = fma(l0, b1, a01);
+                    a02 = fma(l0, b2, a02); a03 = fma(l0, b3, a03);
+                    a10 = fma(l1, b0, a10); a11 = fma(l1, b1, a11);
+                    a12 = fma(l1, b2, a12); a13 = fma(l1, b3, a13);
                 }
-                sh_piv = sqrt(s);
-                A[j * S + j] = sh_piv;
+                double* w0 = A + i0 * S + J + c0;
+                double* w1 = A + i1 * S + J + c0;
+                w0[0] = a00;
+                if (c0 + 1 < nb) w0[1] = a01;
+                if (c0 + 2 < nb) w0[2] = a02;
+                if (c0 + 3 < nb) w0[3] = a03;
+                if (two) {
+                    w1[0] = a10;
+                    if (c0 + 1 < nb) w1[1] = a11;
+                    if (c0 + 2 < nb) w1[2] = a12;
+                    if (c0 + 3 < nb) w1[3] = a13;
+                }
             }
             __syncthreads();
-            const double piv = sh_piv;
-            for (int i = j + 1 + tid; i < D; i += 256) A[i * S + j] = A[i * S + j] / piv;
+        }
+        // right-looking inside the panel; every thread derives the pivot itself
+        for (int c = 0; c < nb; ++c) {
+            const int j = J + c;
+            double s = A[j * S + j];
+            if (!(s > 0.0)) {
+                if (tid == 0 && sh_fail == 0) sh_fail = j + 1;
+                s = 1.0;
+            }
+            const double piv = sqrt(s);
+            if (tid == 0) dg[j] = piv;
+            for (int i = j + 1 + tid; i < D; i += FIN_THREADS) A[i * S + j] = A[i * S + j] / piv;
             __syncthreads();
-            for (int l = j + 1 + ty; l < D; l += 16) {
-                const double clj = A[l * S + j];
-                for (int i = l + tx; i < D; i += 16)
-                    A[i * S + l] = fma(-A[i * S + j], clj, A[i * S + l]);
+            const int ncol = nb - 1 - c;          // remaining panel columns
+            if (ncol > 0) {
+                const int rows = D - (j + 1);
+                for (int u = tid; u < rows * ncol; u += FIN_THREADS) {
+                    const int lc = u / rows, i = j + 1 + (u - lc * rows);
+                    const int l = j + 1 + lc;
+                    if (i >= l) A[i * S + l] = fma(-A[i * S + j], A[l * S + j], A[i * S + l]);
+                }
             }
             __syncthreads();
         }
     }
-    // Z = C^-1 (lower); store Z^T in the strict upper triangle: A[c][r] = Z[r][c], r > c.
-    // Columns 0..111 (the long ones) are shared by two adjacent lanes that split the dot product
-    // by parity of p; columns 112.. get one thread each.
+    // (A[j][j] still holds the pre-pivot value; the diagonal of L lives in dg)
+    for (int j = tid; j < D; j += FIN_THREADS) zd[j] = 1.0 / dg[j];
+    __syncthreads();
+
+    // ---- Z = L^-1 by block rows; Z^T goes to the strict upper triangle: A[c][r] = Z[r][c] ----
+    // diagonal blocks: one thread per column, forward substitution in registers
     {
-        int c, h, nth;
-        if (tid < 224) { c = tid >> 1; h = tid & 1; nth = 2; }
-        else { c = 112 + (tid - 224); h = 0; nth = 1; }
-        const bool active = c < D;
-        const double zcc = active ? 1.0 / A[c * S + c] : 0.0;
-        for (int r = 1; r < D; ++r) {
-            double s = 0.0;
-            if (active && r > c) {
-                if (h == 0) s = A[r * S + c] * zcc;                       // p = c
-                for (int p = c + 1 + h; p < r; p += nth) s = fma(A[r * S + p], A[c * S + p], s);
+        const int nblk = (D + FIN_NB - 1) / FIN_NB;
+        if (tid < nblk * FIN_NB) {
+            const int I = tid / FIN_NB, c = tid - I * FIN_NB, base = I * FIN_NB;
+            const int nb = min(FIN_NB, D - base);
+            if (c < nb) {
+                double z[FIN_NB];
+#pragma unroll
+                for (int r = 0; r < FIN_NB; ++r) z[r] = 0.0;
+#pragma unroll
+                for (int r = 0; r < FIN_NB; ++r) {
+                    if (r == c) z[r] = zd[base + r];
+                    if (r > c && r < nb) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < FIN_NB; ++q)
+                            if (q < r) acc = fma(A[(base + r) * S + base + q], z[q], acc);
+                        z[r] = -acc * zd[base + r];
+                        A[(base + c) * S + base + r] = z[r];
+                    }
+                }
             }
-            if (tid < 224) s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (active && r > c && h == 0) A[c * S + r] = -s / A[r * S + r];
-            __syncwarp();
         }
     }
     __syncthreads();
-    // prec_chol (upper) = Z^T; diagonal 1 / C[j][j]
-    double* pc = prec_chol + (size_t)k * D * D;
-    for (int e = tid; e < D * D; e += 256) {
-        const int r = e / D, c = e - r * D;
-        double v = 0.0;
-        if (c > r) v = A[r * S + c];
-        else if (c == r) v = 1.0 / A[r * S + r];
-        pc[e] = v;
-    }
-    double ld = 0.0;
-    for (int j = tid; j < D; j += 256) ld += log(1.0 / A[j * S + j]);
-    sh_red[tid] = ld;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) sh_red[tid] += sh_red[tid + o];
+    for (int I0 = FIN_NB; I0 < D; I0 += FIN_NB) {
+        const int nb = min(FIN_NB, D - I0);
+        // T[r][c] = sum_{p = c}^{I0 - 1} L[I0 + r][p] Z[p][c];  thread: rows (rp, rp + 8),
+        // columns (c, c + 1)
+        for (int u = tid; u < 8 * (I0 / 2); u += FIN_THREADS) {
+            const int rp = u & 7, c = (u >> 3) * 2;
+            const int ra = min(rp, nb - 1), rb = min(rp + 8, nb - 1);
+            const double* la = A + (I0 + ra) * S;
+            const double* lb = A + (I0 + rb) * S;
+            const double* z0 = A + c * S;
+            const double* z1 = A + (c + 1) * S;
+            // p = c and p = c + 1 by hand (diagonal terms of Z)
+            double t00 = la[c] * zd[c], t10 = lb[c] * zd[c];
+            t00 = fma(la[c + 1], z0[c + 1], t00);
+            t10 = fma(lb[c + 1], z0[c + 1], t10);
+            double t01 = la[c + 1] * zd[c + 1], t11 = lb[c + 1] * zd[c + 1];
+            for (int p = c + 2; p < I0; ++p) {
+                const double xa = la[p], xb = lb[p], y0 = z0[p], y1 = z1[p];
+                t00 = fma(xa, y0, t00); t01 = fma(xa, y1, t01);
+                t10 = fma(xb, y0, t10); t11 = fma(xb, y1, t11);
+            }
+            T[c * (FIN_NB + 1) + rp] = t00;
+            T[(c + 1) * (FIN_NB + 1) + rp] = t01;
+            T[c * (FIN_NB + 1) + rp + 8] = t10;
+            T[(c + 1) * (FIN_NB + 1) + rp + 8] = t11;
+        }
+        __syncthreads();
+        // Z[I0 + r][c] = - sum_{q <= r} Zdiag[r][q] T[q][c]
+        for (int u = tid; u < FIN_NB * I0; u += FIN_THREADS) {
+            const int r = u & (FIN_NB - 1), c = u >> 4;
+            if (r < nb) {
+                const double* tc = T + c * (FIN_NB + 1);
+                double acc = zd[I0 + r] * tc[r];
+                for (int q = 0; q < r; ++q) acc = fma(A[(I0 + q) * S + I0 + r], tc[q], acc);
+                A[c * S + I0 + r] = -acc;
+            }
+        }
         __syncthreads();
     }
+    // prec_chol (upper) = Z^T; diagonal 1 / L[j][j]
+    double* pc = prec_chol + (size_t)k * D * D;
+    for (int r = tid >> 5; r < D; r += FIN_THREADS / 32)
+        for (int c = tid & 31; c < D; c += 32) {
+            double v = 0.0;
+            if (c > r) v = A[r * S + c];
+            else if (c == r) v = zd[r];
+            pc[(size_t)r * D + c] = v;
+        }
+    double ld = 0.0;
+    for (int j = tid; j < D; j += FIN_THREADS) ld += log(zd[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    if ((tid & 31) == 0) sh_red[tid >> 5] = ld;
+    __syncthreads();
     double* ak = aux + (size_t)k * (D + 2);
     if (tid < D) {
         const int j = tid;
         double b = 0.0;
         for (int dd = 0; dd < j; ++dd) b = fma(mu[dd], A[dd * S + j], b);
-        b = fma(mu[j], 1.0 / A[j * S + j], b);
+        b = fma(mu[j], zd[j], b);
         ak[j] = b;
     }
     if (tid == 0) {
-        ak[D] = sh_red[0];
+        double t = 0.0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) t += sh_red[w];
+        ak[D] = t;
         ak[D + 1] = log(wk);
         info[k] = sh_fail;
     }
@@ -614,10 +728,10 @@ int finalize_launch(int K, int D, double reg_covar, int weight_norm, int from_st
         set_error("dim %d > 160 is not supported by the finalize kernel", D);
         return KW_ERR_UNSUPPORTED;
     }
-    const size_t smem = sizeof(double) * (size_t)D * (D + 1);
+    const size_t smem = finalize_smem_bytes(D);
     KW_CUDA_CHECK(cudaFuncSetAttribute(gmm_finalize_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_finalize_kernel<<<K, 256, smem, st>>>(K, D, reg_covar, weight_norm, from_stats, stats,
+    gmm_finalize_kernel<<<K, FIN_THREADS, smem, st>>>(K, D, reg_covar, weight_norm, from_stats, stats,
                                               centres, weights, means, cov, pc, aux, info);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
