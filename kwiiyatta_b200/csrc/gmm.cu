@@ -513,7 +513,10 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
             }
             __syncthreads();
         }
-        // right-looking inside the panel; every thread derives the pivot itself
+        // right-looking inside the panel, one barrier per column: every thread derives the
+        // pivot itself, warp w updates panel column j + 1 + w with the column-j values scaled on
+        // the fly, and the scaled column itself goes to the scratch T (nothing reads column j of
+        // A again inside the panel), copied back once the panel is done.
         for (int c = 0; c < nb; ++c) {
             const int j = J + c;
             double s = A[j * S + j];
@@ -521,21 +524,37 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
                 if (tid == 0 && sh_fail == 0) sh_fail = j + 1;
                 s = 1.0;
             }
-            const double piv = sqrt(s);
-            if (tid == 0) dg[j] = piv;
-            for (int i = j + 1 + tid; i < D; i += FIN_THREADS) A[i * S + j] = A[i * S + j] / piv;
-            __syncthreads();
-            const int ncol = nb - 1 - c;          // remaining panel columns
-            if (ncol > 0) {
-                const int rows = D - (j + 1);
-                for (int u = tid; u < rows * ncol; u += FIN_THREADS) {
-                    const int lc = u / rows, i = j + 1 + (u - lc * rows);
-                    const int l = j + 1 + lc;
-                    if (i >= l) A[i * S + l] = fma(-A[i * S + j], A[l * S + j], A[i * S + l]);
+            const double rinv = rsqrt(s);
+            if (tid == 0) dg[j] = s * rinv;
+            const int w = tid >> 5, l = j + 1 + w;
+            if (l < J + nb) {
+                const double mlj = -(A[l * S + j] * rinv);
+                // loads first, stores last (D <= 160: at most 5 rows per lane)
+                double va[5], vb[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int i = l + (tid & 31) + 32 * q;
+                    if (i < D) {
+                        va[q] = A[i * S + j];
+                        vb[q] = A[i * S + l];
+                    }
                 }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int i = l + (tid & 31) + 32 * q;
+                    if (i < D) A[i * S + l] = fma(va[q] * rinv, mlj, vb[q]);
+                }
+            } else {
+                // idle warps of this step store the finished column
+                const int nidle = FIN_THREADS / 32 - (nb - 1 - c);
+                const int q = (w - (nb - 1 - c)) * 32 + (tid & 31);
+                for (int i = j + 1 + q; i < D; i += nidle * 32) T[c * D + i] = A[i * S + j] * rinv;
             }
             __syncthreads();
         }
+        for (int c = tid >> 5; c < nb; c += FIN_THREADS / 32)
+            for (int i = J + c + 1 + (tid & 31); i < D; i += 32) A[i * S + J + c] = T[c * D + i];
+        __syncthreads();
     }
     // (A[j][j] still holds the pre-pivot value; the diagonal of L lives in dg)
     for (int j = tid; j < D; j += FIN_THREADS) zd[j] = 1.0 / dg[j];
