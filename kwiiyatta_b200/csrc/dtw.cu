@@ -20,7 +20,17 @@
 //   2*NT columns, refilled NT columns at a time with coalesced loads.  The D values of a
 //   strip's last row go through a small global ping-pong buffer to the next strip.
 //   Back-pointers are 2 bits per cell, packed 16 per word by the owning thread.
-//   The distance matrix never exists in memory.
+//
+// Two variants of the sweep:
+//   * exhaustive levels (the coarsest level of a pair, or radius < 0): dtw_dp_kernel computes the
+//     local distances inside the sweep; the distance matrix never exists in memory;
+//   * banded levels: the sweep of a narrow band is latency-bound (one barrier per anti-diagonal
+//     step, few cells in flight), and with ~72 FP64 instructions per cell inside that chain the
+//     FP64 pipe idles most of the time.  dtw_dist_kernel therefore computes the band's local
+//     distances first, dependency-free at FP64 issue rate, into a per-row-pair buffer of
+//     DIST_WCAP columns, and dtw_dpb_kernel sweeps over them (3 additions and 2 integer
+//     comparisons per cell).  Columns of a window beyond the buffer capacity are computed
+//     inside the sweep, so the capacity only affects speed.
 #include <algorithm>
 #include <vector>
 
@@ -45,19 +55,36 @@ struct PairDesc {
     long long bp_off;          // uint32 words, tx0 * ceil(ty0/16)
     long long brow_off;        // doubles, 2 * ty0
     long long path_off;        // points, capacity tx0 + ty0
+    long long dist_off;        // double2 (rows 2q, 2q+1), ceil(tx0/2) * wcap when nlev > 1
 };
 
 struct DtwPlan {
     std::vector<PairDesc> descs;
     std::vector<int> order;
     int maxlev = 0;
-    size_t n_pyr_x = 0, n_pyr_y = 0, n_rowj = 0, n_bp = 0, n_brow = 0;
+    size_t n_pyr_x = 0, n_pyr_y = 0, n_rowj = 0, n_bp = 0, n_brow = 0, n_dist = 0;
     std::vector<int> level_max_tx;
+    std::vector<char> level_has_full, level_has_band;
+    int wcap = 0;
 };
+
+// Columns of local distances kept per row pair of a banded level.  A window is
+// 2 * (span of the coarser path over 2 radius + 1 rows) + 4 radius + 2 columns wide: 8 radius + 2
+// for a diagonal path; wider ones spill into the sweep's inline path.
+static int dist_wcap(int radius) { return radius < 0 ? 0 : std::max(64, 12 * radius + 16); }
+static bool split_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KW_DTW_SPLIT");
+        v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
 
 static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radius, int F,
                      DtwPlan& plan) {
     plan.descs.resize(n_pairs);
+    plan.wcap = split_enabled() ? dist_wcap(radius) : 0;
     long long xrow = 0, yrow = 0, path = 0;
     for (int p = 0; p < n_pairs; ++p) {
         PairDesc& d = plan.descs[p];
@@ -93,6 +120,14 @@ static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radi
         d.nlev = l;
         d.pad_ = 0;
         plan.maxlev = std::max(plan.maxlev, l);
+        if ((int)plan.level_has_full.size() < l) {
+            plan.level_has_full.resize(l, 0);
+            plan.level_has_band.resize(l, 0);
+        }
+        plan.level_has_full[l - 1] = 1;
+        for (int q = 0; q + 1 < l; ++q) plan.level_has_band[q] = 1;
+        d.dist_off = (long long)plan.n_dist;
+        if (l > 1) plan.n_dist += (size_t)((tx[p] + 1) / 2) * (size_t)plan.wcap;
         d.xrow0 = xrow;
         d.yrow0 = yrow;
         xrow += tx[p];
@@ -120,6 +155,7 @@ struct DtwWorkspace {
     int* rowj;
     uint32_t* bp;
     double* brow;
+    double2* dist;
     size_t bytes;
 };
 
@@ -133,6 +169,7 @@ static DtwWorkspace carve(const DtwPlan& plan, void* base) {
     w.rowj = c.take<int>(plan.n_rowj + 1);
     w.bp = c.take<uint32_t>(plan.n_bp);
     w.brow = c.take<double>(plan.n_brow);
+    w.dist = c.take<double2>(plan.n_dist);
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -211,7 +248,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
               int radius, int F, const double* __restrict__ xpyr,
               const double* __restrict__ ypyr, const int* __restrict__ rowj,
               uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost,
-              unsigned long long* __restrict__ cells) {
+              unsigned long long* __restrict__ cells, int only_full) {
     constexpr int CH = NT;
     constexpr int RING = 2 * NT;
     constexpr int RS = RING + 1;
@@ -229,6 +266,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
     const double* __restrict__ xT = xpyr + d.xoff[level];
     const double* __restrict__ yT = ypyr + d.yoff[level];
     const bool full = (level == d.nlev - 1);
+    if (only_full && !full) return;      // banded levels go through dtw_dist / dtw_dpb
     const int ctx = full ? 0 : d.tx[level + 1];
     const int* __restrict__ cfirst = full ? nullptr : rowj + d.rj_off[level + 1];
     const int* __restrict__ clast = full ? nullptr : cfirst + ctx;
@@ -368,6 +406,239 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
 }
 
 // ---------------------------------------------------------------------------------------
+// Banded levels, part 1: local distances of every window cell.  One warp per row pair
+// (rows 2q and 2q+1 share their window), lanes over the window's columns, two columns per lane
+// in flight.  grid (n_pairs, ceil(row pairs / 8)), 256 threads.
+// ---------------------------------------------------------------------------------------
+template <int FP, int P, typename T>
+__global__ void __launch_bounds__(256)
+dtw_dist_kernel(const PairDesc* __restrict__ descs, int level, int radius, int F, int wcap,
+                const double* __restrict__ xpyr, const double* __restrict__ ypyr,
+                const int* __restrict__ rowj, double2* __restrict__ dist) {
+    __shared__ T xs[8][FP][2];
+    const PairDesc& d = descs[blockIdx.x];
+    if (level >= d.nlev - 1) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = d.tx[level], ty = d.ty[level];
+    const int rp = blockIdx.y * 8 + warp;
+    const int ia = 2 * rp, ib = ia + 1;
+    if (ia >= tx) return;                 // (no block-wide barrier below)
+    const double* __restrict__ xT = xpyr + d.xoff[level];
+    const double* __restrict__ yT = ypyr + d.yoff[level];
+    const int ctx = d.tx[level + 1];
+    const int* __restrict__ cfirst = rowj + d.rj_off[level + 1];
+    const int* __restrict__ clast = cfirst + ctx;
+    int lo, hi;
+    {
+        const int ca = ia >> 1;
+        int r0 = max(0, ca - radius);
+        const int r1 = min(ctx - 1, ca + radius);
+        r0 = min(r0, r1);
+        lo = max(0, 2 * (cfirst[r0] - radius));
+        hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
+    }
+    for (int k = lane; k < FP; k += 32) {
+        xs[warp][k][0] = (T)((k < F) ? xT[(size_t)k * tx + ia] : 0.0);
+        xs[warp][k][1] = (T)((k < F && ib < tx) ? xT[(size_t)k * tx + ib] : 0.0);
+    }
+    __syncwarp();
+    const int cap = min(hi - lo + 1, wcap);
+    double2* out = dist + d.dist_off + (size_t)rp * wcap;
+    for (int c0 = 0; c0 < cap; c0 += 64) {
+        const int c1 = c0 + lane, c2 = c1 + 32;
+        const bool v1 = c1 < cap, v2 = c2 < cap;
+        const double* y1 = yT + lo + (v1 ? c1 : 0);
+        const double* y2 = yT + lo + (v2 ? c2 : 0);
+        T s1a = (T)0, s1b = (T)0, s2a = (T)0, s2b = (T)0;
+#pragma unroll
+        for (int k = 0; k < FP; ++k) {
+            if (k < F) {
+                const T xa = xs[warp][k][0], xb = xs[warp][k][1];
+                const T ya = (T)__ldg(y1 + (size_t)k * ty), yb = (T)__ldg(y2 + (size_t)k * ty);
+                s1a = dist_acc<P>(s1a, sub_rn(xa, ya));
+                s1b = dist_acc<P>(s1b, sub_rn(xb, ya));
+                s2a = dist_acc<P>(s2a, sub_rn(xa, yb));
+                s2b = dist_acc<P>(s2b, sub_rn(xb, yb));
+            }
+        }
+        if (v1) out[c1] = make_double2(dist_fin<P>(s1a), dist_fin<P>(s1b));
+        if (v2) out[c2] = make_double2(dist_fin<P>(s2a), dist_fin<P>(s2b));
+    }
+}
+
+// D values are sums of non-negative terms (or +inf): their IEEE bit patterns order like the
+// values, so the "strictly less" of the cell rule runs on the integer pipe.
+__device__ __forceinline__ bool lt_nonneg(double a, double b) {
+    return __double_as_longlong(a) < __double_as_longlong(b);
+}
+
+// ---------------------------------------------------------------------------------------
+// Banded levels, part 2: the sweep over precomputed local distances.  Same strip-mined
+// systolic wavefront as dtw_dp_kernel (thread t owns rows i0+2t, i0+2t+1 and lags t columns);
+// the two distances of a step come from the row pair's slice, fetched four steps ahead.
+// ---------------------------------------------------------------------------------------
+template <int NT, int P, typename T>
+__global__ void __launch_bounds__(NT)
+dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
+               int radius, int F, int wcap, const double* __restrict__ xpyr,
+               const double* __restrict__ ypyr, const int* __restrict__ rowj,
+               const double2* __restrict__ dist, uint32_t* __restrict__ bp,
+               double* __restrict__ brow, double* __restrict__ cost,
+               unsigned long long* __restrict__ cells) {
+    constexpr int CH = NT;
+    constexpr int RING = 2 * NT;
+    constexpr int PD = 4;                 // prefetch distance (steps)
+    __shared__ double xch[2 * NT];
+    __shared__ double brs[RING];
+    __shared__ unsigned long long cell_count;
+
+    const int pair = order[blockIdx.x];
+    const PairDesc& d = descs[pair];
+    if (level >= d.nlev - 1) return;
+    const int t = threadIdx.x;
+    const int tx = d.tx[level], ty = d.ty[level];
+    const double* __restrict__ xT = xpyr + d.xoff[level];
+    const double* __restrict__ yT = ypyr + d.yoff[level];
+    const int ctx = d.tx[level + 1];
+    const int* __restrict__ cfirst = rowj + d.rj_off[level + 1];
+    const int* __restrict__ clast = cfirst + ctx;
+    const int tiles_x = (ty + 15) >> 4;
+    uint32_t* bp_pair = bp + d.bp_off;
+    double* brow_pair = brow + d.brow_off;
+    const double2* dist_pair = dist + d.dist_off;
+    const double INF = CUDART_INF;
+
+    auto window = [&](int a, int& lo, int& hi) {
+        const int ca = a >> 1;
+        int r0 = max(0, ca - radius);
+        const int r1 = min(ctx - 1, ca + radius);
+        r0 = min(r0, r1);
+        lo = max(0, 2 * (cfirst[r0] - radius));
+        hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
+    };
+    // local distance computed in place (columns beyond the buffer capacity)
+    auto inline_dist = [&](int i, int j) -> double {
+        T sacc = (T)0;
+        for (int k = 0; k < F; ++k)
+            sacc = dist_acc<P>(sacc, sub_rn((T)xT[(size_t)k * tx + i], (T)yT[(size_t)k * ty + j]));
+        return dist_fin<P>(sacc);
+    };
+
+    if (t == 0) cell_count = 0ull;
+    unsigned int my_cells = 0;
+    int strip = 0;
+    for (int i0 = 0; i0 < tx; i0 += 2 * NT, ++strip) {
+        const int ia = i0 + 2 * t, ib = ia + 1;
+        const bool has_b = ib < tx;
+        int lo = INT_MAX, hi = INT_MIN;
+        if (ia < tx) window(ia, lo, hi);
+        const double2* drow = dist_pair + (size_t)(ia >> 1) * wcap;
+        int jstart, dummy;
+        window(i0, jstart, dummy);
+        const int il = min(tx, i0 + 2 * NT) - 1;
+        int hil;
+        window(il, dummy, hil);
+        const int n_steps = hil - jstart + ((il - i0) >> 1) + 1;
+        int plo = INT_MAX, phi = INT_MIN;
+        if (i0 > 0) window(i0 - 1, plo, phi);
+        const double* brow_in = brow_pair + ((strip & 1) ? 0 : ty);
+        double* brow_out = brow_pair + ((strip & 1) ? ty : 0);
+        const bool writes_boundary = (t == NT - 1) && (i0 + 2 * NT < tx);
+
+        auto fetch = [&](int j) -> double2 {
+            return (j >= lo && j <= hi && j - lo < wcap) ? drow[j - lo] : make_double2(0.0, 0.0);
+        };
+
+        double va_prev = INF, vb_prev = INF, diag_in = INF;
+        if (t == 0) {
+            const int jm = jstart - 1;
+            if (i0 == 0)
+                diag_in = (jm == -1) ? 0.0 : INF;  // virtual origin D[0][0] = 0
+            else
+                diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
+        }
+        xch[NT + t] = INF;  // parity 1 is read at step 0
+        uint32_t wa = 0u, wb = 0u;
+        double2 cq[PD], nq[PD];
+#pragma unroll
+        for (int q = 0; q < PD; ++q) cq[q] = fetch(jstart + q - t);
+        __syncthreads();
+
+        for (int s0 = 0; s0 < n_steps; s0 += PD) {
+            if ((s0 % CH) == 0) {
+                const int j = jstart + s0 + t;
+                brs[j & (RING - 1)] = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < PD; ++q) nq[q] = fetch(jstart + s0 + PD + q - t);
+#pragma unroll
+            for (int q = 0; q < PD; ++q) {
+                const int s = s0 + q;
+                if (s < n_steps) {          // uniform across the CTA
+                    const int j = jstart + s - t;
+                    const double up_in =
+                        (t == 0) ? brs[j & (RING - 1)] : xch[((s + 1) & 1) * NT + t - 1];
+                    double va = INF, vb = INF;
+                    if (j >= lo && j <= hi) {
+                        double dta = cq[q].x, dtb = cq[q].y;
+                        if (j - lo >= wcap) {
+                            dta = inline_dist(ia, j);
+                            dtb = has_b ? inline_dist(ib, j) : 0.0;
+                        }
+                        {
+                            double best = __dadd_rn(up_in, dta);
+                            uint32_t code = 0u;
+                            double c = __dadd_rn(va_prev, dta);
+                            if (lt_nonneg(c, best)) { best = c; code = 1u; }
+                            c = __dadd_rn(diag_in, dta);
+                            if (lt_nonneg(c, best)) { best = c; code = 2u; }
+                            va = best;
+                            wa |= code << (2 * (j & 15));
+                            if ((j & 15) == 15 || j == hi) {
+                                bp_pair[bp_word(ia, j, tiles_x)] = wa;
+                                wa = 0u;
+                            }
+                            if (ia == tx - 1 && j == ty - 1) cost[pair] = va;
+                            ++my_cells;
+                        }
+                        if (has_b) {
+                            double best = __dadd_rn(va, dtb);
+                            uint32_t code = 0u;
+                            double c = __dadd_rn(vb_prev, dtb);
+                            if (lt_nonneg(c, best)) { best = c; code = 1u; }
+                            c = __dadd_rn(va_prev, dtb);
+                            if (lt_nonneg(c, best)) { best = c; code = 2u; }
+                            vb = best;
+                            wb |= code << (2 * (j & 15));
+                            if ((j & 15) == 15 || j == hi) {
+                                bp_pair[bp_word(ib, j, tiles_x)] = wb;
+                                wb = 0u;
+                            }
+                            if (ib == tx - 1 && j == ty - 1) cost[pair] = vb;
+                            if (writes_boundary) __stcg(brow_out + j, vb);
+                            ++my_cells;
+                        }
+                    }
+                    xch[(s & 1) * NT + t] = vb;
+                    va_prev = va;
+                    vb_prev = vb;
+                    diag_in = up_in;
+                    __syncthreads();
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PD; ++q) cq[q] = nq[q];
+        }
+    }
+    if (cells != nullptr) {
+        atomicAdd(&cell_count, (unsigned long long)my_cells);
+        __syncthreads();
+        if (t == 0) atomicAdd(cells + pair, cell_count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Backtrace: one warp per pair walks the 2-bit codes from (tx-1, ty-1) to the origin.  The warp
 // keeps a 2 x 2 window of back-pointer sectors (16 rows x 32 columns, one word per lane) in
 // registers and looks codes up with shuffles; global memory is touched once per window, not
@@ -438,33 +709,71 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
 
 template <int FP, int NT, int P, typename T>
 static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
-                     double* cost, unsigned long long* cells, cudaStream_t st) {
+                     double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
     constexpr int RS = 2 * NT + 1;
     const size_t smem = sizeof(double) * (2 * NT + 2 * NT) + sizeof(T) * (size_t)FP * RS;
     auto kern = dtw_dp_kernel<FP, NT, P, T>;
     KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     kern<<<n_pairs, NT, smem, st>>>(w.descs, w.order, level, radius, F, w.xpyr, w.ypyr, w.rowj,
-                                    w.bp, w.brow, cost, cells);
+                                    w.bp, w.brow, cost, cells, only_full);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
 
 template <int FP, int P, typename T>
 static int launch_dp_nt(int nt, int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
-                        double* cost, unsigned long long* cells, cudaStream_t st) {
-    if (nt == 32) return launch_dp<FP, 32, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
-    if (nt == 64) return launch_dp<FP, 64, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
-    return launch_dp<FP, 128, P, T>(n_pairs, w, level, radius, F, cost, cells, st);
+                        double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
+    if (nt == 32)
+        return launch_dp<FP, 32, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
+    if (nt == 64)
+        return launch_dp<FP, 64, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
+    return launch_dp<FP, 128, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
 }
 
 template <int P, typename T>
 static int launch_dp_fp(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
-                        double* cost, unsigned long long* cells, cudaStream_t st) {
-    if (F <= 8) return launch_dp_nt<8, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    if (F <= 16) return launch_dp_nt<16, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    if (F <= 26) return launch_dp_nt<26, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
-    return launch_dp_nt<32, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, st);
+                        double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
+    if (F <= 8)
+        return launch_dp_nt<8, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+    if (F <= 16)
+        return launch_dp_nt<16, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+    if (F <= 26)
+        return launch_dp_nt<26, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+    return launch_dp_nt<32, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+}
+
+// Banded level: local distances, then the sweep over them.
+template <int FP, int P, typename T>
+static int launch_dist(int n_pairs, const DtwWorkspace& w, int level, int radius, int F, int wcap,
+                       int max_tx, cudaStream_t st) {
+    const int rp_blocks = ((max_tx + 1) / 2 + 7) / 8;
+    dtw_dist_kernel<FP, P, T><<<dim3(n_pairs, rp_blocks), 256, 0, st>>>(
+        w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.dist);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+template <int P, typename T>
+static int launch_banded(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
+                         int wcap, int max_tx, double* cost, unsigned long long* cells,
+                         cudaStream_t st) {
+    int rc;
+    if (F <= 8) rc = launch_dist<8, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
+    else if (F <= 16) rc = launch_dist<16, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
+    else if (F <= 26) rc = launch_dist<26, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
+    else rc = launch_dist<32, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
+    if (rc != KW_OK) return rc;
+    if (nt == 32)
+        dtw_dpb_kernel<32, P, T><<<n_pairs, 32, 0, st>>>(w.descs, w.order, level, radius, F, wcap,
+                                                         w.xpyr, w.ypyr, w.rowj, w.dist, w.bp,
+                                                         w.brow, cost, cells);
+    else
+        dtw_dpb_kernel<64, P, T><<<n_pairs, 64, 0, st>>>(w.descs, w.order, level, radius, F, wcap,
+                                                         w.xpyr, w.ypyr, w.rowj, w.dist, w.bp,
+                                                         w.brow, cost, cells);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
 }
 
 }  // namespace kw
@@ -525,16 +834,43 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
         int nt = (mtx <= 64) ? 32 : ((mtx <= 128 || radius >= 0) ? 64 : 128);
         if (nt_env == 32 || nt_env == 64 || nt_env == 128) nt = std::min(nt, nt_env);
         unsigned long long* cells = reinterpret_cast<unsigned long long*>(cells_dev);
-        if (precision == 0) {
-            if (p_norm == 2)
-                rc = launch_dp_fp<2, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
-            else
-                rc = launch_dp_fp<1, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
-        } else {
-            if (p_norm == 2)
-                rc = launch_dp_fp<2, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
-            else
-                rc = launch_dp_fp<1, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev, cells, st);
+        const bool split = plan.wcap > 0;
+        if (split && plan.level_has_band[l]) {
+            const int ntb = std::min(nt, 64);
+            if (precision == 0) {
+                if (p_norm == 2)
+                    rc = launch_banded<2, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
+                                                  mtx, cost_dev, cells, st);
+                else
+                    rc = launch_banded<1, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
+                                                  mtx, cost_dev, cells, st);
+            } else {
+                if (p_norm == 2)
+                    rc = launch_banded<2, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
+                                                 mtx, cost_dev, cells, st);
+                else
+                    rc = launch_banded<1, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
+                                                 mtx, cost_dev, cells, st);
+            }
+            if (rc != KW_OK) return rc;
+        }
+        if (!split || plan.level_has_full[l]) {
+            const int only_full = split ? 1 : 0;
+            if (precision == 0) {
+                if (p_norm == 2)
+                    rc = launch_dp_fp<2, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
+                                                 cells, only_full, st);
+                else
+                    rc = launch_dp_fp<1, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
+                                                 cells, only_full, st);
+            } else {
+                if (p_norm == 2)
+                    rc = launch_dp_fp<2, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
+                                                cells, only_full, st);
+                else
+                    rc = launch_dp_fp<1, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
+                                                cells, only_full, st);
+            }
         }
         if (rc != KW_OK) return rc;
         dtw_backtrace_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(
