@@ -28,10 +28,11 @@
 //     step, few cells in flight), and with ~72 FP64 instructions per cell inside that chain the
 //     FP64 pipe idles most of the time.  dtw_dist_kernel therefore computes the band's local
 //     distances first, dependency-free at FP64 issue rate, into a per-row-pair buffer of
-//     DIST_WCAP columns, and dtw_dpb_kernel sweeps over them (3 additions and 2 integer
-//     comparisons per cell).  Columns of a window beyond the buffer capacity are computed
+//     DIST_WCAP columns, and dtw_dpw_kernel sweeps over them, one warp per pair (3 additions and
+//     2 integer comparisons per cell).  Columns of a window beyond the buffer capacity are computed
 //     inside the sweep, so the capacity only affects speed.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include <climits>
@@ -56,14 +57,15 @@ struct PairDesc {
     long long brow_off;        // doubles, 2 * ty0
     long long path_off;        // points, capacity tx0 + ty0
     long long dist_off;        // double2 (rows 2q, 2q+1), ceil(tx0/2) * wcap when nlev > 1
+    long long win_off;         // int2 (lo, hi) per row pair, ceil(tx0/2) when nlev > 1
 };
 
 struct DtwPlan {
     std::vector<PairDesc> descs;
     std::vector<int> order;
     int maxlev = 0;
-    size_t n_pyr_x = 0, n_pyr_y = 0, n_rowj = 0, n_bp = 0, n_brow = 0, n_dist = 0;
-    std::vector<int> level_max_tx;
+    size_t n_pyr_x = 0, n_pyr_y = 0, n_rowj = 0, n_bp = 0, n_brow = 0, n_dist = 0, n_win = 0;
+    std::vector<int> level_max_tx, level_max_ty;
     std::vector<char> level_has_full, level_has_band;
     int wcap = 0;
 };
@@ -110,8 +112,12 @@ static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radi
             } else {
                 d.rj_off[l] = 0;
             }
-            if ((int)plan.level_max_tx.size() <= l) plan.level_max_tx.push_back(0);
+            if ((int)plan.level_max_tx.size() <= l) {
+                plan.level_max_tx.push_back(0);
+                plan.level_max_ty.push_back(0);
+            }
             plan.level_max_tx[l] = std::max(plan.level_max_tx[l], a);
+            plan.level_max_ty[l] = std::max(plan.level_max_ty[l], b);
             ++l;
             if (radius < 0 || a < radius + 2 || b < radius + 2) break;
             a /= 2;
@@ -127,7 +133,11 @@ static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radi
         plan.level_has_full[l - 1] = 1;
         for (int q = 0; q + 1 < l; ++q) plan.level_has_band[q] = 1;
         d.dist_off = (long long)plan.n_dist;
-        if (l > 1) plan.n_dist += (size_t)((tx[p] + 1) / 2) * (size_t)plan.wcap;
+        d.win_off = (long long)plan.n_win;
+        if (l > 1) {
+            plan.n_dist += (size_t)((tx[p] + 1) / 2) * (size_t)plan.wcap;
+            plan.n_win += (size_t)((tx[p] + 1) / 2);
+        }
         d.xrow0 = xrow;
         d.yrow0 = yrow;
         xrow += tx[p];
@@ -156,6 +166,7 @@ struct DtwWorkspace {
     uint32_t* bp;
     double* brow;
     double2* dist;
+    int2* win;
     size_t bytes;
 };
 
@@ -170,6 +181,7 @@ static DtwWorkspace carve(const DtwPlan& plan, void* base) {
     w.bp = c.take<uint32_t>(plan.n_bp);
     w.brow = c.take<double>(plan.n_brow);
     w.dist = c.take<double2>(plan.n_dist);
+    w.win = c.take<int2>(plan.n_win + 1);
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -406,63 +418,82 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
 }
 
 // ---------------------------------------------------------------------------------------
-// Banded levels, part 1: local distances of every window cell.  One warp per row pair
-// (rows 2q and 2q+1 share their window), lanes over the window's columns, two columns per lane
-// in flight.  grid (n_pairs, ceil(row pairs / 8)), 256 threads.
+// Banded levels, part 1: local distances of every window cell.  A CTA takes 8 row pairs (rows
+// 2q and 2q+1 share their window) and the union of their windows; a thread owns one column of
+// that union and keeps the 16 running sums in registers, so a y value is loaded once per 16
+// cells and the x rows are shared-memory broadcasts.  Also records each row pair's window and
+// counts the level's cells.  grid (n_pairs, ceil(row pairs / 8)), 256 threads.
 // ---------------------------------------------------------------------------------------
 template <int FP, int P, typename T>
 __global__ void __launch_bounds__(256)
 dtw_dist_kernel(const PairDesc* __restrict__ descs, int level, int radius, int F, int wcap,
                 const double* __restrict__ xpyr, const double* __restrict__ ypyr,
-                const int* __restrict__ rowj, double2* __restrict__ dist) {
-    __shared__ T xs[8][FP][2];
+                const int* __restrict__ rowj, int2* __restrict__ win, double2* __restrict__ dist,
+                unsigned long long* __restrict__ cells) {
+    __shared__ __align__(16) T xs[FP][8][2];
+    __shared__ int los[8], his[8];
     const PairDesc& d = descs[blockIdx.x];
     if (level >= d.nlev - 1) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = d.tx[level], ty = d.ty[level];
-    const int rp = blockIdx.y * 8 + warp;
-    const int ia = 2 * rp, ib = ia + 1;
-    if (ia >= tx) return;                 // (no block-wide barrier below)
+    const int n_rp = (tx + 1) >> 1;
+    const int rp0 = blockIdx.y * 8;
+    if (rp0 >= n_rp) return;
+    const int nrp = min(8, n_rp - rp0);
     const double* __restrict__ xT = xpyr + d.xoff[level];
     const double* __restrict__ yT = ypyr + d.yoff[level];
-    const int ctx = d.tx[level + 1];
-    const int* __restrict__ cfirst = rowj + d.rj_off[level + 1];
-    const int* __restrict__ clast = cfirst + ctx;
-    int lo, hi;
-    {
-        const int ca = ia >> 1;
-        int r0 = max(0, ca - radius);
-        const int r1 = min(ctx - 1, ca + radius);
+    const int tid = threadIdx.x;
+    if (tid < 8) {
+        const int ctx = d.tx[level + 1];
+        const int* __restrict__ cfirst = rowj + d.rj_off[level + 1];
+        const int* __restrict__ clast = cfirst + ctx;
+        const int rp = min(rp0 + tid, n_rp - 1);
+        int r0 = max(0, rp - radius);
+        const int r1 = min(ctx - 1, rp + radius);
         r0 = min(r0, r1);
-        lo = max(0, 2 * (cfirst[r0] - radius));
-        hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
+        const int lo = max(0, 2 * (cfirst[r0] - radius));
+        const int hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
+        los[tid] = lo;
+        his[tid] = hi;
+        if (tid < nrp) {
+            win[d.win_off + rp] = make_int2(lo, hi);
+            if (cells != nullptr) {
+                const int rows = (2 * rp + 1 < tx) ? 2 : 1;
+                atomicAdd(cells + blockIdx.x, (unsigned long long)rows * (unsigned)(hi - lo + 1));
+            }
+        }
     }
-    for (int k = lane; k < FP; k += 32) {
-        xs[warp][k][0] = (T)((k < F) ? xT[(size_t)k * tx + ia] : 0.0);
-        xs[warp][k][1] = (T)((k < F && ib < tx) ? xT[(size_t)k * tx + ib] : 0.0);
+    for (int e = tid; e < FP * 16; e += 256) {
+        const int k = e >> 4, r = (e >> 1) & 7, ab = e & 1;
+        const int i = 2 * (rp0 + r) + ab;
+        xs[k][r][ab] = (T)((k < F && i < tx) ? xT[(size_t)k * tx + i] : 0.0);
     }
-    __syncwarp();
-    const int cap = min(hi - lo + 1, wcap);
-    double2* out = dist + d.dist_off + (size_t)rp * wcap;
-    for (int c0 = 0; c0 < cap; c0 += 64) {
-        const int c1 = c0 + lane, c2 = c1 + 32;
-        const bool v1 = c1 < cap, v2 = c2 < cap;
-        const double* y1 = yT + lo + (v1 ? c1 : 0);
-        const double* y2 = yT + lo + (v2 ? c2 : 0);
-        T s1a = (T)0, s1b = (T)0, s2a = (T)0, s2b = (T)0;
+    __syncthreads();
+    const int LO = los[0], HI = his[nrp - 1];
+    double2* out = dist + d.dist_off + (size_t)rp0 * wcap;
+    for (int j = LO + tid; j <= HI; j += 256) {
+        T acc[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = (T)0;
 #pragma unroll
         for (int k = 0; k < FP; ++k) {
             if (k < F) {
-                const T xa = xs[warp][k][0], xb = xs[warp][k][1];
-                const T ya = (T)__ldg(y1 + (size_t)k * ty), yb = (T)__ldg(y2 + (size_t)k * ty);
-                s1a = dist_acc<P>(s1a, sub_rn(xa, ya));
-                s1b = dist_acc<P>(s1b, sub_rn(xb, ya));
-                s2a = dist_acc<P>(s2a, sub_rn(xa, yb));
-                s2b = dist_acc<P>(s2b, sub_rn(xb, yb));
+                const T yv = (T)__ldg(yT + (size_t)k * ty + j);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    acc[r][0] = dist_acc<P>(acc[r][0], sub_rn(xs[k][r][0], yv));
+                    acc[r][1] = dist_acc<P>(acc[r][1], sub_rn(xs[k][r][1], yv));
+                }
             }
         }
-        if (v1) out[c1] = make_double2(dist_fin<P>(s1a), dist_fin<P>(s1b));
-        if (v2) out[c2] = make_double2(dist_fin<P>(s2a), dist_fin<P>(s2b));
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r < nrp) {
+                const int lo = los[r], hi = his[r];
+                if (j >= lo && j <= hi && j - lo < wcap)
+                    out[(size_t)r * wcap + (j - lo)] =
+                        make_double2(dist_fin<P>(acc[r][0]), dist_fin<P>(acc[r][1]));
+            }
+        }
     }
 }
 
@@ -473,25 +504,25 @@ __device__ __forceinline__ bool lt_nonneg(double a, double b) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Banded levels, part 2: the sweep over precomputed local distances.  Same strip-mined
-// systolic wavefront as dtw_dp_kernel (thread t owns rows i0+2t, i0+2t+1 and lags t columns);
-// the two distances of a step come from the row pair's slice, fetched four steps ahead.
+// Banded levels, part 2: the sweep over the stored local distances, one WARP per pair.
+// What is left per cell is 3 additions and 2 comparisons on a chain that runs through every
+// anti-diagonal, so the sweep is bound by per-step latency, not throughput: the systolic
+// wavefront of dtw_dp_kernel (lane t owns rows i0+2t, i0+2t+1 of a 64-row strip and lags t
+// columns) is kept, but the neighbour's value comes through a shuffle instead of shared memory
+// plus a CTA barrier, the previous strip's boundary row is read 32 columns at a time into a
+// register per lane, and the two distances of a step arrive through a per-lane shared-memory
+// ring filled by cp.async 24 steps ahead (the slices were just written by dtw_dist_kernel and
+// mostly live in DRAM).
 // ---------------------------------------------------------------------------------------
-template <int NT, int P, typename T>
-__global__ void __launch_bounds__(NT)
-dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
-               int radius, int F, int wcap, const double* __restrict__ xpyr,
-               const double* __restrict__ ypyr, const int* __restrict__ rowj,
-               const double2* __restrict__ dist, uint32_t* __restrict__ bp,
-               double* __restrict__ brow, double* __restrict__ cost,
-               unsigned long long* __restrict__ cells) {
-    constexpr int CH = NT;
-    constexpr int RING = 2 * NT;
-    constexpr int PD = 4;                 // prefetch distance (steps)
-    __shared__ double xch[2 * NT];
-    __shared__ double brs[RING];
-    __shared__ unsigned long long cell_count;
-
+template <int P, typename T>
+__global__ void __launch_bounds__(32)
+dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
+               int F, int wcap, const double* __restrict__ xpyr, const double* __restrict__ ypyr,
+               const int2* __restrict__ win, const double2* __restrict__ dist,
+               uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost) {
+    constexpr int RD = 32, PD = 24;       // ring slots per lane, prefetch distance (steps)
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double2 ring[RD][32];      // local distances in flight: [step % RD][lane]
     const int pair = order[blockIdx.x];
     const PairDesc& d = descs[pair];
     if (level >= d.nlev - 1) return;
@@ -499,24 +530,14 @@ dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
     const int tx = d.tx[level], ty = d.ty[level];
     const double* __restrict__ xT = xpyr + d.xoff[level];
     const double* __restrict__ yT = ypyr + d.yoff[level];
-    const int ctx = d.tx[level + 1];
-    const int* __restrict__ cfirst = rowj + d.rj_off[level + 1];
-    const int* __restrict__ clast = cfirst + ctx;
+    const int2* __restrict__ winp = win + d.win_off;
+    const double2* __restrict__ dist_pair = dist + d.dist_off;
     const int tiles_x = (ty + 15) >> 4;
     uint32_t* bp_pair = bp + d.bp_off;
     double* brow_pair = brow + d.brow_off;
-    const double2* dist_pair = dist + d.dist_off;
     const double INF = CUDART_INF;
 
-    auto window = [&](int a, int& lo, int& hi) {
-        const int ca = a >> 1;
-        int r0 = max(0, ca - radius);
-        const int r1 = min(ctx - 1, ca + radius);
-        r0 = min(r0, r1);
-        lo = max(0, 2 * (cfirst[r0] - radius));
-        hi = min(ty - 1, 2 * (clast[r1] + radius) + 1);
-    };
-    // local distance computed in place (columns beyond the buffer capacity)
+    // local distance computed in place (columns beyond the stored slice)
     auto inline_dist = [&](int i, int j) -> double {
         T sacc = (T)0;
         for (int k = 0; k < F; ++k)
@@ -524,29 +545,41 @@ dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         return dist_fin<P>(sacc);
     };
 
-    if (t == 0) cell_count = 0ull;
-    unsigned int my_cells = 0;
     int strip = 0;
-    for (int i0 = 0; i0 < tx; i0 += 2 * NT, ++strip) {
+    for (int i0 = 0; i0 < tx; i0 += 64, ++strip) {
         const int ia = i0 + 2 * t, ib = ia + 1;
         const bool has_b = ib < tx;
         int lo = INT_MAX, hi = INT_MIN;
-        if (ia < tx) window(ia, lo, hi);
+        if (ia < tx) {
+            const int2 w = winp[ia >> 1];
+            lo = w.x;
+            hi = w.y;
+        }
         const double2* drow = dist_pair + (size_t)(ia >> 1) * wcap;
-        int jstart, dummy;
-        window(i0, jstart, dummy);
-        const int il = min(tx, i0 + 2 * NT) - 1;
-        int hil;
-        window(il, dummy, hil);
-        const int n_steps = hil - jstart + ((il - i0) >> 1) + 1;
+        const int il = min(tx, i0 + 64) - 1;
+        const int tl = (il - i0) >> 1;                        // lane of the strip's last row
+        const int jstart = __shfl_sync(FULL, lo, 0);
+        const int hil = __shfl_sync(FULL, hi, tl);
+        const int n_steps = hil - jstart + tl + 1;
         int plo = INT_MAX, phi = INT_MIN;
-        if (i0 > 0) window(i0 - 1, plo, phi);
+        if (i0 > 0) {
+            const int2 w = winp[(i0 - 1) >> 1];
+            plo = w.x;
+            phi = w.y;
+        }
         const double* brow_in = brow_pair + ((strip & 1) ? 0 : ty);
         double* brow_out = brow_pair + ((strip & 1) ? ty : 0);
-        const bool writes_boundary = (t == NT - 1) && (i0 + 2 * NT < tx);
+        const bool writes_boundary = (t == 31) && (i0 + 64 < tx);
 
-        auto fetch = [&](int j) -> double2 {
-            return (j >= lo && j <= hi && j - lo < wcap) ? drow[j - lo] : make_double2(0.0, 0.0);
+        // asynchronous copy of this lane's distances for step s into its ring slot
+        auto prefetch = [&](int s) {
+            const int j = jstart + s - t;
+            if (j >= lo && j <= hi && j - lo < wcap) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[s & (RD - 1)][t]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                             "l"(drow + (j - lo)) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
@@ -557,34 +590,37 @@ dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
             else
                 diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
         }
-        xch[NT + t] = INF;  // parity 1 is read at step 0
         uint32_t wa = 0u, wb = 0u;
-        double2 cq[PD], nq[PD];
-#pragma unroll
-        for (int q = 0; q < PD; ++q) cq[q] = fetch(jstart + q - t);
-        __syncthreads();
+        double bval = INF;
+        __syncwarp();                     // the previous strip's reads of the ring are done
+        for (int q = 0; q < PD; ++q) prefetch(q);
 
-        for (int s0 = 0; s0 < n_steps; s0 += PD) {
-            if ((s0 % CH) == 0) {
+        for (int s0 = 0; s0 < n_steps; s0 += 4) {
+            if ((s0 & 31) == 0) {
+                // boundary row of the previous strip, columns jstart+s0 .. +31 (lane = column)
                 const int j = jstart + s0 + t;
-                brs[j & (RING - 1)] = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
-                __syncthreads();
+                bval = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
             }
 #pragma unroll
-            for (int q = 0; q < PD; ++q) nq[q] = fetch(jstart + s0 + PD + q - t);
-#pragma unroll
-            for (int q = 0; q < PD; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const int s = s0 + q;
-                if (s < n_steps) {          // uniform across the CTA
+                if (s < n_steps) {          // uniform across the warp
                     const int j = jstart + s - t;
-                    const double up_in =
-                        (t == 0) ? brs[j & (RING - 1)] : xch[((s + 1) & 1) * NT + t - 1];
+                    prefetch(s + PD);
+                    asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
+                    const double from_lane = __shfl_up_sync(FULL, vb_prev, 1);
+                    const double from_brow = __shfl_sync(FULL, bval, s & 31);
+                    const double up_in = (t == 0) ? from_brow : from_lane;
                     double va = INF, vb = INF;
                     if (j >= lo && j <= hi) {
-                        double dta = cq[q].x, dtb = cq[q].y;
+                        double dta, dtb;
                         if (j - lo >= wcap) {
                             dta = inline_dist(ia, j);
                             dtb = has_b ? inline_dist(ib, j) : 0.0;
+                        } else {
+                            const double2 dd = ring[s & (RD - 1)][t];
+                            dta = dd.x;
+                            dtb = dd.y;
                         }
                         {
                             double best = __dadd_rn(up_in, dta);
@@ -599,8 +635,6 @@ dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                                 bp_pair[bp_word(ia, j, tiles_x)] = wa;
                                 wa = 0u;
                             }
-                            if (ia == tx - 1 && j == ty - 1) cost[pair] = va;
-                            ++my_cells;
                         }
                         if (has_b) {
                             double best = __dadd_rn(va, dtb);
@@ -615,26 +649,18 @@ dtw_dpb_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                                 bp_pair[bp_word(ib, j, tiles_x)] = wb;
                                 wb = 0u;
                             }
-                            if (ib == tx - 1 && j == ty - 1) cost[pair] = vb;
                             if (writes_boundary) __stcg(brow_out + j, vb);
-                            ++my_cells;
                         }
                     }
-                    xch[(s & 1) * NT + t] = vb;
                     va_prev = va;
                     vb_prev = vb;
                     diag_in = up_in;
-                    __syncthreads();
                 }
             }
-#pragma unroll
-            for (int q = 0; q < PD; ++q) cq[q] = nq[q];
         }
-    }
-    if (cells != nullptr) {
-        atomicAdd(&cell_count, (unsigned long long)my_cells);
-        __syncthreads();
-        if (t == 0) atomicAdd(cells + pair, cell_count);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // the strip's last row finishes on the last step: D[tx-1][ty-1] of the last strip
+        if (i0 + 64 >= tx && t == tl) cost[pair] = (il == ia) ? va_prev : vb_prev;
     }
 }
 
@@ -746,32 +772,28 @@ static int launch_dp_fp(int F, int nt, int n_pairs, const DtwWorkspace& w, int l
 // Banded level: local distances, then the sweep over them.
 template <int FP, int P, typename T>
 static int launch_dist(int n_pairs, const DtwWorkspace& w, int level, int radius, int F, int wcap,
-                       int max_tx, cudaStream_t st) {
+                       int max_tx, unsigned long long* cells, cudaStream_t st) {
     const int rp_blocks = ((max_tx + 1) / 2 + 7) / 8;
     dtw_dist_kernel<FP, P, T><<<dim3(n_pairs, rp_blocks), 256, 0, st>>>(
-        w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.dist);
+        w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.win, w.dist, cells);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
 
 template <int P, typename T>
 static int launch_banded(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
-                         int wcap, int max_tx, double* cost, unsigned long long* cells,
-                         cudaStream_t st) {
+                         int wcap, int max_tx, int max_ty, double* cost,
+                         unsigned long long* cells, cudaStream_t st) {
     int rc;
-    if (F <= 8) rc = launch_dist<8, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
-    else if (F <= 16) rc = launch_dist<16, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
-    else if (F <= 26) rc = launch_dist<26, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
-    else rc = launch_dist<32, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, st);
+    if (F <= 8) rc = launch_dist<8, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
+    else if (F <= 16) rc = launch_dist<16, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
+    else if (F <= 26) rc = launch_dist<26, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
+    else rc = launch_dist<32, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
     if (rc != KW_OK) return rc;
-    if (nt == 32)
-        dtw_dpb_kernel<32, P, T><<<n_pairs, 32, 0, st>>>(w.descs, w.order, level, radius, F, wcap,
-                                                         w.xpyr, w.ypyr, w.rowj, w.dist, w.bp,
-                                                         w.brow, cost, cells);
-    else
-        dtw_dpb_kernel<64, P, T><<<n_pairs, 64, 0, st>>>(w.descs, w.order, level, radius, F, wcap,
-                                                         w.xpyr, w.ypyr, w.rowj, w.dist, w.bp,
-                                                         w.brow, cost, cells);
+    (void)nt;
+    (void)max_ty;
+    dtw_dpw_kernel<P, T><<<n_pairs, 32, 0, st>>>(w.descs, w.order, level, F, wcap, w.xpyr, w.ypyr,
+                                                 w.win, w.dist, w.bp, w.brow, cost);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
@@ -840,17 +862,17 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
             if (precision == 0) {
                 if (p_norm == 2)
                     rc = launch_banded<2, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                  mtx, cost_dev, cells, st);
+                                                  mtx, plan.level_max_ty[l], cost_dev, cells, st);
                 else
                     rc = launch_banded<1, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                  mtx, cost_dev, cells, st);
+                                                  mtx, plan.level_max_ty[l], cost_dev, cells, st);
             } else {
                 if (p_norm == 2)
                     rc = launch_banded<2, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                 mtx, cost_dev, cells, st);
+                                                 mtx, plan.level_max_ty[l], cost_dev, cells, st);
                 else
                     rc = launch_banded<1, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                 mtx, cost_dev, cells, st);
+                                                 mtx, plan.level_max_ty[l], cost_dev, cells, st);
             }
             if (rc != KW_OK) return rc;
         }
