@@ -43,6 +43,8 @@
 namespace kw {
 
 constexpr int MAXLEV = 20;
+constexpr int DPW_NW = 4;             // warps per pair in the banded sweep (strips in flight)
+constexpr int DPW_NB = DPW_NW + 1;    // boundary-row buffers per pair
 
 struct PairDesc {
     int nlev;
@@ -54,7 +56,7 @@ struct PairDesc {
     long long rj_off[MAXLEV];  // int32: first_j[tx] then last_j[tx] for levels >= 1
     long long xrow0, yrow0;    // first row in the caller's concatenated inputs
     long long bp_off;          // uint32 words, tx0 * ceil(ty0/16)
-    long long brow_off;        // doubles, 2 * ty0
+    long long brow_off;        // doubles, DPW_NB * ty0 (strip boundary rows in flight)
     long long path_off;        // points, capacity tx0 + ty0
     long long dist_off;        // double2 (rows 2q, 2q+1), ceil(tx0/2) * wcap when nlev > 1
     long long win_off;         // int2 (lo, hi) per row pair, ceil(tx0/2) when nlev > 1
@@ -145,7 +147,7 @@ static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radi
         d.bp_off = (long long)plan.n_bp;
         plan.n_bp += (size_t)((tx[p] + 7) / 8) * (size_t)((ty[p] + 15) / 16) * 8;
         d.brow_off = (long long)plan.n_brow;
-        plan.n_brow += 2 * (size_t)ty[p];
+        plan.n_brow += (size_t)DPW_NB * (size_t)ty[p];
         d.path_off = path;
         path += (long long)tx[p] + ty[p];
     }
@@ -515,18 +517,23 @@ __device__ __forceinline__ bool lt_nonneg(double a, double b) {
 // mostly live in DRAM).
 // ---------------------------------------------------------------------------------------
 template <int P, typename T>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * DPW_NW)
 dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
                int F, int wcap, const double* __restrict__ xpyr, const double* __restrict__ ypyr,
                const int2* __restrict__ win, const double2* __restrict__ dist,
                uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost) {
-    constexpr int RD = 32, PD = 24;       // ring slots per lane, prefetch distance (steps)
+    constexpr int RD = 16, PD = 12;       // ring slots per lane, prefetch distance (steps)
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ double2 ring[RD][32];      // local distances in flight: [step % RD][lane]
+    __shared__ double2 ring_all[DPW_NW][RD][32];   // local distances in flight: [step % RD][lane]
+    __shared__ unsigned long long prog_s[DPW_NB];  // (strip << 32 | last finished boundary column + 1)
     const int pair = order[blockIdx.x];
     const PairDesc& d = descs[pair];
     if (level >= d.nlev - 1) return;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2 (*ring)[32] = ring_all[warp];
+    volatile unsigned long long* prog = prog_s;
+    if (threadIdx.x < DPW_NB) prog_s[threadIdx.x] = 0ull;
+    __syncthreads();
     const int tx = d.tx[level], ty = d.ty[level];
     const double* __restrict__ xT = xpyr + d.xoff[level];
     const double* __restrict__ yT = ypyr + d.yoff[level];
@@ -545,8 +552,12 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         return dist_fin<P>(sacc);
     };
 
-    int strip = 0;
-    for (int i0 = 0; i0 < tx; i0 += 64, ++strip) {
+    // Strips are pipelined over the CTA's warps: warp w takes strips w, w + NW, ...; strip k
+    // starts as soon as strip k-1 has finished the first 32 columns of its last row, and keeps
+    // checking the producer's progress once per 32 columns.
+    const int n_strips = (tx + 63) >> 6;
+    for (int strip = warp; strip < n_strips; strip += DPW_NW) {
+        const int i0 = strip << 6;
         const int ia = i0 + 2 * t, ib = ia + 1;
         const bool has_b = ib < tx;
         int lo = INT_MAX, hi = INT_MIN;
@@ -567,9 +578,26 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
             plo = w.x;
             phi = w.y;
         }
-        const double* brow_in = brow_pair + ((strip & 1) ? 0 : ty);
-        double* brow_out = brow_pair + ((strip & 1) ? ty : 0);
+        const double* brow_in = brow_pair + (size_t)((strip + DPW_NB - 1) % DPW_NB) * ty;
+        double* brow_out = brow_pair + (size_t)(strip % DPW_NB) * ty;
         const bool writes_boundary = (t == 31) && (i0 + 64 < tx);
+        volatile unsigned long long* prog_in = prog + (strip + DPW_NB - 1) % DPW_NB;
+        volatile unsigned long long* prog_out = prog + strip % DPW_NB;
+        // wait until the previous strip's last row is final up to column `col`
+        auto wait_boundary = [&](int col) {
+            if (i0 > 0) {
+                col = min(col, phi);
+                if (col >= plo) {
+                    const unsigned long long need =
+                        ((unsigned long long)(unsigned)(strip - 1) << 32) | (unsigned)(col + 1);
+                    const long long t0 = clock64();
+                    while (*prog_in < need) {
+                        __nanosleep(200);       // leave the issue slots to the producers
+                        if (clock64() - t0 > 4000000000LL) __trap();   // protocol bug: never hang
+                    }
+                }
+            }
+        };
 
         // asynchronous copy of this lane's distances for step s into its ring slot
         auto prefetch = [&](int s) {
@@ -583,6 +611,7 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         };
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
+        wait_boundary(jstart + 31);
         if (t == 0) {
             const int jm = jstart - 1;
             if (i0 == 0)
@@ -598,6 +627,7 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         for (int s0 = 0; s0 < n_steps; s0 += 4) {
             if ((s0 & 31) == 0) {
                 // boundary row of the previous strip, columns jstart+s0 .. +31 (lane = column)
+                if (s0 > 0) wait_boundary(jstart + s0 + 31);
                 const int j = jstart + s0 + t;
                 bval = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
             }
@@ -649,7 +679,14 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                                 bp_pair[bp_word(ib, j, tiles_x)] = wb;
                                 wb = 0u;
                             }
-                            if (writes_boundary) __stcg(brow_out + j, vb);
+                            if (writes_boundary) {
+                                __stcg(brow_out + j, vb);
+                                if ((j & 15) == 15 || j == hi) {
+                                    __threadfence_block();
+                                    *prog_out = ((unsigned long long)(unsigned)strip << 32) |
+                                                (unsigned)(j + 1);
+                                }
+                            }
                         }
                     }
                     va_prev = va;
@@ -660,7 +697,7 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         // the strip's last row finishes on the last step: D[tx-1][ty-1] of the last strip
-        if (i0 + 64 >= tx && t == tl) cost[pair] = (il == ia) ? va_prev : vb_prev;
+        if (strip == n_strips - 1 && t == tl) cost[pair] = (il == ia) ? va_prev : vb_prev;
     }
 }
 
@@ -792,7 +829,7 @@ static int launch_banded(int F, int nt, int n_pairs, const DtwWorkspace& w, int 
     if (rc != KW_OK) return rc;
     (void)nt;
     (void)max_ty;
-    dtw_dpw_kernel<P, T><<<n_pairs, 32, 0, st>>>(w.descs, w.order, level, F, wcap, w.xpyr, w.ypyr,
+    dtw_dpw_kernel<P, T><<<n_pairs, 32 * DPW_NW, 0, st>>>(w.descs, w.order, level, F, wcap, w.xpyr, w.ypyr,
                                                  w.win, w.dist, w.bp, w.brow, cost);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
