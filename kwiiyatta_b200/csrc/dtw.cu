@@ -505,6 +505,18 @@ __device__ __forceinline__ bool lt_nonneg(double a, double b) {
     return __double_as_longlong(a) < __double_as_longlong(b);
 }
 
+// Local distance of one cell straight from the pyramids: the rare columns of a window that is
+// wider than the stored slice.  Kept out of line so the sweep's loop stays small.
+template <int P, typename T>
+__device__ __noinline__ double slow_dist(const double* __restrict__ xT,
+                                         const double* __restrict__ yT, int tx, int ty, int F,
+                                         int i, int j) {
+    T sacc = (T)0;
+    for (int k = 0; k < F; ++k)
+        sacc = dist_acc<P>(sacc, sub_rn((T)xT[(size_t)k * tx + i], (T)yT[(size_t)k * ty + j]));
+    return dist_fin<P>(sacc);
+}
+
 // ---------------------------------------------------------------------------------------
 // Banded levels, part 2: the sweep over the stored local distances, one WARP per pair.
 // What is left per cell is 3 additions and 2 comparisons on a chain that runs through every
@@ -526,11 +538,13 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ double2 ring_all[DPW_NW][RD][32];   // local distances in flight: [step % RD][lane]
     __shared__ unsigned long long prog_s[DPW_NB];  // (strip << 32 | last finished boundary column + 1)
+    __shared__ double bch_all[DPW_NW][32];         // boundary-row chunk of each warp, for its lane 0
     const int pair = order[blockIdx.x];
     const PairDesc& d = descs[pair];
     if (level >= d.nlev - 1) return;
     const int t = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2 (*ring)[32] = ring_all[warp];
+    double* bch = bch_all[warp];
     volatile unsigned long long* prog = prog_s;
     if (threadIdx.x < DPW_NB) prog_s[threadIdx.x] = 0ull;
     __syncthreads();
@@ -544,34 +558,28 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
     double* brow_pair = brow + d.brow_off;
     const double INF = CUDART_INF;
 
-    // local distance computed in place (columns beyond the stored slice)
-    auto inline_dist = [&](int i, int j) -> double {
-        T sacc = (T)0;
-        for (int k = 0; k < F; ++k)
-            sacc = dist_acc<P>(sacc, sub_rn((T)xT[(size_t)k * tx + i], (T)yT[(size_t)k * ty + j]));
-        return dist_fin<P>(sacc);
-    };
-
     // Strips are pipelined over the CTA's warps: warp w takes strips w, w + NW, ...; strip k
     // starts as soon as strip k-1 has finished the first 32 columns of its last row, and keeps
     // checking the producer's progress once per 32 columns.
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[0][t]);
     const int n_strips = (tx + 63) >> 6;
     for (int strip = warp; strip < n_strips; strip += DPW_NW) {
         const int i0 = strip << 6;
         const int ia = i0 + 2 * t, ib = ia + 1;
         const bool has_b = ib < tx;
-        int lo = INT_MAX, hi = INT_MIN;
+        int lo = 0, hi = -1;                 // lanes past the last row: empty window
         if (ia < tx) {
             const int2 w = winp[ia >> 1];
             lo = w.x;
             hi = w.y;
         }
+        const int width = hi - lo + 1, lim = min(width, wcap);
         const double2* drow = dist_pair + (size_t)(ia >> 1) * wcap;
         const int il = min(tx, i0 + 64) - 1;
         const int tl = (il - i0) >> 1;                        // lane of the strip's last row
         const int jstart = __shfl_sync(FULL, lo, 0);
         const int hil = __shfl_sync(FULL, hi, tl);
-        const int n_steps = hil - jstart + tl + 1;
+        const int n_steps = (hil - jstart + tl + 1 + 3) & ~3;   // padded steps touch no window
         int plo = INT_MAX, phi = INT_MIN;
         if (i0 > 0) {
             const int2 w = winp[(i0 - 1) >> 1];
@@ -583,6 +591,8 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         const bool writes_boundary = (t == 31) && (i0 + 64 < tx);
         volatile unsigned long long* prog_in = prog + (strip + DPW_NB - 1) % DPW_NB;
         volatile unsigned long long* prog_out = prog + strip % DPW_NB;
+        uint32_t* bpa = bp_pair + bp_word(ia, 0, tiles_x);    // + 8 * (j >> 4); row ib: + 1
+        const int col0 = jstart - t - lo;                     // window-relative column at step 0
         // wait until the previous strip's last row is final up to column `col`
         auto wait_boundary = [&](int col) {
             if (i0 > 0) {
@@ -592,22 +602,30 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                         ((unsigned long long)(unsigned)(strip - 1) << 32) | (unsigned)(col + 1);
                     const long long t0 = clock64();
                     while (*prog_in < need) {
-                        __nanosleep(200);       // leave the issue slots to the producers
+                        __nanosleep(100);       // leave the issue slots to the producers
                         if (clock64() - t0 > 4000000000LL) __trap();   // protocol bug: never hang
                     }
                 }
             }
         };
-
-        // asynchronous copy of this lane's distances for step s into its ring slot
+        // This lane's two distances for step s go to ring slot s % RD: an asynchronous copy of
+        // the stored value, +inf outside the window (so the cell code needs no activity test),
+        // computed in place for the columns of a window wider than the stored slice.
         auto prefetch = [&](int s) {
-            const int j = jstart + s - t;
-            if (j >= lo && j <= hi && j - lo < wcap) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[s & (RD - 1)][t]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
-                             "l"(drow + (j - lo)) : "memory");
+            const int c = col0 + s;
+            const unsigned dst = ring_base + ((unsigned)(s & (RD - 1)) << 9);
+            if ((unsigned)c < (unsigned)lim) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(drow + c)
+                             : "memory");
+            } else {
+                double da = INF, db = INF;
+                if ((unsigned)c < (unsigned)width) {
+                    da = slow_dist<P, T>(xT, yT, tx, ty, F, ia, lo + c);
+                    db = has_b ? slow_dist<P, T>(xT, yT, tx, ty, F, ib, lo + c) : INF;
+                }
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst), "d"(da), "d"(db)
+                             : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
@@ -620,84 +638,84 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                 diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
         }
         uint32_t wa = 0u, wb = 0u;
-        double bval = INF;
+        double last_a = INF, last_b = INF;    // D at the last column of this lane's rows
         __syncwarp();                     // the previous strip's reads of the ring are done
-        for (int q = 0; q < PD; ++q) prefetch(q);
+#pragma unroll
+        for (int g = 0; g < PD / 4; ++g) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) prefetch(4 * g + q);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         for (int s0 = 0; s0 < n_steps; s0 += 4) {
             if ((s0 & 31) == 0) {
-                // boundary row of the previous strip, columns jstart+s0 .. +31 (lane = column)
+                // boundary row of the previous strip, columns jstart+s0 .. +31 (lane = column),
+                // staged for lane 0
                 if (s0 > 0) wait_boundary(jstart + s0 + 31);
                 const int j = jstart + s0 + t;
-                bval = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                __syncwarp();
+                bch[t] = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                __syncwarp();
             }
+            asm volatile("cp.async.wait_group %0;" ::"n"(PD / 4 - 1) : "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) prefetch(s0 + PD + q);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            const unsigned slot0 = ring_base + ((unsigned)(s0 & (RD - 1)) << 9);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int s = s0 + q;
-                if (s < n_steps) {          // uniform across the warp
-                    const int j = jstart + s - t;
-                    prefetch(s + PD);
-                    asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
-                    const double from_lane = __shfl_up_sync(FULL, vb_prev, 1);
-                    const double from_brow = __shfl_sync(FULL, bval, s & 31);
-                    const double up_in = (t == 0) ? from_brow : from_lane;
-                    double va = INF, vb = INF;
-                    if (j >= lo && j <= hi) {
-                        double dta, dtb;
-                        if (j - lo >= wcap) {
-                            dta = inline_dist(ia, j);
-                            dtb = has_b ? inline_dist(ib, j) : 0.0;
-                        } else {
-                            const double2 dd = ring[s & (RD - 1)][t];
-                            dta = dd.x;
-                            dtb = dd.y;
+                const int c = col0 + s0 + q;          // window-relative column
+                const int j = lo + c;
+                double dta, dtb;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dta), "=d"(dtb)
+                             : "r"(slot0 + (unsigned)q * 512u) : "memory");
+                double up_in = __shfl_up_sync(FULL, vb_prev, 1);
+                if (t == 0) up_in = bch[(s0 + q) & 31];
+                // row a
+                double best = __dadd_rn(up_in, dta);
+                double cnd = __dadd_rn(va_prev, dta);
+                const bool a1 = cnd < best;
+                best = a1 ? cnd : best;
+                cnd = __dadd_rn(diag_in, dta);
+                const bool a2 = cnd < best;
+                const double va = a2 ? cnd : best;
+                wa = __funnelshift_r(wa, a2 ? 2u : (a1 ? 1u : 0u), 2);
+                // row b
+                best = __dadd_rn(va, dtb);
+                cnd = __dadd_rn(vb_prev, dtb);
+                const bool b1 = cnd < best;
+                best = b1 ? cnd : best;
+                cnd = __dadd_rn(va_prev, dtb);
+                const bool b2 = cnd < best;
+                const double vb = b2 ? cnd : best;
+                wb = __funnelshift_r(wb, b2 ? 2u : (b1 ? 1u : 0u), 2);
+                if ((unsigned)c < (unsigned)width) {
+                    // codes enter at the top of the word: cell j sits at bits 2 (j & 15) once
+                    // the word's last column is in
+                    if ((j & 15) == 15 || c == width - 1) {
+                        const int sh = 2 * (15 - (j & 15));
+                        uint32_t* wp = bpa + ((j >> 4) << 3);
+                        last_a = va;
+                        last_b = vb;
+                        wp[0] = wa >> sh;
+                        if (has_b) wp[1] = wb >> sh;
+                        if (writes_boundary) {
+                            __stcg(brow_out + j, vb);
+                            __threadfence_block();
+                            *prog_out = ((unsigned long long)(unsigned)strip << 32) | (unsigned)(j + 1);
                         }
-                        {
-                            double best = __dadd_rn(up_in, dta);
-                            uint32_t code = 0u;
-                            double c = __dadd_rn(va_prev, dta);
-                            if (lt_nonneg(c, best)) { best = c; code = 1u; }
-                            c = __dadd_rn(diag_in, dta);
-                            if (lt_nonneg(c, best)) { best = c; code = 2u; }
-                            va = best;
-                            wa |= code << (2 * (j & 15));
-                            if ((j & 15) == 15 || j == hi) {
-                                bp_pair[bp_word(ia, j, tiles_x)] = wa;
-                                wa = 0u;
-                            }
-                        }
-                        if (has_b) {
-                            double best = __dadd_rn(va, dtb);
-                            uint32_t code = 0u;
-                            double c = __dadd_rn(vb_prev, dtb);
-                            if (lt_nonneg(c, best)) { best = c; code = 1u; }
-                            c = __dadd_rn(va_prev, dtb);
-                            if (lt_nonneg(c, best)) { best = c; code = 2u; }
-                            vb = best;
-                            wb |= code << (2 * (j & 15));
-                            if ((j & 15) == 15 || j == hi) {
-                                bp_pair[bp_word(ib, j, tiles_x)] = wb;
-                                wb = 0u;
-                            }
-                            if (writes_boundary) {
-                                __stcg(brow_out + j, vb);
-                                if ((j & 15) == 15 || j == hi) {
-                                    __threadfence_block();
-                                    *prog_out = ((unsigned long long)(unsigned)strip << 32) |
-                                                (unsigned)(j + 1);
-                                }
-                            }
-                        }
+                    } else if (writes_boundary) {
+                        __stcg(brow_out + j, vb);
                     }
-                    va_prev = va;
-                    vb_prev = vb;
-                    diag_in = up_in;
                 }
+                va_prev = va;
+                vb_prev = vb;
+                diag_in = up_in;
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // the strip's last row finishes on the last step: D[tx-1][ty-1] of the last strip
-        if (strip == n_strips - 1 && t == tl) cost[pair] = (il == ia) ? va_prev : vb_prev;
+        // D[tx-1][ty-1] is the last column of the last strip's last row
+        if (strip == n_strips - 1 && t == tl) cost[pair] = (il == ia) ? last_a : last_b;
     }
 }
 
