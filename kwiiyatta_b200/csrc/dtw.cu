@@ -202,11 +202,22 @@ __global__ void dtw_pyramid_kernel(const PairDesc* __restrict__ descs, int level
     const int T = is_y ? d.ty[level] : d.tx[level];
     double* out = is_y ? ypyr + d.yoff[level] : xpyr + d.xoff[level];
     if (level == 0) {
+        // row-major (T x F) -> k-major (F x T) through a shared tile of 64 rows: both the
+        // global reads and the global writes are contiguous runs
+        __shared__ double tile[64][33];
         const double* in = is_y ? y_in + d.yrow0 * F : x_in + d.xrow0 * F;
-        const long long n = (long long)T * F;
-        for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-            const int i = (int)(e / F), k = (int)(e % F);
-            out[(size_t)k * T + i] = in[e];
+        for (int r0 = 0; r0 < T; r0 += 64) {
+            const int nr = min(64, T - r0);
+            for (int e = threadIdx.x; e < nr * F; e += blockDim.x) {
+                const int i = e / F, k = e - i * F;
+                tile[i][k] = in[(size_t)r0 * F + e];
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < F * 64; e += blockDim.x) {
+                const int k = e >> 6, i = e & 63;
+                if (i < nr) out[(size_t)k * T + r0 + i] = tile[i][k];
+            }
+            __syncthreads();
         }
     } else {
         const int Tp = is_y ? d.ty[level - 1] : d.tx[level - 1];
@@ -611,21 +622,30 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         // This lane's two distances for step s go to ring slot s % RD: an asynchronous copy of
         // the stored value, +inf outside the window (so the cell code needs no activity test),
         // computed in place for the columns of a window wider than the stored slice.
+        const bool wide = width > wcap;
         auto prefetch = [&](int s) {
             const int c = col0 + s;
             const unsigned dst = ring_base + ((unsigned)(s & (RD - 1)) << 9);
-            if ((unsigned)c < (unsigned)lim) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(drow + c)
-                             : "memory");
-            } else {
-                double da = INF, db = INF;
-                if ((unsigned)c < (unsigned)width) {
-                    da = slow_dist<P, T>(xT, yT, tx, ty, F, ia, lo + c);
-                    db = has_b ? slow_dist<P, T>(xT, yT, tx, ty, F, ib, lo + c) : INF;
-                }
+            const bool v = (unsigned)c < (unsigned)lim;
+            asm volatile(
+                "{\n .reg .pred p;\n setp.ne.b32 p, %0, 0;\n"
+                " @p cp.async.cg.shared.global [%1], [%2], 16;\n"
+                " @!p st.shared.v2.f64 [%1], {%3, %3};\n}"
+                ::"r"((int)v), "r"(dst), "l"(drow + c), "d"(INF) : "memory");
+            if (wide && !v && (unsigned)c < (unsigned)width) {
+                const double da = slow_dist<P, T>(xT, yT, tx, ty, F, ia, lo + c);
+                const double db = has_b ? slow_dist<P, T>(xT, yT, tx, ty, F, ib, lo + c) : INF;
                 asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst), "d"(da), "d"(db)
                              : "memory");
             }
+        };
+        // back-pointer word of the 16-column group ending at column e, from a 64-bit shift
+        // register that holds the codes of columns jl-31 .. jl (column jl in the top two bits)
+        auto store_words = [&](int e, int jl, unsigned long long qa, unsigned long long qb) {
+            const int sh = 32 - 2 * (jl - e);          // e in [jl - 15, jl + 15]
+            uint32_t* wp = bpa + ((e >> 4) << 3);
+            wp[0] = (uint32_t)(qa >> sh);
+            if (has_b) wp[1] = (uint32_t)(qb >> sh);
         };
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
@@ -637,9 +657,12 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
             else
                 diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
         }
-        uint32_t wa = 0u, wb = 0u;
-        double last_a = INF, last_b = INF;    // D at the last column of this lane's rows
-        __syncwarp();                     // the previous strip's reads of the ring are done
+        unsigned long long qa = 0ull, qb = 0ull;
+        double ha[4], hb[4];                  // D of the last four steps (for the final cell)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ha[q] = hb[q] = INF;
+        int e_done = -1;                      // last column group already stored
+        __syncwarp();                         // the previous strip's reads of the ring are done
 #pragma unroll
         for (int g = 0; g < PD / 4; ++g) {
 #pragma unroll
@@ -661,61 +684,85 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
 #pragma unroll
             for (int q = 0; q < 4; ++q) prefetch(s0 + PD + q);
             asm volatile("cp.async.commit_group;" ::: "memory");
+            // this iteration's distances and (for lane 0) boundary values, ahead of the chain
             const unsigned slot0 = ring_base + ((unsigned)(s0 & (RD - 1)) << 9);
+            double da[4], db[4], bq[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int c = col0 + s0 + q;          // window-relative column
-                const int j = lo + c;
-                double dta, dtb;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dta), "=d"(dtb)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(da[q]), "=d"(db[q])
                              : "r"(slot0 + (unsigned)q * 512u) : "memory");
+                bq[q] = bch[(s0 + q) & 31];
+            }
+            const int cbase = col0 + s0;              // window-relative column of step s0
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
                 double up_in = __shfl_up_sync(FULL, vb_prev, 1);
-                if (t == 0) up_in = bch[(s0 + q) & 31];
+                up_in = (t == 0) ? bq[q] : up_in;
                 // row a
-                double best = __dadd_rn(up_in, dta);
-                double cnd = __dadd_rn(va_prev, dta);
+                double best = __dadd_rn(up_in, da[q]);
+                double cnd = __dadd_rn(va_prev, da[q]);
                 const bool a1 = cnd < best;
                 best = a1 ? cnd : best;
-                cnd = __dadd_rn(diag_in, dta);
+                cnd = __dadd_rn(diag_in, da[q]);
                 const bool a2 = cnd < best;
                 const double va = a2 ? cnd : best;
-                wa = __funnelshift_r(wa, a2 ? 2u : (a1 ? 1u : 0u), 2);
+                qa = (qa >> 2) | ((unsigned long long)(a2 ? 2u : (a1 ? 1u : 0u)) << 62);
                 // row b
-                best = __dadd_rn(va, dtb);
-                cnd = __dadd_rn(vb_prev, dtb);
+                best = __dadd_rn(va, db[q]);
+                cnd = __dadd_rn(vb_prev, db[q]);
                 const bool b1 = cnd < best;
                 best = b1 ? cnd : best;
-                cnd = __dadd_rn(va_prev, dtb);
+                cnd = __dadd_rn(va_prev, db[q]);
                 const bool b2 = cnd < best;
                 const double vb = b2 ? cnd : best;
-                wb = __funnelshift_r(wb, b2 ? 2u : (b1 ? 1u : 0u), 2);
-                if ((unsigned)c < (unsigned)width) {
-                    // codes enter at the top of the word: cell j sits at bits 2 (j & 15) once
-                    // the word's last column is in
-                    if ((j & 15) == 15 || c == width - 1) {
-                        const int sh = 2 * (15 - (j & 15));
-                        uint32_t* wp = bpa + ((j >> 4) << 3);
-                        last_a = va;
-                        last_b = vb;
-                        wp[0] = wa >> sh;
-                        if (has_b) wp[1] = wb >> sh;
-                        if (writes_boundary) {
-                            __stcg(brow_out + j, vb);
-                            __threadfence_block();
-                            *prog_out = ((unsigned long long)(unsigned)strip << 32) | (unsigned)(j + 1);
-                        }
-                    } else if (writes_boundary) {
-                        __stcg(brow_out + j, vb);
-                    }
-                }
+                qb = (qb >> 2) | ((unsigned long long)(b2 ? 2u : (b1 ? 1u : 0u)) << 62);
+                if (writes_boundary && (unsigned)(cbase + q) < (unsigned)width)
+                    __stcg(brow_out + lo + cbase + q, vb);
+                ha[q] = va;
+                hb[q] = vb;
                 va_prev = va;
                 vb_prev = vb;
                 diag_in = up_in;
             }
+            if ((s0 & 15) == 12) {
+                // every 16 steps (all lanes together): store the column group that was
+                // completed since the last time, and publish the boundary row's progress
+                const int jl = lo + cbase + 3;
+                const int e = jl - ((jl + 1) & 15);
+                if (e >= lo && e - 15 <= hi) store_words(e, jl, qa, qb);
+                e_done = e;
+                if (writes_boundary) {
+                    const int jp = min(jl, hi);
+                    if (jp >= lo) {
+                        __threadfence_block();
+                        *prog_out = ((unsigned long long)(unsigned)strip << 32) | (unsigned)(jp + 1);
+                    }
+                }
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // D[tx-1][ty-1] is the last column of the last strip's last row
-        if (strip == n_strips - 1 && t == tl) cost[pair] = (il == ia) ? last_a : last_b;
+        {
+            // column groups not stored yet: the last complete one and the partial one after it
+            const int jl = lo + col0 + n_steps - 1;
+            const int e = jl - ((jl + 1) & 15);
+            if (width > 0) {
+                if (e > e_done && e >= lo && e - 15 <= hi) store_words(e, jl, qa, qb);
+                if (e != jl && hi > e) store_words(e + 16, jl, qa, qb);
+            }
+            if (writes_boundary) {
+                __threadfence_block();
+                *prog_out = ((unsigned long long)(unsigned)strip << 32) | (unsigned)(hi + 1);
+            }
+        }
+        // D[tx-1][ty-1]: the last row's last column, reached n_steps - 1 - (padding) steps in
+        if (strip == n_strips - 1 && t == tl) {
+            const int pad = (n_steps - 1) - (hil - jstart + tl);      // 0..3
+            double fa = ha[3], fb = hb[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (pad == 3 - q) { fa = ha[q]; fb = hb[q]; }
+            cost[pair] = (il == ia) ? fa : fb;
+        }
     }
 }
 
