@@ -196,6 +196,9 @@ def run_b200(args):
     nominal_total = sum_over_ranks(nominal_local)
     dtw_cells_per_s = cells_total * K / (dtw_ms / 1e3)
     # end to end through the fastdtw-compatible API: host features in, host paths out
+    kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)     # warm-up (pins the staging)
+    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)
     torch.cuda.synchronize()
@@ -244,7 +247,7 @@ def run_b200(args):
     flops_half = 2.0 * n_frames * N_MIX_EM * dim * dim
     # end to end through the converter back-end API with host buffers
     x_pinned = torch.from_numpy(x_joint).pin_memory()
-    e2e_iters = max(2, min(K, 5))
+    e2e_iters = 100     # the reference's own default (GMMFeatureConverter(max_iter=100)), tol = 0
     conv = kw.B200GMMFeatureConverter(components=N_MIX_EM, max_iter=e2e_iters, tol=0.0,
                                       verbose=0, device=dev, precision=args.precision)
     barrier()
@@ -285,7 +288,10 @@ def run_b200(args):
     conv_value = conv_frames_total * K / (conv_ms / 1e3)
     src_host = src_dev.cpu().numpy()
     src_list = [src_host[i * UTT_FRAMES:(i + 1) * UTT_FRAMES] for i in range(n_utts)]
+    paramgen.transform_many(src_list[:max(1, n_utts // 8)])     # warm-up (pins the staging)
+    paramgen.transform_many(src_list)
     torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     paramgen.transform_many(src_list)
     torch.cuda.synchronize()

@@ -2,6 +2,8 @@
 
 There is no CPU fallback: if the library is missing or a call fails, this raises."""
 import ctypes
+
+import numpy as np
 import os
 
 from . import build as _build
@@ -97,3 +99,77 @@ def ptr(t):
 
 def stream_ptr(torch):
     return torch.cuda.current_stream().cuda_stream
+
+
+# Pinned staging buffers for the host -> device copy of a batch, kept between calls (pinning is
+# far more expensive than the copy).  slot -> (tensor, event of the last copy that read it)
+_STAGING = {}
+_GATHER_THREADS = 8
+
+
+def gather_to_device(torch, arrays, dev, slot):
+    """Row-concatenate ``arrays`` into a pinned buffer (several threads; numpy releases the
+    GIL while copying) and start one asynchronous copy to ``dev``."""
+    from concurrent.futures import ThreadPoolExecutor
+    rows = np.array([len(a) for a in arrays], dtype=np.int64)
+    f = arrays[0].shape[1]
+    total = int(rows.sum())
+    key = (slot, str(dev))
+    buf, ev = _STAGING.get(key, (None, None))
+    if buf is None or buf.numel() < total * f:
+        buf = torch.empty(max(total * f, 1), dtype=torch.float64).pin_memory()
+        ev = None
+    if ev is not None:
+        ev.synchronize()            # the previous batch's copy has left the buffer
+    view = buf[:total * f].view(total, f)
+    host = view.numpy()
+    off = np.concatenate(([0], np.cumsum(rows)))
+    n = len(arrays)
+    step = max(1, (n + _GATHER_THREADS - 1) // _GATHER_THREADS)
+
+    def copy(lo):
+        for i in range(lo, min(n, lo + step)):
+            host[off[i]:off[i + 1]] = arrays[i]
+
+    if total * f * 8 < (1 << 22) or n == 1:
+        copy(0) if n == 1 else [copy(lo) for lo in range(0, n, step)]
+    else:
+        with ThreadPoolExecutor(_GATHER_THREADS) as ex:
+            list(ex.map(copy, range(0, n, step)))
+    out = view.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    _STAGING[key] = (buf, ev)
+    return out
+
+
+def scatter_to_host(torch, tensor, offsets, slot):
+    """Device (rows, F) tensor -> list of freshly allocated host arrays, rows
+    ``offsets[i]:offsets[i + 1]`` each: one copy into a pinned buffer kept between calls, then
+    the per-segment copies on several threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    total, f = tensor.shape
+    key = (slot, str(tensor.device))
+    buf, _ = _STAGING.get(key, (None, None))
+    if buf is None or buf.numel() < total * f or buf.dtype != tensor.dtype:
+        buf = torch.empty(max(total * f, 1), dtype=tensor.dtype).pin_memory()
+    _STAGING[key] = (buf, None)
+    view = buf[:total * f].view(total, f)
+    view.copy_(tensor, non_blocking=True)
+    torch.cuda.current_stream(tensor.device).synchronize()
+    host = view.numpy()
+    n = len(offsets) - 1
+    out = [None] * n
+    step = max(1, (n + _GATHER_THREADS - 1) // _GATHER_THREADS)
+
+    def copy(lo):
+        for i in range(lo, min(n, lo + step)):
+            out[i] = host[offsets[i]:offsets[i + 1]].copy()
+
+    if total * f * tensor.element_size() < (1 << 22) or n == 1:
+        for lo in range(0, n, step):
+            copy(lo)
+    else:
+        with ThreadPoolExecutor(_GATHER_THREADS) as ex:
+            list(ex.map(copy, range(0, n, step)))
+    return out

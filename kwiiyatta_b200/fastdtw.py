@@ -109,8 +109,8 @@ def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None):
     dev = torch.device('cuda' if device is None else device)
     tx = np.array([len(x) for x in xs], dtype=np.int32)
     ty = np.array([len(y) for y in ys], dtype=np.int32)
-    x_dev = torch.from_numpy(np.concatenate(xs)).to(dev, non_blocking=True)
-    y_dev = torch.from_numpy(np.concatenate(ys)).to(dev, non_blocking=True)
+    x_dev = _lib.gather_to_device(torch, xs, dev, 'dtw_x')
+    y_dev = _lib.gather_to_device(torch, ys, dev, 'dtw_y')
     return fastdtw_batch_device(x_dev, y_dev, tx, ty, radius, dist, precision).to_host()
 
 

@@ -79,10 +79,10 @@ class MLPG:
         if lens.sum() == 0:
             return [np.zeros((0, self.static_dim)) for _ in feats]
         off = np.concatenate(([0], np.cumsum(lens)))
-        src = torch.from_numpy(np.concatenate(feats)).to(self._dev, non_blocking=True)
+        src = _lib.gather_to_device(torch, feats, self._dev, 'mlpg_in')
         off_dev = torch.from_numpy(off).to(self._dev, non_blocking=True)
-        out = self.transform_device(src, off_dev, len(feats), int(lens.max())).cpu().numpy()
-        return [out[off[i]:off[i + 1]] for i in range(len(feats))]
+        out = self.transform_device(src, off_dev, len(feats), int(lens.max()))
+        return _lib.scatter_to_host(torch, out, off, 'mlpg_out')
 
     def transform_soft(self, src):
         """MLPGBase.transform: per-frame soft-posterior conditional mean, (T, dim_half)."""
