@@ -257,16 +257,79 @@ convert_soft_kernel(long long N, long long Npad, int K, int Dh, const double* __
     }
 }
 
-// MLPG: one thread per (utterance, static dim).  Banded Cholesky (bandwidth 2) with the
-// factor and the forward solution kept in a global workspace laid out [frame][static dim].
+// MLPG in two kernels.
+//  1. convert_band_kernel, one thread per (frame, static dim): the pentadiagonal normal
+//     equations W^T P W y = W^T P mu of that dimension, row by row: a_i = P[i][i],
+//     b_i = P[i][i+1], c_i = P[i][i+2] and the right-hand side.  Fully parallel; this is where
+//     the per-frame gathers (mixture -> variance) and the divisions happen.
+//  2. convert_mlpg_kernel, one thread per (utterance, static dim): banded Cholesky
+//     (bandwidth 2) and the two substitutions, in place over the four arrays, reading four
+//     steps ahead of the recurrence.  The chain per frame is two fused multiply-adds and one
+//     reciprocal square root: with r_i = 1 / L[i][i], e_i = L[i][i-1], f_i = L[i][i-2]
+//        f_i = c_{i-2} r_{i-2};  e_i = (b_{i-1} - f_i e_{i-1}) r_{i-1};
+//        r_i = rsqrt(a_i - f_i^2 - e_i^2);  z_i = (rhs_i - e_i z_{i-1} - f_i z_{i-2}) r_i
+//     and back:  y_i = (z_i - e_{i+1} y_{i+1} - f_{i+2} y_{i+2}) r_i.
 struct Windows {
     double c[3][3];  // c[w][o+1]: coefficient of window w at offset o in {-1, 0, 1}
 };
 
+// flags[n]: bit 0 = first frame of its utterance, bit 1 = last frame
+__global__ void convert_flags_kernel(int n_utts, const int64_t* __restrict__ off,
+                                     unsigned char* __restrict__ flags) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utts) return;
+    const long long t0 = off[u], t1 = off[u + 1];
+    if (t1 <= t0) return;
+    if (t1 - t0 == 1) {
+        flags[t0] = 3;
+    } else {
+        flags[t0] = 1;
+        flags[t1 - 1] = 2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+convert_band_kernel(long long total, int sd, int Dh, const double* __restrict__ E,
+                    const int32_t* __restrict__ mix, const double* __restrict__ var,
+                    const unsigned char* __restrict__ flags, Windows win,
+                    double* __restrict__ band) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total * sd) return;
+    const long long n = gid / sd;
+    const int d = (int)(gid - n * sd);
+    const unsigned fl = flags[n];
+    // p[w], bs[w] at frames n-1 (m), n (c), n+1 (x)
+    double pm[3] = {0, 0, 0}, bm[3] = {0, 0, 0}, pc[3], bc[3], px[3] = {0, 0, 0}, bx[3] = {0, 0, 0};
+    auto load = [&](long long t, double* p, double* b) {
+        const int m = mix[t];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const double prec = 1.0 / var[(size_t)m * Dh + w * sd + d];
+            p[w] = prec;
+            b[w] = prec * E[t * Dh + w * sd + d];
+        }
+    };
+    load(n, pc, bc);
+    if (!(fl & 1u)) load(n - 1, pm, bm);
+    if (!(fl & 2u)) load(n + 1, px, bx);
+    double a_i = 0.0, b_i = 0.0, c_i = 0.0, rhs = 0.0;
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        const double cm = win.c[w][0], c0 = win.c[w][1], cp = win.c[w][2];
+        a_i += cp * cp * pm[w] + c0 * c0 * pc[w] + cm * cm * px[w];
+        rhs += cp * bm[w] + c0 * bc[w] + cm * bx[w];
+        b_i += c0 * cp * pc[w] + cm * c0 * px[w];
+        c_i += cm * cp * px[w];
+    }
+    const size_t plane = (size_t)total * sd;
+    band[gid] = a_i;
+    band[plane + gid] = b_i;
+    band[2 * plane + gid] = c_i;
+    band[3 * plane + gid] = rhs;
+}
+
 __global__ void __launch_bounds__(96)
-convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, int Dh,
-                    const double* __restrict__ E, const int32_t* __restrict__ mix,
-                    const double* __restrict__ var, Windows win, double* __restrict__ ws,
+convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, double* __restrict__ ws,
                     long long total, double* __restrict__ out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int u = gid / sd, d = gid - u * sd;
@@ -274,64 +337,69 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, int Dh,
     const long long t0 = off[u];
     const int T = (int)(off[u + 1] - t0);
     if (T <= 0) return;
-    double* l0 = ws;
-    double* l1 = ws + (size_t)total * sd;
-    double* l2 = ws + 2 * (size_t)total * sd;
-    double* zz = ws + 3 * (size_t)total * sd;
-    // p[w], bs[w] at frames i-1 (m), i (c), i+1 (n)
-    double pm[3] = {0, 0, 0}, bm[3] = {0, 0, 0}, pc[3], bc[3], pn[3] = {0, 0, 0}, bn[3] = {0, 0, 0};
-    auto load = [&](int t, double* p, double* b) {
-        const long long n = t0 + t;
-        const int m = mix[n];
+    const size_t plane = (size_t)total * sd;
+    double* pa = ws + (size_t)t0 * sd + d;     // a -> r
+    double* pb = pa + plane;                   // b -> e
+    double* pcc = pb + plane;                  // c -> f
+    double* pr = pcc + plane;                  // rhs -> z
+    constexpr int PF = 4;
+    double c_m2 = 0, c_m1 = 0, b_m1 = 0, r_m1 = 1, r_m2 = 1, e_m1 = 0, z_m1 = 0, z_m2 = 0;
+    double na[PF], nb[PF], nc[PF], nr[PF];
+    auto fetch = [&](int i0) {
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            const double prec = 1.0 / var[(size_t)m * Dh + w * sd + d];
-            p[w] = prec;
-            b[w] = prec * E[n * Dh + w * sd + d];
+        for (int q = 0; q < PF; ++q) {
+            const int i = min(i0 + q, T - 1);
+            const size_t o = (size_t)i * sd;
+            na[q] = pa[o]; nb[q] = pb[o]; nc[q] = pcc[o]; nr[q] = pr[o];
         }
     };
-    load(0, pc, bc);
-    // banded Cholesky P = L L^T with d_i = L[i][i], e_i = L[i][i-1], f_i = L[i][i-2]:
-    //   f_i = c_{i-2} / d_{i-2};  e_i = (b_{i-1} - f_i e_{i-1}) / d_{i-1};
-    //   d_i = sqrt(a_i - f_i^2 - e_i^2);  z_i = (rhs_i - e_i z_{i-1} - f_i z_{i-2}) / d_i
-    // where a_i = P[i][i], b_i = P[i][i+1], c_i = P[i][i+2].
-    double c_m2 = 0, c_m1 = 0, b_m1 = 0, d_m1 = 1, d_m2 = 1, e_m1 = 0, z_m1 = 0, z_m2 = 0;
-    for (int i = 0; i < T; ++i) {
-        if (i + 1 < T) {
-            load(i + 1, pn, bn);
-        } else {
+    fetch(0);
+    for (int i0 = 0; i0 < T; i0 += PF) {
+        double ca[PF], cb[PF], cc[PF], cr[PF];
 #pragma unroll
-            for (int w = 0; w < 3; ++w) { pn[w] = 0.0; bn[w] = 0.0; }
+        for (int q = 0; q < PF; ++q) { ca[q] = na[q]; cb[q] = nb[q]; cc[q] = nc[q]; cr[q] = nr[q]; }
+        if (i0 + PF < T) fetch(i0 + PF);
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            if (i0 + q < T) {
+                const double f = c_m2 * r_m2;
+                const double e = (b_m1 - f * e_m1) * r_m1;
+                const double r = rsqrt(ca[q] - f * f - e * e);
+                const double z = (cr[q] - e * z_m1 - f * z_m2) * r;
+                const size_t o = (size_t)(i0 + q) * sd;
+                pa[o] = r; pb[o] = e; pcc[o] = f; pr[o] = z;
+                c_m2 = c_m1; c_m1 = cc[q]; b_m1 = cb[q];
+                r_m2 = r_m1; r_m1 = r; e_m1 = e;
+                z_m2 = z_m1; z_m1 = z;
+            }
         }
-        double a_i = 0.0, b_i = 0.0, c_i = 0.0, rhs = 0.0;
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            const double cm = win.c[w][0], c0 = win.c[w][1], cp = win.c[w][2];
-            a_i += cp * cp * pm[w] + c0 * c0 * pc[w] + cm * cm * pn[w];
-            rhs += cp * bm[w] + c0 * bc[w] + cm * bn[w];
-            b_i += c0 * cp * pc[w] + cm * c0 * pn[w];
-            c_i += cm * cp * pn[w];
-        }
-        const double f = (i >= 2) ? c_m2 / d_m2 : 0.0;
-        const double e = (i >= 1) ? (b_m1 - f * e_m1) / d_m1 : 0.0;
-        const double dg = sqrt(a_i - f * f - e * e);
-        const double z = (rhs - e * z_m1 - f * z_m2) / dg;
-        const size_t idx = (size_t)(t0 + i) * sd + d;
-        l0[idx] = dg; l1[idx] = e; l2[idx] = f; zz[idx] = z;
-        c_m2 = c_m1; c_m1 = c_i; b_m1 = b_i;
-        d_m2 = d_m1; d_m1 = dg; e_m1 = e;
-        z_m2 = z_m1; z_m1 = z;
-#pragma unroll
-        for (int w = 0; w < 3; ++w) { pm[w] = pc[w]; bm[w] = bc[w]; pc[w] = pn[w]; bc[w] = bn[w]; }
     }
-    // back substitution L^T y = z:  y_i = (z_i - e_{i+1} y_{i+1} - f_{i+2} y_{i+2}) / d_i
+    // back substitution L^T y = z
+    double* po = out + (size_t)t0 * sd + d;
     double y1 = 0, y2 = 0, e_n1 = 0, f_n1 = 0, f_n2 = 0;
-    for (int i = T - 1; i >= 0; --i) {
-        const size_t idx = (size_t)(t0 + i) * sd + d;
-        const double y = (zz[idx] - e_n1 * y1 - f_n2 * y2) / l0[idx];
-        out[idx] = y;
-        y2 = y1; y1 = y;
-        f_n2 = f_n1; f_n1 = l2[idx]; e_n1 = l1[idx];
+    auto fetch_back = [&](int i0) {      // steps i0, i0-1, ...
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            const int i = max(i0 - q, 0);
+            const size_t o = (size_t)i * sd;
+            na[q] = pa[o]; nb[q] = pb[o]; nc[q] = pcc[o]; nr[q] = pr[o];
+        }
+    };
+    fetch_back(T - 1);
+    for (int i0 = T - 1; i0 >= 0; i0 -= PF) {
+        double ca[PF], cb[PF], cc[PF], cr[PF];
+#pragma unroll
+        for (int q = 0; q < PF; ++q) { ca[q] = na[q]; cb[q] = nb[q]; cc[q] = nc[q]; cr[q] = nr[q]; }
+        if (i0 - PF >= 0) fetch_back(i0 - PF);
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            if (i0 - q >= 0) {
+                const double y = (cr[q] - e_n1 * y1 - f_n2 * y2) * ca[q];
+                po[(size_t)(i0 - q) * sd] = y;
+                y2 = y1; y1 = y;
+                f_n2 = f_n1; f_n1 = cc[q]; e_n1 = cb[q];
+            }
+        }
     }
 }
 
@@ -344,6 +412,7 @@ struct ConvertWorkspace {
     int* order;       // total
     double* E;
     double* band;
+    unsigned char* flags;
     size_t bytes;
 };
 
@@ -358,6 +427,7 @@ static ConvertWorkspace carve_convert(long long total, int K, int Dh, int sd, vo
     w.order = c.take<int>((size_t)total);
     w.E = c.take<double>((size_t)total * Dh);
     w.band = c.take<double>(4 * (size_t)total * sd);
+    w.flags = c.take<unsigned char>((size_t)total);
     w.bytes = align_up(c.used, 256);
     return w;
 }
@@ -480,9 +550,16 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
     }
     {
         Windows win = {{{0.0, 1.0, 0.0}, {-0.5, 0.0, 0.5}, {1.0, -2.0, 1.0}}};
+        KW_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)total, st));
+        convert_flags_kernel<<<(n_utts + 127) / 128, 128, 0, st>>>(n_utts, off_dev, w.flags);
+        KW_CUDA_CHECK(cudaGetLastError());
+        const long long cells = total * sd;
+        convert_band_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(
+            total, sd, Dh, w.E, w.mix, v.var, w.flags, win, w.band);
+        KW_CUDA_CHECK(cudaGetLastError());
         const long long threads = (long long)n_utts * sd;
         convert_mlpg_kernel<<<(unsigned)((threads + 95) / 96), 96, 0, st>>>(
-            n_utts, off_dev, sd, Dh, w.E, w.mix, v.var, win, w.band, total, out_dev);
+            n_utts, off_dev, sd, w.band, total, out_dev);
         KW_CUDA_CHECK(cudaGetLastError());
     }
     if (mix_dev != nullptr)

@@ -241,46 +241,82 @@ __host__ __device__ inline size_t bmat_elems(int DP) { return btri_off(DP, DP / 
 // ------------------------------------------------------------------------------------------
 // Column statistics of X: partial sums / min / max per chunk, then centre and power-of-two scale.
 // ------------------------------------------------------------------------------------------
-__global__ void colstats_partial_kernel(long long N, int D, const double* __restrict__ X,
-                                        double* __restrict__ partial, long long frames_per_chunk) {
+// grid = chunks of frames, 256 threads = 8 row workers x 32 column lanes (D <= 160).
+__global__ void __launch_bounds__(256)
+colstats_partial_kernel(long long N, int D, const double* __restrict__ X,
+                        double* __restrict__ partial, long long frames_per_chunk) {
+    __shared__ double red[3][8][160];
     const long long n0 = (long long)blockIdx.x * frames_per_chunk;
     const long long n1 = min(N, n0 + frames_per_chunk);
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        double s = 0.0, mn = CUDART_INF, mx = -CUDART_INF;
-        for (long long n = n0; n < n1; ++n) {
-            const double v = X[n * D + d];
-            s += v;
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
+    const int lane = threadIdx.x & 31, rw = threadIdx.x >> 5;
+    double s[5], mn[5], mx[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { s[q] = 0.0; mn[q] = CUDART_INF; mx[q] = -CUDART_INF; }
+    for (long long n = n0 + rw; n < n1; n += 8) {
+        const double* row = X + n * D;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int d = lane + 32 * q;
+            if (d < D) {
+                const double v = row[d];
+                s[q] += v;
+                mn[q] = fmin(mn[q], v);
+                mx[q] = fmax(mx[q], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int d = lane + 32 * q;
+        red[0][rw][d] = s[q];
+        red[1][rw][d] = mn[q];
+        red[2][rw][d] = mx[q];
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += 256) {
+        double ts = 0.0, tmn = CUDART_INF, tmx = -CUDART_INF;
+        for (int r = 0; r < 8; ++r) {      // fixed order
+            ts += red[0][r][d];
+            tmn = fmin(tmn, red[1][r][d]);
+            tmx = fmax(tmx, red[2][r][d]);
         }
         double* p = partial + (size_t)blockIdx.x * 3 * D;
-        p[d] = s;
-        p[D + d] = mn;
-        p[2 * D + d] = mx;
+        p[d] = ts;
+        p[D + d] = tmn;
+        p[2 * D + d] = tmx;
     }
 }
-// xinfo: [centre (DP) | sigma = 2^e (DP)]
-__global__ void colstats_final_kernel(long long N, int D, int DP, int chunks,
-                                      const double* __restrict__ partial,
-                                      double* __restrict__ xinfo) {
-    for (int d = threadIdx.x; d < DP; d += blockDim.x) {
-        double c = 0.0, sigma = 1.0;
-        if (d < D) {
-            double s = 0.0, mn = CUDART_INF, mx = -CUDART_INF;
-            for (int q = 0; q < chunks; ++q) {
-                const double* p = partial + (size_t)q * 3 * D;
-                s += p[d];
-                mn = fmin(mn, p[D + d]);
-                mx = fmax(mx, p[2 * D + d]);
-            }
-            c = s / (double)N;
-            const double amax = fmax(mx - c, c - mn);
-            if (amax > 0.0 && isfinite(amax)) {
-                int e;
-                frexp(amax, &e);        // amax = m * 2^e, m in [0.5, 1)  ->  amax < 2^e
-                sigma = ldexp(1.0, e);
-            }
+// xinfo: [centre (DP) | sigma = 2^e (DP)];  one warp per column, 8 columns per CTA
+__global__ void __launch_bounds__(256)
+colstats_final_kernel(long long N, int D, int DP, int chunks, const double* __restrict__ partial,
+                      double* __restrict__ xinfo) {
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (d >= DP) return;
+    double c = 0.0, sigma = 1.0;
+    if (d < D) {
+        double s = 0.0, mn = CUDART_INF, mx = -CUDART_INF;
+        for (int q = lane; q < chunks; q += 32) {
+            const double* p = partial + (size_t)q * 3 * D;
+            s += p[d];
+            mn = fmin(mn, p[D + d]);
+            mx = fmax(mx, p[2 * D + d]);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        c = s / (double)N;
+        const double amax = fmax(mx - c, c - mn);
+        if (amax > 0.0 && isfinite(amax)) {
+            int e;
+            frexp(amax, &e);        // amax = m * 2^e, m in [0.5, 1)  ->  amax < 2^e
+            sigma = ldexp(1.0, e);
+        }
+    }
+    if (lane == 0) {
         xinfo[d] = c;
         xinfo[DP + d] = sigma;
     }
@@ -1353,7 +1389,7 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, const double* __rest
 
 }  // namespace tc
 
-constexpr int TC_STAT_CHUNKS = 296;
+constexpr int TC_STAT_CHUNKS = 1184;
 
 struct TcWorkspace {
     double* colpartial;
@@ -1450,9 +1486,10 @@ int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
     const int DP = tc_dp(D);
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
     const long long fpc = (N + TC_STAT_CHUNKS - 1) / TC_STAT_CHUNKS;
-    tc::colstats_partial_kernel<<<TC_STAT_CHUNKS, 160, 0, st>>>(N, D, X, w.colpartial, fpc);
+    tc::colstats_partial_kernel<<<TC_STAT_CHUNKS, 256, 0, st>>>(N, D, X, w.colpartial, fpc);
     KW_CUDA_CHECK(cudaGetLastError());
-    tc::colstats_final_kernel<<<1, 160, 0, st>>>(N, D, DP, TC_STAT_CHUNKS, w.colpartial, w.xinfo);
+    tc::colstats_final_kernel<<<(DP + 7) / 8, 256, 0, st>>>(N, D, DP, TC_STAT_CHUNKS, w.colpartial,
+                                                            w.xinfo);
     KW_CUDA_CHECK(cudaGetLastError());
     tc::pack_x_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(N, D, DP, X, w.xinfo, w.xt);
     KW_CUDA_CHECK(cudaGetLastError());
