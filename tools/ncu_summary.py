@@ -17,7 +17,14 @@ WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'sm__cycles_elapsed.avg', 'smsp__cycles_active.avg',
+        'smsp__average_warp_latency_per_inst_issued.ratio']
 
 
 def main(path):
