@@ -105,6 +105,8 @@ def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None):
             raise ValueError('second dimension of x and y must be the same')
         if len(x) == 0 or len(y) == 0:
             raise ValueError('x and y must not be empty')
+    if any(x.shape[1] != xs[0].shape[1] for x in xs):
+        raise ValueError('all pairs of a batch must have the same number of features')
     _norm_from_dist(dist, 2)
     dev = torch.device('cuda' if device is None else device)
     tx = np.array([len(x) for x in xs], dtype=np.int32)

@@ -156,3 +156,49 @@ def test_fp32_distance_mode_cost_within_1e6(cuda):
         assert abs(local.sum() - c0) <= 1e-6 * c0
         same += int(p0.shape == p1.shape and np.array_equal(p0, p1))
     assert same >= 4       # identical paths except on near-ties
+
+
+def _plateau_pair(rng, tx, ty, f, jump_x, jump_y):
+    """Two step-like sequences whose steps sit at very different places: the optimal path has
+    long horizontal / vertical runs, so the windows of the finer levels are far wider than
+    8 radius + 2 (wider than the stored distance slice: exercises the in-place distance path)."""
+    x = np.where(np.arange(tx)[:, None] < jump_x, 0.0, 4.0) + 0.01 * rng.standard_normal((tx, f))
+    y = np.where(np.arange(ty)[:, None] < jump_y, 0.0, 4.0) + 0.01 * rng.standard_normal((ty, f))
+    return x, y
+
+
+@pytest.mark.parametrize('radius', [1, 3])
+def test_wide_windows_overflow_the_distance_slice(cuda, radius):
+    rng = np.random.default_rng(40 + radius)
+    pairs = [_plateau_pair(rng, 600, 640, 3, 60, 560), _plateau_pair(rng, 513, 300, 3, 450, 30),
+             _plateau_pair(rng, 257, 700, 3, 128, 650), _rand_pair(rng, 333, 444, 3)]
+    got = kfd.fastdtw_batch(pairs, radius=radius, dist=2)
+    widest = 0
+    for (x, y), (cost, path) in zip(pairs, got):
+        ecost, epath, ecells = dtw_c.fastdtw(x, y, radius=radius, dist=2, use_fma=True,
+                                             return_cells=True)
+        assert np.array_equal(path, epath)
+        assert cost == ecost
+        # the longest run of the path in one row bounds the window width from below
+        runs = np.bincount(path[:, 0])
+        widest = max(widest, int(runs.max()))
+    assert widest > max(64, 12 * radius + 16)      # the slice capacity really was exceeded
+
+
+@pytest.mark.parametrize('tx,ty', [(63, 64), (64, 65), (65, 129), (127, 128), (128, 64), (191, 257)])
+def test_strip_boundaries_of_the_banded_sweep(cuda, tx, ty):
+    """Lengths around the 64-row strips / 16-column back-pointer groups of the banded sweep."""
+    rng = np.random.default_rng(tx * 1000 + ty)
+    pairs = [_rand_pair(rng, tx, ty, 5), _rand_pair(rng, ty, tx, 5)]
+    _check(pairs, 2)
+    _check(pairs, 7)
+    got = kfd.fastdtw_batch(pairs, radius=2, dist=2, precision=1)
+    for (x, y), (cost, path) in zip(pairs, got):
+        ecost, _ = dtw_c.fastdtw(x, y, radius=2, dist=2, use_fma=True)
+        assert abs(cost - ecost) <= 1e-6 * abs(ecost)
+
+
+def test_batch_rejects_mixed_feature_dims(cuda):
+    rng = np.random.default_rng(3)
+    with pytest.raises(ValueError, match='same number of features'):
+        kfd.fastdtw_batch([_rand_pair(rng, 10, 12, 3), _rand_pair(rng, 10, 12, 2)], radius=1, dist=2)
