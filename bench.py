@@ -551,6 +551,8 @@ def main():
     ap.add_argument('--utts', type=int, default=N_UTTS, help='conversion utterances per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner / debug output on stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     if args.impl == 'reference':
         run_reference(args)
     else:
