@@ -437,7 +437,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
 // cells and the x rows are shared-memory broadcasts.  Also records each row pair's window and
 // counts the level's cells.  grid (n_pairs, ceil(row pairs / 8)), 256 threads.
 // ---------------------------------------------------------------------------------------
-template <int FP, int P, typename T>
+template <int FP, int P, typename T, bool FULLF>
 __global__ void __launch_bounds__(256)
 dtw_dist_kernel(const PairDesc* __restrict__ descs, int level, int radius, int F, int wcap,
                 const double* __restrict__ xpyr, const double* __restrict__ ypyr,
@@ -489,7 +489,7 @@ dtw_dist_kernel(const PairDesc* __restrict__ descs, int level, int radius, int F
         for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = (T)0;
 #pragma unroll
         for (int k = 0; k < FP; ++k) {
-            if (k < F) {
+            if (FULLF || k < F) {       // FULLF: F == FP, no per-coefficient test in the loop
                 const T yv = (T)__ldg(yT + (size_t)k * ty + j);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -876,8 +876,12 @@ template <int FP, int P, typename T>
 static int launch_dist(int n_pairs, const DtwWorkspace& w, int level, int radius, int F, int wcap,
                        int max_tx, unsigned long long* cells, cudaStream_t st) {
     const int rp_blocks = ((max_tx + 1) / 2 + 7) / 8;
-    dtw_dist_kernel<FP, P, T><<<dim3(n_pairs, rp_blocks), 256, 0, st>>>(
-        w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.win, w.dist, cells);
+    if (F == FP)
+        dtw_dist_kernel<FP, P, T, true><<<dim3(n_pairs, rp_blocks), 256, 0, st>>>(
+            w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.win, w.dist, cells);
+    else
+        dtw_dist_kernel<FP, P, T, false><<<dim3(n_pairs, rp_blocks), 256, 0, st>>>(
+            w.descs, level, radius, F, wcap, w.xpyr, w.ypyr, w.rowj, w.win, w.dist, cells);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
