@@ -664,7 +664,13 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
                 if (part > 0) qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
                 const long long e3 = tick<PROF>();
-                asm volatile("bar.sync 3, 512;" ::: "memory");
+                // parts 1..3 only signal that their partial sums are in shared memory; part 0
+                // waits for them.  (They cannot run more than one component ahead: barrier 1
+                // of the next component needs part 0, and qpart is double-buffered.)
+                if (part == 0)
+                    asm volatile("bar.sync 3, 512;" ::: "memory");
+                else
+                    asm volatile("bar.arrive 3, 512;" ::: "memory");
                 q_work += e3 - e2; q_bar += tick<PROF>() - e3;
                 if (part == 0) {
                     q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
