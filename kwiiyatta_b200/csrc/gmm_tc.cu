@@ -236,7 +236,11 @@ __host__ __device__ inline size_t btri_off(int DP, int ks) {
     const int ng = DP / 8;
     return (size_t)128 * (size_t)(ng * ks - ks * (ks - 1));
 }
-__host__ __device__ inline size_t bmat_elems(int DP) { return btri_off(DP, DP / 16); }
+// After the triangular blocks comes one more 16-deep block over ALL column groups: the bias row.
+// Its first K index multiplies the column of ones of the packed frames (index DP), so the MMA
+// itself subtracts b'_j = sum_d (mu_d - c_d) L[d][j]; the other 15 K indices are zero.
+__host__ __device__ inline size_t bbias_off(int DP) { return btri_off(DP, DP / 16); }
+__host__ __device__ inline size_t bmat_elems(int DP) { return bbias_off(DP) + (size_t)DP * 16; }
 
 // ------------------------------------------------------------------------------------------
 // Column statistics of X: partial sums / min / max per chunk, then centre and power-of-two scale.
@@ -353,19 +357,24 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
     }
 }
 
-// One CTA per component: B[j][d] = sigma_d L[d][j] 2^-t_j (split), column scale 2^t_j and
-// b'_j = sum_d (mu_d - c_d) L[d][j], plus [log|L|, log w] from aux.
+// One CTA per component: B[j][d] = sigma_d L[d][j] 2^-t (split), the bias row -b'_j 2^-t with
+// b'_j = sum_d (mu_d - c_d) L[d][j], and cst = [log|L|, log w, 4^t].  ONE power-of-two scale per
+// component: the frames are standardised (|x'| <= 1), so a column of L whose entries are small
+// next to the largest one also contributes little to q = |y|^2, and the absolute error bound is
+// what matters; with a common scale (and the bias inside the MMA) the epilogue is just
+// q = 4^t sum_j acc_j^2, with no per-column vectors to fetch.
 __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ means,
                               const double* __restrict__ prec_chol, const double* __restrict__ aux,
                               const double* __restrict__ xinfo, __half* __restrict__ bt,
-                              float* __restrict__ sc, double* __restrict__ cst) {
-    extern __shared__ double colinv[];  // DP: 2^-t_j
+                              double* __restrict__ cst) {
+    extern __shared__ double bpv[];      // DP: b'_j
+    __shared__ double red[256];
     const int k = blockIdx.x;
     const double* L = prec_chol + (size_t)k * D * D;
     const double* mu = means + (size_t)k * D;
-    float* sck = sc + (size_t)k * 3 * DP;
+    double amax = 0.0;
     for (int j = threadIdx.x; j < DP; j += blockDim.x) {
-        double amax = 0.0, bp = 0.0;
+        double bp = 0.0;
         if (j < D) {
             for (int d = 0; d <= j; ++d) {
                 const double l = L[(size_t)d * D + j];
@@ -373,22 +382,28 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
                 bp = fma(mu[d] - xinfo[d], l, bp);
             }
         }
-        double scale = 1.0;
-        if (amax > 0.0 && isfinite(amax)) {
-            int e;
-            frexp(amax, &e);
-            scale = ldexp(1.0, e);
-        }
-        colinv[j] = 1.0 / scale;
-        sck[j] = (float)scale;
-        sck[DP + j] = -(float)bp;                                  // -b' (hi)
-        sck[2 * DP + j] = -(float)(bp - (double)(float)bp);        // -b' (lo)
+        bpv[j] = bp;
+        amax = fmax(amax, fabs(bp));
     }
-    if (threadIdx.x == 0) {
-        cst[2 * k] = aux[(size_t)k * (D + 2) + D];
-        cst[2 * k + 1] = aux[(size_t)k * (D + 2) + D + 1];
-    }
+    red[threadIdx.x] = amax;
     __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    amax = red[0];
+    double scale = 1.0;
+    if (amax > 0.0 && isfinite(amax)) {
+        int e;
+        frexp(amax, &e);
+        scale = ldexp(1.0, e);
+    }
+    const double inv = 1.0 / scale;
+    if (threadIdx.x == 0) {
+        cst[3 * k] = aux[(size_t)k * (D + 2) + D];
+        cst[3 * k + 1] = aux[(size_t)k * (D + 2) + D + 1];
+        cst[3 * k + 2] = scale * scale;
+    }
     __half* hi = bt + (size_t)k * 2 * bmat_elems(DP);
     __half* lo = hi + bmat_elems(DP);
     for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
@@ -396,9 +411,16 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
         const int ks = d >> 4, jg = j >> 3;
         if (jg < 2 * ks) continue;             // structurally zero block: not stored
         double v = 0.0;
-        if (j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * colinv[j];
+        if (j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * inv;
         const size_t o = btri_off(DP, ks) + ((size_t)(jg - 2 * ks) * 2 + ((d >> 3) & 1)) * 64 +
                          (j & 7) * 8 + (d & 7);
+        split_store(v, hi + o, lo + o);
+    }
+    for (int e = threadIdx.x; e < DP * 16; e += blockDim.x) {
+        const int j = e >> 4, dd = e & 15, jg = j >> 3;
+        const double v = (dd == 0) ? -bpv[j] * inv : 0.0;
+        const size_t o = bbias_off(DP) + ((size_t)jg * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 +
+                         (dd & 7);
         split_store(v, hi + o, lo + o);
     }
 }
@@ -416,8 +438,8 @@ __host__ __device__ inline EstepSmem estep_smem(int DP) {
     s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
     s.b_hi = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
     s.b_lo = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
-    s.scl = o;   o += 2u * 3 * DP * 4;                 // two stages of [scale | b' hi | b' lo]
-    s.cst = o;   o += 2u * 2 * 8;
+    s.scl = o;                                          // (unused)
+    s.cst = o;   o += 2u * 4 * 8;                      // two stages of [log|L|, log w, 4^t, -]
     s.qpart = o; o += 3u * 2 * TILE_M * 8;
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
@@ -433,7 +455,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(576, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
-                const float* __restrict__ sc, const double* __restrict__ cst,
+                const double* __restrict__ cst,
                 double* __restrict__ wlpT, int mode, int32_t* __restrict__ mix,
                 int32_t* __restrict__ cand, double near_tie,
                 unsigned long long* __restrict__ prof) {
@@ -443,7 +465,6 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     __half* a_lo = a_hi + tile_elems(DP);
     __half* b_hi0 = reinterpret_cast<__half*>(smem + L.b_hi);
     __half* b_lo = reinterpret_cast<__half*>(smem + L.b_lo);
-    float* scl = reinterpret_cast<float*>(smem + L.scl);
     double* cst_s = reinterpret_cast<double*>(smem + L.cst);
     double* qpart = reinterpret_cast<double*>(smem + L.qpart);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -509,7 +530,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             long long p_tm = 0, p_blo = 0, p_bhi = 0, p_issue = 0;
             const long long p_start = tick<PROF>();
             const uint32_t ta_hi = tmem_base + 2u * (uint32_t)DP;       // A (hi) after the accumulators
-            const uint32_t ta_lo = ta_hi + (uint32_t)DP / 2;
+            const uint32_t ta_lo = ta_hi + (uint32_t)DP / 2 + 8;        // hi has the ones k-step too
+            const uint64_t bias_off = (uint64_t)(bbias_off(DP) * 2) >> 4;   // descriptor address units
             // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
             //   N = DP - 16 ks, B block at btri_off(ks), accumulator columns from 16 ks.
             const uint32_t ng = (uint32_t)DP / 8;
@@ -529,6 +551,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             tmem_cp_128x256b(ta_hi + 8 * ks, d_a_hi + ks * KSTEP);
                             tmem_cp_128x256b(ta_lo + 8 * ks, d_a_lo + ks * KSTEP);
                         }
+                        // the k-step that holds the column of ones (its lo part is zero)
+                        tmem_cp_128x256b(ta_hi + 8 * (uint32_t)ksteps, d_a_hi + (uint64_t)ksteps * KSTEP);
                         umma_commit(bars + BAR_A_EMPTY);
                     }
                     const long long c0 = tick<PROF>();
@@ -547,6 +571,9 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             cols -= 16;
                             id = make_idesc(TILE_M, (int)cols);
                         }
+                        // 1 . (-b'_lo): the bias row, every column
+                        umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps,
+                                    (s ? d_b_lo1 : d_b_lo0) + bias_off, idesc, 1u);
                     }
                     umma_commit(bars + BAR_BLO_EMPTY0 + s);
                     const long long c3 = tick<PROF>();
@@ -574,6 +601,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db,
                                         make_idesc(TILE_M, (int)cols), 1u);
                         }
+                        // 1 . (-b'_hi)
+                        umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps, d_b_hi + bias_off, idesc, 1u);
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
                     umma_commit(bars + BAR_TM_FULL0 + s);
@@ -607,18 +636,14 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
             // per-component epilogue constants, prefetched one component ahead
-            float pre = 0.f;
             double pre_c = 0.0;
             auto fetch = [&](int k) {
-                pre = (et < 3 * DP) ? sc[(size_t)k * 3 * DP + et] : 0.f;
-                if (et < 2) pre_c = cst[2 * k + et];
+                if (et < 3) pre_c = cst[3 * k + et];
             };
             fetch(0);
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                float* sk = scl + (size_t)s * 3 * DP;
-                if (et < 3 * DP) sk[et] = pre;
-                if (et < 2) cst_s[s * 2 + et] = pre_c;
+                if (et < 3) cst_s[s * 4 + et] = pre_c;
                 if (k + 1 < K) fetch(k + 1);
                 const long long e0 = tick<PROF>();
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -638,24 +663,13 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
 #pragma unroll
                 for (int h = 0; h < 3; ++h) {
                     if (c_begin + h >= c_end) break;
-                    const float* sc_p = sk + (c_begin + h) * 16;
-                    // packed fp32x2: y = acc * 2^t - b'_hi - b'_lo,  part += y * y
+                    // the accumulator IS y / 2^t (scale and bias are inside the MMA): sum squares
                     float2 p2 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 cs = *reinterpret_cast<const float4*>(sc_p + 4 * j4);
-                        const float4 nbh = *reinterpret_cast<const float4*>(sc_p + DP + 4 * j4);
-                        const float4 nbl = *reinterpret_cast<const float4*>(sc_p + 2 * DP + 4 * j4);
-                        float2 ya = __ffma2_rn(make_float2(__uint_as_float(v[h][4 * j4 + 0]),
-                                                           __uint_as_float(v[h][4 * j4 + 1])),
-                                               make_float2(cs.x, cs.y), make_float2(nbh.x, nbh.y));
-                        float2 yb = __ffma2_rn(make_float2(__uint_as_float(v[h][4 * j4 + 2]),
-                                                           __uint_as_float(v[h][4 * j4 + 3])),
-                                               make_float2(cs.z, cs.w), make_float2(nbh.z, nbh.w));
-                        ya = __fadd2_rn(ya, make_float2(nbl.x, nbl.y));
-                        yb = __fadd2_rn(yb, make_float2(nbl.z, nbl.w));
+                    for (int j2 = 0; j2 < 8; ++j2) {
+                        const float2 ya = make_float2(__uint_as_float(v[h][2 * j2]),
+                                                      __uint_as_float(v[h][2 * j2 + 1]));
                         p2 = __ffma2_rn(ya, ya, p2);
-                        p2 = __ffma2_rn(yb, yb, p2);
                     }
                     q += (double)(p2.x + p2.y);
                 }
@@ -676,7 +690,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                     q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
                          qpart[(2 * 2 + s) * TILE_M + row];
                     const double wlp =
-                        (-0.5 * ((double)D * LOG2PI + q) + cst_s[s * 2]) + cst_s[s * 2 + 1];
+                        (-0.5 * ((double)D * LOG2PI + q * cst_s[s * 4 + 2]) + cst_s[s * 4]) +
+                        cst_s[s * 4 + 1];
                     if (mode == 0) {
                         if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
                     } else if (wlp > v1) {
@@ -1455,7 +1470,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.xt = c.take<__half>((size_t)n_tiles * tc::X_PARTS * tc::tile_elems(DP));
     w.bt = c.take<__half>((size_t)K * 2 * tc::bmat_elems(DP));
     w.sc = c.take<float>((size_t)K * 3 * DP);
-    w.cst = c.take<double>(2 * (size_t)K);
+    w.cst = c.take<double>(3 * (size_t)K);
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
     w.cand = c.take<int32_t>((size_t)N);
     w.mu32 = c.take<float>((size_t)K * G.DA);
@@ -1515,7 +1530,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
     const long long Npad = resp_pad(N);
     tc::pack_l_kernel<<<K, 256, sizeof(double) * DP, st>>>(K, D, DP, means, pc, aux, w.xinfo,
-                                                          w.bt, w.sc, w.cst);
+                                                          w.bt, w.cst);
     KW_CUDA_CHECK(cudaGetLastError());
     const int sms = device_sms();
     const tc::EstepSmem L = tc::estep_smem(DP);
@@ -1524,7 +1539,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     uint32_t cols = 32;
-    while (cols < 3u * DP) cols <<= 1;      // two accumulator stages + the frame tile (hi, lo)
+    while (cols < 3u * DP + 16) cols <<= 1;  // two accumulator stages + the frame tile (hi+ones, lo)
     const int grid = (int)std::min<long long>(n_tiles, sms);
     static unsigned long long* prof_dev = nullptr;
     static int prof_on = -1;
@@ -1534,11 +1549,11 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     }
     if (prof_on)
         tc::estep_tc_kernel<true><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
-                                                              w.xt, w.bt, w.sc, w.cst, resp, mode,
+                                                              w.xt, w.bt, w.cst, resp, mode,
                                                               mix, w.cand, 0.05, prof_dev);
     else
         tc::estep_tc_kernel<false><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
-                                                               w.xt, w.bt, w.sc, w.cst, resp, mode,
+                                                               w.xt, w.bt, w.cst, resp, mode,
                                                                mix, w.cand, 0.05, nullptr);
     if (prof_on) {
         unsigned long long h[16];
