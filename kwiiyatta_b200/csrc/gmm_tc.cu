@@ -635,18 +635,22 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const long long n = (long long)tile * TILE_M + row;
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
-            // per-component epilogue constants, prefetched one component ahead
-            double pre_c = 0.0;
+            // per-component constants [log|L|, log w, 4^t] (part 0 finishes the component),
+            // prefetched one component ahead
+            double c_ld = 0.0, c_lw = 0.0, c_s2 = 0.0, n_ld = 0.0, n_lw = 0.0, n_s2 = 0.0;
             auto fetch = [&](int k) {
-                if (et < 3) pre_c = cst[3 * k + et];
+                if (part == 0) {
+                    n_ld = cst[3 * k];
+                    n_lw = cst[3 * k + 1];
+                    n_s2 = cst[3 * k + 2];
+                }
             };
             fetch(0);
             for (int k = 0; k < K; ++k) {
                 const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                if (et < 3) cst_s[s * 4 + et] = pre_c;
+                c_ld = n_ld; c_lw = n_lw; c_s2 = n_s2;
                 if (k + 1 < K) fetch(k + 1);
                 const long long e0 = tick<PROF>();
-                asm volatile("bar.sync 1, 512;" ::: "memory");
                 const long long e1 = tick<PROF>();
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
                 const long long e2 = tick<PROF>();
@@ -675,23 +679,31 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                if (part > 0) qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
+                if (part > 0) {
+                    if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
+                    qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
+                }
                 const long long e3 = tick<PROF>();
-                // parts 1..3 only signal that their partial sums are in shared memory; part 0
-                // waits for them.  (They cannot run more than one component ahead: barrier 1
-                // of the next component needs part 0, and qpart is double-buffered.)
-                if (part == 0)
-                    asm volatile("bar.sync 3, 512;" ::: "memory");
-                else
-                    asm volatile("bar.arrive 3, 512;" ::: "memory");
+                // The only CTA-level synchronisation of a component: parts 1..3 signal that their
+                // partial sums are in shared memory (named barrier 3 + stage, they do not wait),
+                // part 0 waits for them.  Part 0 frees the accumulator stage only AFTER it has
+                // read the partial sums: the MMAs of component g+2 (same stage) wait for that, so
+                // neither the partial sums nor the barrier of stage s are touched again before
+                // part 0 is done with component g.
+                if (part == 0) {
+                    if (s) asm volatile("bar.sync 4, 512;" ::: "memory");
+                    else asm volatile("bar.sync 3, 512;" ::: "memory");
+                } else {
+                    if (s) asm volatile("bar.arrive 4, 512;" ::: "memory");
+                    else asm volatile("bar.arrive 3, 512;" ::: "memory");
+                }
                 q_work += e3 - e2; q_bar += tick<PROF>() - e3;
                 if (part == 0) {
                     q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
                          qpart[(2 * 2 + s) * TILE_M + row];
-                    const double wlp =
-                        (-0.5 * ((double)D * LOG2PI + q * cst_s[s * 4 + 2]) + cst_s[s * 4]) +
-                        cst_s[s * 4 + 1];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
+                    const double wlp = (-0.5 * ((double)D * LOG2PI + q * c_s2) + c_ld) + c_lw;
                     if (mode == 0) {
                         if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
                     } else if (wlp > v1) {
