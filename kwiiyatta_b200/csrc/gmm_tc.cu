@@ -363,19 +363,25 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
 // next to the largest one also contributes little to q = |y|^2, and the absolute error bound is
 // what matters; with a common scale (and the bias inside the MMA) the epilogue is just
 // q = 4^t sum_j acc_j^2, with no per-column vectors to fetch.
-__global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ means,
+// G components share one B operand ("item"): their 8-row groups are interleaved (A g0, B g0,
+// A g1, ...), so one MMA of N = G (DP - 16 ks) computes the k-step for all of them and output
+// j of component c lands in accumulator column 8 G (j / 8) + 8 c + j % 8 whatever the k-step.
+// grid = G * ceil(K / G); components >= K are zero blocks.
+__global__ void pack_l_kernel(int K, int D, int DP, int G, const double* __restrict__ means,
                               const double* __restrict__ prec_chol, const double* __restrict__ aux,
                               const double* __restrict__ xinfo, __half* __restrict__ bt,
                               double* __restrict__ cst) {
     extern __shared__ double bpv[];      // DP: b'_j
     __shared__ double red[256];
     const int k = blockIdx.x;
-    const double* L = prec_chol + (size_t)k * D * D;
-    const double* mu = means + (size_t)k * D;
+    const int item = k / G, ci = k - item * G;
+    const bool real = k < K;
+    const double* L = prec_chol + (size_t)(real ? k : 0) * D * D;
+    const double* mu = means + (size_t)(real ? k : 0) * D;
     double amax = 0.0;
     for (int j = threadIdx.x; j < DP; j += blockDim.x) {
         double bp = 0.0;
-        if (j < D) {
+        if (j < D && real) {
             for (int d = 0; d <= j; ++d) {
                 const double l = L[(size_t)d * D + j];
                 amax = fmax(amax, fabs(l * xinfo[DP + d]));
@@ -399,28 +405,29 @@ __global__ void pack_l_kernel(int K, int D, int DP, const double* __restrict__ m
         scale = ldexp(1.0, e);
     }
     const double inv = 1.0 / scale;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && real) {
         cst[3 * k] = aux[(size_t)k * (D + 2) + D];
         cst[3 * k + 1] = aux[(size_t)k * (D + 2) + D + 1];
         cst[3 * k + 2] = scale * scale;
     }
-    __half* hi = bt + (size_t)k * 2 * bmat_elems(DP);
-    __half* lo = hi + bmat_elems(DP);
+    __half* hi = bt + (size_t)item * 2 * G * bmat_elems(DP);
+    __half* lo = hi + (size_t)G * bmat_elems(DP);
     for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
         const int j = e / DP, d = e - j * DP;
         const int ks = d >> 4, jg = j >> 3;
         if (jg < 2 * ks) continue;             // structurally zero block: not stored
         double v = 0.0;
-        if (j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * inv;
-        const size_t o = btri_off(DP, ks) + ((size_t)(jg - 2 * ks) * 2 + ((d >> 3) & 1)) * 64 +
+        if (real && j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * inv;
+        const size_t o = (size_t)G * btri_off(DP, ks) +
+                         ((size_t)(G * (jg - 2 * ks) + ci) * 2 + ((d >> 3) & 1)) * 64 +
                          (j & 7) * 8 + (d & 7);
         split_store(v, hi + o, lo + o);
     }
     for (int e = threadIdx.x; e < DP * 16; e += blockDim.x) {
         const int j = e >> 4, dd = e & 15, jg = j >> 3;
-        const double v = (dd == 0) ? -bpv[j] * inv : 0.0;
-        const size_t o = bbias_off(DP) + ((size_t)jg * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 +
-                         (dd & 7);
+        const double v = (dd == 0 && real) ? -bpv[j] * inv : 0.0;
+        const size_t o = (size_t)G * bbias_off(DP) +
+                         ((size_t)(G * jg + ci) * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 + (dd & 7);
         split_store(v, hi + o, lo + o);
     }
 }
@@ -432,15 +439,15 @@ struct EstepSmem {
     // byte offsets into dynamic shared memory
     uint32_t a, b_hi, b_lo, scl, cst, qpart, bars, tmem_ptr, total;
 };
-__host__ __device__ inline EstepSmem estep_smem(int DP) {
+__host__ __device__ inline EstepSmem estep_smem(int DP, int G) {
     EstepSmem s;
     uint32_t o = 0;
     s.a = o;     o += 2u * TILE_M * dpb_of(DP) * 2;    // hi then lo (scaled)
-    s.b_hi = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
-    s.b_lo = o;  o += 2u * (uint32_t)bmat_elems(DP) * 2;   // two stages
+    s.b_hi = o;  o += 2u * (uint32_t)(G * bmat_elems(DP)) * 2;   // two stages
+    s.b_lo = o;  o += 2u * (uint32_t)(G * bmat_elems(DP)) * 2;   // two stages
     s.scl = o;                                          // (unused)
     s.cst = o;   o += 2u * 4 * 8;                      // two stages of [log|L|, log w, 4^t, -]
-    s.qpart = o; o += 3u * 2 * TILE_M * 8;
+    s.qpart = o; o += 3u * 2 * TILE_M * 2 * 8;       // [part - 1][stage][row][component of the item]
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
     s.total = o;
@@ -451,7 +458,7 @@ enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_BLO_FULL0, BAR_BLO_FULL1, BAR_BLO_EMPTY0
        BAR_BHI_FULL0, BAR_BHI_FULL1,
        BAR_BHI_EMPTY0, BAR_BHI_EMPTY1, BAR_TM_FULL0, BAR_TM_FULL1, BAR_TM_EMPTY0, BAR_TM_EMPTY1 };
 
-template <bool PROF>
+template <bool PROF, int G>
 __global__ void __launch_bounds__(576, 1)
 estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
@@ -460,7 +467,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 int32_t* __restrict__ cand, double near_tie,
                 unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const EstepSmem L = estep_smem(DP);
+    const EstepSmem L = estep_smem(DP, G);
     __half* a_hi = reinterpret_cast<__half*>(smem + L.a);
     __half* a_lo = a_hi + tile_elems(DP);
     __half* b_hi0 = reinterpret_cast<__half*>(smem + L.b_hi);
@@ -473,11 +480,16 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     // warp index through a shuffle so the compiler knows the role branches are warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t a_bytes = 2u * TILE_M * dpb_of(DP) * 2;
-    const uint32_t b_bytes = (uint32_t)bmat_elems(DP) * 2;
+    // An item = G components sharing one B operand and one accumulator stage (G = 2 when two
+    // accumulators fit an MMA's N <= 256: halves the number of MMAs per component).
+    const int KI = (K + G - 1) / G;
+    const size_t item_elems = (size_t)G * bmat_elems(DP);
+    const uint32_t b_bytes = (uint32_t)item_elems * 2;
+    const uint32_t acc_w = (uint32_t)(G * DP);
     const uint32_t lbo = 128;
     const uint32_t sbo_a = (uint32_t)(dpb_of(DP) / 8) * 128;
     const int ksteps = DP / 16;
-    const uint32_t idesc = make_idesc(TILE_M, DP);
+    const uint32_t idesc = make_idesc(TILE_M, G * DP);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 14; ++i) mbar_init(bars + i, (i >= BAR_TM_EMPTY0) ? 16u : 1u);
@@ -494,16 +506,16 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                for (int k = 0; k < K; ++k) {
-                    const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                    const __half* bk = bt + (size_t)k * 2 * bmat_elems(DP);
+                for (int k = 0; k < KI; ++k) {
+                    const uint32_t g = (uint32_t)it * KI + k, s = g & 1u, u = g >> 1;
+                    const __half* bk = bt + (size_t)k * 2 * item_elems;
                     mbar_wait(bars + BAR_BLO_EMPTY0 + s, (u & 1u) ^ 1u);
                     mbar_expect_tx(bars + BAR_BLO_FULL0 + s, b_bytes);
-                    bulk_g2s(b_lo + (size_t)s * bmat_elems(DP), bk + bmat_elems(DP), b_bytes,
+                    bulk_g2s(b_lo + (size_t)s * item_elems, bk + item_elems, b_bytes,
                              bars + BAR_BLO_FULL0 + s);
                     mbar_wait(bars + BAR_BHI_EMPTY0 + s, (u & 1u) ^ 1u);
                     mbar_expect_tx(bars + BAR_BHI_FULL0 + s, b_bytes);
-                    bulk_g2s(b_hi0 + (size_t)s * bmat_elems(DP), bk, b_bytes,
+                    bulk_g2s(b_hi0 + (size_t)s * item_elems, bk, b_bytes,
                              bars + BAR_BHI_FULL0 + s);
                     if (k == 0) {
                         mbar_wait(bars + BAR_A_EMPTY, ((uint32_t)it & 1u) ^ 1u);
@@ -523,24 +535,25 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const uint64_t d_a_hi = make_desc(smem_u32(a_hi), lbo, sbo_a);
             const uint64_t d_a_lo = make_desc(smem_u32(a_lo), lbo, sbo_a);
             const uint64_t d_b_lo0 = make_desc(smem_u32(b_lo), 128, 256);
-            const uint64_t d_b_lo1 = make_desc(smem_u32(b_lo + bmat_elems(DP)), 128, 256);
+            const uint64_t d_b_lo1 = make_desc(smem_u32(b_lo + item_elems), 128, 256);
             const uint64_t d_b_hi0 = make_desc(smem_u32(b_hi0), 128, 256);
-            const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + bmat_elems(DP)), 128, 256);
+            const uint64_t d_b_hi1 = make_desc(smem_u32(b_hi0 + item_elems), 128, 256);
             constexpr uint64_t KSTEP = 256 >> 4;      // A: 16 fp16 along K = two core matrices
             long long p_tm = 0, p_blo = 0, p_bhi = 0, p_issue = 0;
             const long long p_start = tick<PROF>();
-            const uint32_t ta_hi = tmem_base + 2u * (uint32_t)DP;       // A (hi) after the accumulators
+            const uint32_t ta_hi = tmem_base + 2u * acc_w;              // A (hi) after the accumulators
             const uint32_t ta_lo = ta_hi + (uint32_t)DP / 2 + 8;        // hi has the ones k-step too
-            const uint64_t bias_off = (uint64_t)(bbias_off(DP) * 2) >> 4;   // descriptor address units
+            const uint64_t bias_off = (uint64_t)(G * bbias_off(DP) * 2) >> 4;   // descriptor address units
             // k-step ks touches output columns [16 ks, DP) only (L_k is triangular):
             //   N = DP - 16 ks, B block at btri_off(ks), accumulator columns from 16 ks.
             const uint32_t ng = (uint32_t)DP / 8;
+            const uint32_t Gu = (uint32_t)G;
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                for (int k = 0; k < K; ++k) {
-                    const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
+                for (int k = 0; k < KI; ++k) {
+                    const uint32_t g = (uint32_t)it * KI + k, s = g & 1u, u = g >> 1;
                     const uint64_t d_b_hi = s ? d_b_hi1 : d_b_hi0;
-                    const uint32_t acc = tmem_base + s * (uint32_t)DP;
+                    const uint32_t acc = tmem_base + s * acc_w;
                     if (k == 0) {
                         // stage the frame tile (hi and scaled lo) in tensor memory once per tile:
                         // every MMA of the tile then reads A from TMEM and shared-memory bandwidth
@@ -566,10 +579,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         uint64_t db = s ? d_b_lo1 : d_b_lo0;          // x_hi . l_lo
                         uint32_t id = idesc, cols = (uint32_t)DP;
                         for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
-                            umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db, id, ks > 0 ? 1u : 0u);
-                            db += (uint64_t)(ng - 2 * ks) * 16;      // next block: (ng-2ks)*256 B
+                            umma_f16_ts(acc + Gu * 16 * ks, ta_hi + 8 * ks, db, id, ks > 0 ? 1u : 0u);
+                            db += (uint64_t)(Gu * (ng - 2 * ks)) * 16;   // next block: G (ng-2ks) 256 B
                             cols -= 16;
-                            id = make_idesc(TILE_M, (int)cols);
+                            id = make_idesc(TILE_M, (int)(Gu * cols));
                         }
                         // 1 . (-b'_lo): the bias row, every column
                         umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps,
@@ -585,10 +598,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         uint64_t db = d_b_hi;          // x_lo . l_hi
                         uint32_t id = idesc, cols = (uint32_t)DP;
                         for (uint32_t ks = 0; ks < (uint32_t)ksteps; ++ks) {
-                            umma_f16_ts(acc + 16 * ks, ta_lo + 8 * ks, db, id, 1u);
-                            db += (uint64_t)(ng - 2 * ks) * 16;
+                            umma_f16_ts(acc + Gu * 16 * ks, ta_lo + 8 * ks, db, id, 1u);
+                            db += (uint64_t)(Gu * (ng - 2 * ks)) * 16;
                             cols -= 16;
-                            id = make_idesc(TILE_M, (int)cols);
+                            id = make_idesc(TILE_M, (int)(Gu * cols));
                         }
                     }
                     {
@@ -596,10 +609,10 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                         umma_f16_ts_scaled(acc, ta_hi, db, idesc);  // ks = 0 spans every column
                         uint32_t cols = (uint32_t)DP;
                         for (uint32_t ks = 1; ks < (uint32_t)ksteps; ++ks) {
-                            db += (uint64_t)(ng - 2 * (ks - 1)) * 16;
+                            db += (uint64_t)(Gu * (ng - 2 * (ks - 1))) * 16;
                             cols -= 16;
-                            umma_f16_ts(acc + 16 * ks, ta_hi + 8 * ks, db,
-                                        make_idesc(TILE_M, (int)cols), 1u);
+                            umma_f16_ts(acc + Gu * 16 * ks, ta_hi + 8 * ks, db,
+                                        make_idesc(TILE_M, (int)(Gu * cols)), 1u);
                         }
                         // 1 . (-b'_hi)
                         umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps, d_b_hi + bias_off, idesc, 1u);
@@ -626,7 +639,8 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
         const uint32_t quarter = (uint32_t)(warp & 3);
         const int part = (warp - 2) >> 2;           // 0..3
         const int row = (int)quarter * 32 + lane;   // TMEM lane = row of the tile
-        const int c_begin = (ksteps * part) / 4, c_end = (ksteps * (part + 1)) / 4;
+        const int n_chunks = G * ksteps;            // 16-column chunks of an accumulator stage
+        const int c_begin = (n_chunks * part) / 4, c_end = (n_chunks * (part + 1)) / 4;
         const double LOG2PI = 1.8378770664093453;
         long long q_bar = 0, q_wait = 0, q_work = 0;
         const long long q_start = tick<PROF>();
@@ -635,29 +649,37 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
             const long long n = (long long)tile * TILE_M + row;
             double v1 = -CUDART_INF, v2 = -CUDART_INF;
             int k1 = 0, k2 = -1;
-            // per-component constants [log|L|, log w, 4^t] (part 0 finishes the component),
-            // prefetched one component ahead
-            double c_ld = 0.0, c_lw = 0.0, c_s2 = 0.0, n_ld = 0.0, n_lw = 0.0, n_s2 = 0.0;
-            auto fetch = [&](int k) {
+            // per-component constants [log|L|, log w, 4^t] (part 0 finishes the item's
+            // components), prefetched one item ahead
+            double cc[2][3], nc[2][3];
+            auto fetch = [&](int item) {
                 if (part == 0) {
-                    n_ld = cst[3 * k];
-                    n_lw = cst[3 * k + 1];
-                    n_s2 = cst[3 * k + 2];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int k = min(item * G + c, K - 1);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) nc[c][e] = cst[3 * k + e];
+                    }
                 }
             };
             fetch(0);
-            for (int k = 0; k < K; ++k) {
-                const uint32_t g = (uint32_t)it * K + k, s = g & 1u, u = g >> 1;
-                c_ld = n_ld; c_lw = n_lw; c_s2 = n_s2;
-                if (k + 1 < K) fetch(k + 1);
+            for (int item = 0; item < KI; ++item) {
+                const uint32_t g = (uint32_t)it * KI + item, s = g & 1u, u = g >> 1;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) cc[c][e] = nc[c][e];
+                if (item + 1 < KI) fetch(item + 1);
                 const long long e0 = tick<PROF>();
                 const long long e1 = tick<PROF>();
                 mbar_wait(bars + BAR_TM_FULL0 + s, u & 1u);
                 const long long e2 = tick<PROF>();
                 q_bar += e1 - e0; q_wait += e2 - e1;
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * (uint32_t)DP;
-                double q = 0.0;
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + s * acc_w;
+                // with G = 2 a chunk holds 8 columns of the item's first component, then 8 of
+                // the second (interleaved row groups of the B operand)
+                double qa = 0.0, qb = 0.0;
                 // all TMEM loads of this thread's (at most 3) chunks are issued before one wait
                 uint32_t v[3][16];
 #pragma unroll
@@ -668,28 +690,38 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 for (int h = 0; h < 3; ++h) {
                     if (c_begin + h >= c_end) break;
                     // the accumulator IS y / 2^t (scale and bias are inside the MMA): sum squares
-                    float2 p2 = make_float2(0.f, 0.f);
+                    float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int j2 = 0; j2 < 8; ++j2) {
+                    for (int j2 = 0; j2 < 4; ++j2) {
                         const float2 ya = make_float2(__uint_as_float(v[h][2 * j2]),
                                                       __uint_as_float(v[h][2 * j2 + 1]));
-                        p2 = __ffma2_rn(ya, ya, p2);
+                        const float2 yb = make_float2(__uint_as_float(v[h][8 + 2 * j2]),
+                                                      __uint_as_float(v[h][8 + 2 * j2 + 1]));
+                        pa = __ffma2_rn(ya, ya, pa);
+                        pb = __ffma2_rn(yb, yb, pb);
                     }
-                    q += (double)(p2.x + p2.y);
+                    if (G == 2) {
+                        qa += (double)(pa.x + pa.y);
+                        qb += (double)(pb.x + pb.y);
+                    } else {
+                        qa += (double)((pa.x + pa.y) + (pb.x + pb.y));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (part > 0) {
                     if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                    qpart[((part - 1) * 2 + s) * TILE_M + row] = q;
+                    double* qp = qpart + ((size_t)((part - 1) * 2 + s) * TILE_M + row) * 2;
+                    qp[0] = qa;
+                    qp[1] = qb;
                 }
                 const long long e3 = tick<PROF>();
-                // The only CTA-level synchronisation of a component: parts 1..3 signal that their
+                // The only CTA-level synchronisation of an item: parts 1..3 signal that their
                 // partial sums are in shared memory (named barrier 3 + stage, they do not wait),
                 // part 0 waits for them.  Part 0 frees the accumulator stage only AFTER it has
-                // read the partial sums: the MMAs of component g+2 (same stage) wait for that, so
+                // read the partial sums: the MMAs of item g+2 (same stage) wait for that, so
                 // neither the partial sums nor the barrier of stage s are touched again before
-                // part 0 is done with component g.
+                // part 0 is done with item g.
                 if (part == 0) {
                     if (s) asm volatile("bar.sync 4, 512;" ::: "memory");
                     else asm volatile("bar.sync 3, 512;" ::: "memory");
@@ -699,17 +731,29 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 }
                 q_work += e3 - e2; q_bar += tick<PROF>() - e3;
                 if (part == 0) {
-                    q += qpart[(0 * 2 + s) * TILE_M + row] + qpart[(1 * 2 + s) * TILE_M + row] +
-                         qpart[(2 * 2 + s) * TILE_M + row];
+#pragma unroll
+                    for (int pp = 0; pp < 3; ++pp) {
+                        const double* qp = qpart + ((size_t)(pp * 2 + s) * TILE_M + row) * 2;
+                        qa += qp[0];
+                        qb += qp[1];
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                    const double wlp = (-0.5 * ((double)D * LOG2PI + q * c_s2) + c_ld) + c_lw;
-                    if (mode == 0) {
-                        if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
-                    } else if (wlp > v1) {
-                        v2 = v1; k2 = k1; v1 = wlp; k1 = k;
-                    } else if (wlp > v2) {
-                        v2 = wlp; k2 = k;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int k = item * G + c;
+                        if (c < G && k < K) {
+                            const double q = c ? qb : qa;
+                            const double wlp =
+                                (-0.5 * ((double)D * LOG2PI + q * cc[c][2]) + cc[c][0]) + cc[c][1];
+                            if (mode == 0) {
+                                if (n < N) wlpT[(size_t)k * Npad + n] = wlp;
+                            } else if (wlp > v1) {
+                                v2 = v1; k2 = k1; v1 = wlp; k1 = k;
+                            } else if (wlp > v2) {
+                                v2 = wlp; k2 = k;
+                            }
+                        }
                     }
                 }
             }
@@ -1480,7 +1524,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.colpartial = c.take<double>((size_t)TC_STAT_CHUNKS * 3 * D);
     w.xinfo = c.take<double>(2 * (size_t)DP);
     w.xt = c.take<__half>((size_t)n_tiles * tc::X_PARTS * tc::tile_elems(DP));
-    w.bt = c.take<__half>((size_t)K * 2 * tc::bmat_elems(DP));
+    w.bt = c.take<__half>((size_t)(K + 1) * 2 * tc::bmat_elems(DP));   // (+1: odd K padded to a pair)
     w.sc = c.take<float>((size_t)K * 3 * DP);
     w.cst = c.take<double>(3 * (size_t)K);
     w.lse_partial = c.take<double>((size_t)n_tiles + 1);
@@ -1541,17 +1585,16 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     const int DP = tc_dp(D);
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
     const long long Npad = resp_pad(N);
-    tc::pack_l_kernel<<<K, 256, sizeof(double) * DP, st>>>(K, D, DP, means, pc, aux, w.xinfo,
-                                                          w.bt, w.cst);
+    // two components per MMA when both accumulators fit N <= 256 and TMEM (DP <= 96)
+    const int G = (DP <= 96 && K >= 2) ? 2 : 1;
+    const int KI = (K + G - 1) / G;
+    tc::pack_l_kernel<<<KI * G, 256, sizeof(double) * DP, st>>>(K, D, DP, G, means, pc, aux,
+                                                                w.xinfo, w.bt, w.cst);
     KW_CUDA_CHECK(cudaGetLastError());
     const int sms = device_sms();
-    const tc::EstepSmem L = tc::estep_smem(DP);
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::estep_tc_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const tc::EstepSmem L = tc::estep_smem(DP, G);
     uint32_t cols = 32;
-    while (cols < 3u * DP + 16) cols <<= 1;  // two accumulator stages + the frame tile (hi+ones, lo)
+    while (cols < 2u * G * DP + DP + 16) cols <<= 1;  // two accumulator stages + the frame tile (hi+ones, lo)
     const int grid = (int)std::min<long long>(n_tiles, sms);
     static unsigned long long* prof_dev = nullptr;
     static int prof_on = -1;
@@ -1559,14 +1602,20 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
         prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
         if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
     }
+    auto launch = [&](auto kern, unsigned long long* pd) -> int {
+        KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)L.total));
+        kern<<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt, w.bt, w.cst,
+                                         resp, mode, mix, w.cand, 0.05, pd);
+        return KW_OK;
+    };
     if (prof_on)
-        tc::estep_tc_kernel<true><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
-                                                              w.xt, w.bt, w.cst, resp, mode,
-                                                              mix, w.cand, 0.05, prof_dev);
+        rc = (G == 2) ? launch(tc::estep_tc_kernel<true, 2>, prof_dev)
+                      : launch(tc::estep_tc_kernel<true, 1>, prof_dev);
     else
-        tc::estep_tc_kernel<false><<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols,
-                                                               w.xt, w.bt, w.cst, resp, mode,
-                                                               mix, w.cand, 0.05, nullptr);
+        rc = (G == 2) ? launch(tc::estep_tc_kernel<false, 2>, nullptr)
+                      : launch(tc::estep_tc_kernel<false, 1>, nullptr);
+    if (rc != KW_OK) return rc;
     if (prof_on) {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
