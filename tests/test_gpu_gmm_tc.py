@@ -96,3 +96,30 @@ def test_single_em_iteration_from_the_same_state(cuda, n, d, k, t):
     assert rel_err(gm.weights_, ref['weights']) <= TOL
     assert rel_err(gm.means_, ref['means']) <= TOL
     assert rel_err(gm.covariances_, ref['covariances']) <= TOL
+
+
+@pytest.mark.parametrize('d,k,spread', [(24, 3, 1e3), (72, 4, 1e4), (144, 2, 1e3)])
+def test_estep_with_tight_oblique_directions(cuda, d, k, spread):
+    """Components whose covariance has eigenvalues spread over `spread`, along directions that are
+    not the coordinate axes: the columns of L_k then differ by orders of magnitude, which is the
+    hard case for the single power-of-two scale per component of the tensor-core E-step."""
+    rng = np.random.default_rng(int(d * 7 + spread))
+    n = 3000
+    centres = rng.standard_normal((k, d))
+    covs, xs = [], []
+    for c in range(k):
+        qmat, _ = np.linalg.qr(rng.standard_normal((d, d)))
+        lam = np.exp(np.linspace(0.0, -np.log(spread), d))
+        a = qmat * np.sqrt(lam)
+        covs.append(a @ a.T)
+        xs.append(centres[c] + rng.standard_normal((n // k, d)) @ a.T)
+    x = np.concatenate(xs)
+    w = np.full(k, 1.0 / k)
+    covs = np.stack(covs)
+    pc = gmm_ref.precision_cholesky(covs)
+    lb, log_resp = gmm_ref.e_step(x, w, centres, pc)
+    gm = GaussianMixture(n_components=k, precision='tc').set_parameters(w, centres, covs)
+    assert abs(gm.score(x) - lb) <= TOL * abs(lb)
+    got = gm.predict_proba(x)
+    assert np.abs(got - np.exp(log_resp)).max() <= 2e-3
+    assert (got.argmax(1) == log_resp.argmax(1)).mean() >= 0.999
