@@ -268,7 +268,7 @@ convert_soft_kernel(long long N, long long Npad, int K, int Dh, const double* __
 //     reciprocal square root: with r_i = 1 / L[i][i], e_i = L[i][i-1], f_i = L[i][i-2]
 //        f_i = c_{i-2} r_{i-2};  e_i = (b_{i-1} - f_i e_{i-1}) r_{i-1};
 //        r_i = rsqrt(a_i - f_i^2 - e_i^2);  z_i = (rhs_i - e_i z_{i-1} - f_i z_{i-2}) r_i
-//     and back:  y_i = (z_i - e_{i+1} y_{i+1} - f_{i+2} y_{i+2}) r_i.
+//     and back:  y_i = (z_i - e_{i+1} y_{i+1} - f_{i+2} y_{i+2}) r_i  with f_{i+2} = c_i r_i.
 struct Windows {
     double c[3][3];  // c[w][o+1]: coefficient of window w at offset o in {-1, 0, 1}
 };
@@ -340,7 +340,7 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, double*
     const size_t plane = (size_t)total * sd;
     double* pa = ws + (size_t)t0 * sd + d;     // a -> r
     double* pb = pa + plane;                   // b -> e
-    double* pcc = pb + plane;                  // c -> f
+    double* pcc = pb + plane;                  // c (kept)
     double* pr = pcc + plane;                  // rhs -> z
     constexpr int PF = 4;
     double c_m2 = 0, c_m1 = 0, b_m1 = 0, r_m1 = 1, r_m2 = 1, e_m1 = 0, z_m1 = 0, z_m2 = 0;
@@ -367,7 +367,7 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, double*
                 const double r = rsqrt(ca[q] - f * f - e * e);
                 const double z = (cr[q] - e * z_m1 - f * z_m2) * r;
                 const size_t o = (size_t)(i0 + q) * sd;
-                pa[o] = r; pb[o] = e; pcc[o] = f; pr[o] = z;
+                pa[o] = r; pb[o] = e; pr[o] = z;      // c stays: f_{i+2} = c_i r_i on the way back
                 c_m2 = c_m1; c_m1 = cc[q]; b_m1 = cb[q];
                 r_m2 = r_m1; r_m1 = r; e_m1 = e;
                 z_m2 = z_m1; z_m1 = z;
@@ -376,7 +376,7 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, double*
     }
     // back substitution L^T y = z
     double* po = out + (size_t)t0 * sd + d;
-    double y1 = 0, y2 = 0, e_n1 = 0, f_n1 = 0, f_n2 = 0;
+    double y1 = 0, y2 = 0, e_n1 = 0;
     auto fetch_back = [&](int i0) {      // steps i0, i0-1, ...
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
@@ -394,10 +394,10 @@ convert_mlpg_kernel(int n_utts, const int64_t* __restrict__ off, int sd, double*
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             if (i0 - q >= 0) {
-                const double y = (cr[q] - e_n1 * y1 - f_n2 * y2) * ca[q];
+                const double y = (cr[q] - e_n1 * y1 - (cc[q] * ca[q]) * y2) * ca[q];
                 po[(size_t)(i0 - q) * sd] = y;
                 y2 = y1; y1 = y;
-                f_n2 = f_n1; f_n1 = cc[q]; e_n1 = cb[q];
+                e_n1 = cb[q];
             }
         }
     }
