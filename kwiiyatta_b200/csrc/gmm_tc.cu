@@ -472,7 +472,6 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     __half* a_lo = a_hi + tile_elems(DP);
     __half* b_hi0 = reinterpret_cast<__half*>(smem + L.b_hi);
     __half* b_lo = reinterpret_cast<__half*>(smem + L.b_lo);
-    double* cst_s = reinterpret_cast<double*>(smem + L.cst);
     double* qpart = reinterpret_cast<double*>(smem + L.qpart);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
@@ -892,7 +891,7 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     o = (o + 15u) & ~15u;
     g.off_mu = o;   o += (uint32_t)g.DA * 4;
     o = (o + 15u) & ~15u;
-    g.off_flags = o; o += 64;    // rmax[2][2] (float), tile_skip[2], group_empty[2] (int)
+    g.off_flags = o; o += 64;    // group_empty[2] at +32, pskip[2] at +48 (int)
     g.off_bars = o; o += 16 * 8;
     g.off_tmem = o; o += 16;
     g.off_corner = o; o += 2 * 12 * 32 * 4;  // second-level sums of the two corner warps
@@ -930,9 +929,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     unsigned char* a_base = smem + G.off_a;
     float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
     float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
-    volatile float* rmax_s = reinterpret_cast<volatile float*>(smem + G.off_flags);       // [2]
-    volatile int* tile_skip = reinterpret_cast<volatile int*>(smem + G.off_flags + 16);  // [2 stages]
     volatile int* group_empty = reinterpret_cast<volatile int*>(smem + G.off_flags + 32); // [2 stages]
+    volatile int* pskip = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);       // [2 stages]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
     // warp index through a shuffle so the compiler knows the role branches are warp-uniform
@@ -979,21 +977,45 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
       reg_dec<40>();
       if (warp == 0) {
         // ---------------- producer: packed frames (hi, unscaled lo) ----------------
-        if (lane == 0) {
+        // The whole warp looks at the tile's weights for this component first (two frames per
+        // lane, one tile ahead): a tile whose responsibilities are all <= 1e-16 contributes
+        // nothing representable, so it is not even loaded - the stage is handed over empty and
+        // flagged, and the generators / MMA / corner warps pass it on.
+        {
             uint32_t g = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int k, t0, t1;
                 item_tiles(item, k, t0, t1);
+                auto tile_max = [&](int t) -> float {
+                    const long long n = (long long)t * MT + 2 * lane;
+                    const double* rp = respT + (size_t)k * Npad + n;
+                    const double r0 = (t < t1 && n < N) ? rp[0] : 0.0;
+                    const double r1 = (t < t1 && n + 1 < N) ? rp[1] : 0.0;
+                    return fmaxf(fmaxf((float)r0, (float)r1), 0.f);
+                };
+                float m_next = tile_max(t0);
                 for (int t = t0; t < t1; ++t, ++g) {
                     const uint32_t s = g & 1u, u = g >> 1;
-                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                    mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
-                    const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
-                                         (size_t)(t & 1) * MT * G.DPB;
-                    unsigned char* dst = b_base + s * G.b_stage;
-                    bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
-                    bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
-                             bars + MB_B_FULL + s);
+                    const float m = m_next;
+                    m_next = tile_max(t + 1);
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                    const bool skip = __uint_as_float(mx) <= 1e-16f;
+                    if (lane == 0) {
+                        mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
+                        pskip[s] = skip ? 1 : 0;
+                        if (!skip) {
+                            mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
+                            const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                                 (size_t)(t & 1) * MT * G.DPB;
+                            unsigned char* dst = b_base + s * G.b_stage;
+                            bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
+                            bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
+                                     bars + MB_B_FULL + s);
+                        } else {
+                            mbar_arrive(bars + MB_B_FULL + s);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -1043,7 +1065,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const uint32_t acc1 = tmem_base + ts * acc_cols;
                     const uint32_t acc2 = acc1 + (uint32_t)G.N1;
                     if (in_group == 0) group_has_data = false;
-                    const bool skip = tile_skip[s] != 0 || swap_strides == 1;   // (1 = timing experiment: no MMAs)
+                    const bool skip = pskip[s] != 0 || swap_strides == 1;   // (1 = timing experiment: no MMAs)
                     const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
                     const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
                     if (!skip) {
@@ -1121,7 +1143,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
                 const long long c1 = tick<PROF>();
                 c_wait += c1 - c0;
-                if (tile_skip[s] == 0 && swap_strides != 1) {
+                if (pskip[s] == 0 && swap_strides != 1) {
                     const uint32_t ab = a_s0 + s * G.a_stage + la, bb = b_s0 + s * G.b_stage;
 #pragma unroll
                     for (int kq = 0; kq < MT / 32; ++kq) {
@@ -1234,8 +1256,6 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const float rf = (float)rv;
                     r_s[st * MT + gt] = rf;
                     nacc += (double)rf;
-                    const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(rf, 0.f)));
-                    if (lane == 0) rmax_s[st * 2 + (gt >> 5)] = __uint_as_float(mx);
                 }
             };
             asm volatile("bar.sync 2, 256;" ::: "memory");   // previous item fully consumed
@@ -1244,9 +1264,6 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             asm volatile("bar.sync 2, 256;" ::: "memory");
             for (int t = t0; t < t1; ++t, ++g) {
                 const uint32_t s = g & 1u, u = g >> 1;
-                // a tile whose responsibilities for this component are all <= 1e-16 contributes
-                // nothing representable: no operand generation, no MMAs
-                const bool skip = fmaxf(rmax_s[s * 2], rmax_s[s * 2 + 1]) <= 1e-16f;
                 const double r_next = r_ahead;         // loaded one tile ago
                 r_ahead = load_r(t + 2);
                 const long long c0 = tick<PROF>();
@@ -1255,7 +1272,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
                 const long long c2 = tick<PROF>();
                 g_b += c1 - c0; g_a += c2 - c1;
-                if (gt == 0) tile_skip[s] = skip ? 1 : 0;   // the MMA warp is done with this stage
+                const bool skip = pskip[s] != 0;      // the producer handed the stage over empty
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
                 const float* rt = r_s + s * MT;

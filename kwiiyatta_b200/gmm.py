@@ -43,7 +43,7 @@ class GaussianMixture:
                  max_iter=100, n_init=1, init_params='kmeans', weights_init=None,
                  means_init=None, precisions_init=None, random_state=None, warm_start=False,
                  verbose=0, verbose_interval=10, precision='fp64', resp_init=None,
-                 process_group=None, device=None):
+                 process_group=None, device=None, reorder_every=10):
         if covariance_type != 'full':
             raise NotImplementedError("only covariance_type='full' is built "
                                       '(kwiiyatta/converter/gmm.py:17-18)')
@@ -68,6 +68,14 @@ class GaussianMixture:
         self.process_group = process_group
         self.device = device
         self.iter_callback = None
+        # Tensor-core path only: the M-step skips (64-frame tile, component) pairs without
+        # responsibility mass, so the frames are kept sorted by their dominant component
+        # (at initialisation and again every `reorder_every` iterations; 0 = never).  EM sums
+        # over frames, the order only changes the rounding of those sums.
+        self.reorder_every = int(reorder_every)
+        self._x_src = None
+        self._x_used = None
+        self._iters_done = 0
 
     # ------------------------------------------------------------------ device plumbing
     def _alloc(self, torch, n, d, dev):
@@ -94,7 +102,29 @@ class GaussianMixture:
                                            _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_pack_frames')
 
+    def _frames(self, x):
+        """The tensor the kernels read for the caller's ``x``: its reordered copy if one is
+        in use."""
+        if self._x_used is not None and self._x_src is not None and \
+                x.data_ptr() == self._x_src.data_ptr():
+            return self._x_used
+        return x
+
+    def _reorder(self, torch, n):
+        """Sort the frames (and the responsibilities in place) by dominant component and
+        re-pack them."""
+        labels = self._resp[:, :n].argmax(dim=0)
+        perm = torch.argsort(labels, stable=True)
+        base = self._x_used if self._x_used is not None else self._x_src
+        self._x_used = base.index_select(0, perm)
+        self._resp[:, :n] = self._resp[:, :n].index_select(1, perm)
+        self._pack(torch, self._x_used)
+
+    def _wants_reorder(self, n):
+        return self.precision == 1 and self.reorder_every > 0 and n >= 8192
+
     def _estep(self, torch, x):
+        x = self._frames(x)
         n, d = x.shape
         rc = _lib.lib().kw_gmm_estep(
             n, x.data_ptr(), self.n_components, d, self._means[self._cur].data_ptr(),
@@ -104,6 +134,7 @@ class GaussianMixture:
         _lib.check(rc, 'kw_gmm_estep')
 
     def _accumulate(self, torch, x, centres):
+        x = self._frames(x)
         n, d = x.shape
         rc = _lib.lib().kw_gmm_mstep_accumulate(
             n, x.data_ptr(), self.n_components, d, self._resp.data_ptr(), centres.data_ptr(),
@@ -174,11 +205,15 @@ class GaussianMixture:
             raise ValueError('Expected n_samples >= n_components '
                              f'but got n_components = {k}, n_samples = {n}')
         self._alloc(torch, n, d, dev)
-        self._pack(torch, x)
+        self._x_src, self._x_used, self._iters_done = x, None, 0
         if self.verbose:
             print('Initialization 0')
         # GaussianMixture._initialize: one M-step from the initial responsibilities
         self._resp[:, :n].copy_(self._initial_resp(torch, x))
+        if self._wants_reorder(n):
+            self._reorder(torch, n)
+        else:
+            self._pack(torch, x)
         centre = x.sum(dim=0, keepdim=True)
         count = torch.tensor([float(n)], dtype=torch.float64, device=dev)
         import torch.distributed as dist
@@ -226,6 +261,7 @@ class GaussianMixture:
         self._publish()
         self._resp = None
         self._ws = None
+        self._x_src = self._x_used = None
         return self
 
     def em_iteration(self, x):
@@ -234,6 +270,9 @@ class GaussianMixture:
         torch = _lib.require_cuda()
         centres = self._means[self._cur]
         self._estep(torch, x)
+        self._iters_done += 1
+        if self._wants_reorder(x.shape[0]) and self._iters_done % self.reorder_every == 0:
+            self._reorder(torch, x.shape[0])
         self._accumulate(torch, x, centres)
         self._allreduce(torch)
         tail = self._stats[-2:].cpu().numpy()

@@ -21,5 +21,10 @@ for it in range(1, 31):
         r = gm._resp[:, :n]
         nt = n // 64
         rt = r[:, :nt * 64].reshape(K, nt, 64).amax(dim=2)
+        order = torch.argsort(lab, stable=True)
+        rs = r[:, order][:, :nt * 64].reshape(K, nt, 64).amax(dim=2)
+        order2 = torch.argsort(r.argmax(dim=0), stable=True)
+        rs2 = r[:, order2][:, :nt * 64].reshape(K, nt, 64).amax(dim=2)
+        print(f'   sorted by the INITIAL labels: {(rs > 1e-16).float().mean().item():.3f}; sorted by the current argmax: {(rs2 > 1e-16).float().mean().item():.3f}')
         print(f'iter {it}: frames {n}, mean comps/frame > 1e-16: {(r > 1e-16).sum().item() / n:.1f}; '
               f'(tile,k) with max r > 1e-16: {(rt > 1e-16).float().mean().item():.3f}, > 1e-10: {(rt > 1e-10).float().mean().item():.3f}')
