@@ -892,7 +892,7 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     g.off_mu = o;   o += (uint32_t)g.DA * 4;
     o = (o + 15u) & ~15u;
     g.off_flags = o; o += 64;    // group_empty[2] at +32, pskip[2] at +48 (int)
-    g.off_bars = o; o += 16 * 8;
+    g.off_bars = o; o += 24 * 8;
     g.off_tmem = o; o += 16;
     g.off_corner = o; o += 2 * 12 * 32 * 4;  // second-level sums of the two corner warps
     g.total = o;
@@ -902,7 +902,7 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
 }
 
 enum { MB_B_FULL = 0, MB_B_EMPTY = 2, MB_A_FULL = 4, MB_A_EMPTY = 6, MB_TM_FULL = 8,
-       MB_TM_EMPTY = 10 };
+       MB_TM_EMPTY = 10, MB_IT_FULL = 12, MB_IT_EMPTY = 16 };   // 4 item-ring slots each
 
 // mu'_k = fl32((mu_k - c) / sigma) for the generators, one CTA per component.
 __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restrict__ centres,
@@ -922,7 +922,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
                  const float* __restrict__ mu32, float* __restrict__ partial,
                  double* __restrict__ npartial, int swap_strides, int M_FLUSH,
-                 unsigned long long* __restrict__ prof) {
+                 int* __restrict__ item_counter, unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     unsigned char* b_base = smem + G.off_b;
@@ -950,6 +950,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             mbar_init(bars + MB_TM_FULL + i, 1);
             mbar_init(bars + MB_TM_EMPTY + i, 8);
         }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bars + MB_IT_FULL + i, 1);
+            // consumers of an item: MMA warp, corner warps, 8 generator and 8 epilogue warps
+            mbar_init(bars + MB_IT_EMPTY + i, 17 + (G.corner ? 2 : 0));
+        }
         fence_barrier_init();
     }
     // zero the A stages once (feature rows >= DP stay zero)
@@ -962,6 +967,32 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // Work items (component, chunk of tiles) are handed out dynamically: the frames are kept
+    // sorted by dominant component, so items differ widely in how many of their tiles carry
+    // weight, and a static round-robin leaves the kernel waiting for the unlucky CTAs.  The
+    // producer warp draws the next item from a global counter and passes it to the other roles
+    // through a 4-slot ring (every role sees the same sequence; -1 ends it).
+    volatile int* item_ring = reinterpret_cast<volatile int*>(smem + G.off_flags);   // [4]
+    auto next_item = [&](uint32_t idx) -> int {          // consumer side, whole warp
+        const uint32_t slot = idx & 3u;
+        mbar_wait(bars + MB_IT_FULL + slot, (idx >> 2) & 1u);
+        const int it = item_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + MB_IT_EMPTY + slot);
+        return it;
+    };
+    auto draw_item = [&](uint32_t idx) -> int {          // producer warp
+        int it = 0;
+        if (lane == 0) {
+            const uint32_t slot = idx & 3u;
+            mbar_wait(bars + MB_IT_EMPTY + slot, ((idx >> 2) & 1u) ^ 1u);
+            it = atomicAdd(item_counter, 1);
+            if (it >= n_items) it = -1;
+            item_ring[slot] = it;
+            mbar_arrive(bars + MB_IT_FULL + slot);
+        }
+        return __shfl_sync(0xffffffffu, it, 0);
+    };
     auto item_tiles = [&](int item, int& k, int& t0, int& t1) {
         const int chunk = item / K;
         k = item - chunk * K;
@@ -983,7 +1014,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         // flagged, and the generators / MMA / corner warps pass it on.
         {
             uint32_t g = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (uint32_t it_idx = 0;; ++it_idx) {
+                const int item = draw_item(it_idx);
+                if (item < 0) break;
                 int k, t0, t1;
                 item_tiles(item, k, t0, t1);
                 auto tile_max = [&](int t) -> float {
@@ -1045,7 +1078,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             const long long p_start = tick<PROF>();
             bool group_has_data = false;
             uint32_t g = 0, f = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
                 int k, t0, t1;
                 item_tiles(item, k, t0, t1);
                 for (int t = t0; t < t1; ++t, ++g) {
@@ -1131,7 +1166,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         for (int i = 0; i < 12; ++i) acc[i] = 0.f;
         uint32_t g = 0;
         long long c_wait = 0, c_work = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
             for (int t = t0; t < t1; ++t, ++g) {
@@ -1236,7 +1273,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         uint32_t g = 0;
         long long g_b = 0, g_a = 0, g_gen = 0, g_pub = 0, g_bar = 0;
         const long long g_start = tick<PROF>();
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
             float mu_a[8], mu_b[8];
@@ -1348,7 +1387,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         const int c2_end = half == 0 ? (n16_2 + 1) / 2 : n16_2;
         float acc[6][16];
         uint32_t f = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
 #pragma unroll
@@ -1497,6 +1538,7 @@ struct TcWorkspace {
     float* mu32;
     float* mpartial;
     double* npartial;
+    int* item_counter;
     double* mraw;
     int m_chunks, tiles_per_chunk, n_mtiles;
     size_t bytes;
@@ -1549,6 +1591,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.mu32 = c.take<float>((size_t)K * G.DA);
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
     w.npartial = c.take<double>(2 * (size_t)w.m_chunks * K);
+    w.item_counter = c.take<int>(4);
     w.mraw = c.take<double>((size_t)K * (G.partial_len + 1));
     w.bytes = align_up(c.used, 256);
     return w;
@@ -1671,6 +1714,7 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
+    KW_CUDA_CHECK(cudaMemsetAsync(w.item_counter, 0, sizeof(int), st));
     static int swap_strides = -1, m_flush = 2;
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
@@ -1687,11 +1731,11 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
     if (prof_on)
         tc::mstats_tc_kernel<true><<<grid, 640, G.total, st>>>(
             N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, prof_dev);
+            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, prof_dev);
     else
         tc::mstats_tc_kernel<false><<<grid, 640, G.total, st>>>(
             N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, nullptr);
+            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, nullptr);
     if (prof_on) {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
