@@ -929,8 +929,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     unsigned char* a_base = smem + G.off_a;
     float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
     float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
-    volatile int* group_empty = reinterpret_cast<volatile int*>(smem + G.off_flags + 32); // [2 stages]
-    volatile int* pskip = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);       // [2 stages]
+    volatile int* gflag = reinterpret_cast<volatile int*>(smem + G.off_flags + 32);       // [2 TMEM stages]
+    volatile int* pent = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);        // [2 stages] tile of the entry, -1 = end of item
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
     // warp index through a shuffle so the compiler knows the role branches are warp-uniform
@@ -1009,9 +1009,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
       if (warp == 0) {
         // ---------------- producer: packed frames (hi, unscaled lo) ----------------
         // The whole warp looks at the tile's weights for this component first (two frames per
-        // lane, one tile ahead): a tile whose responsibilities are all <= 1e-16 contributes
-        // nothing representable, so it is not even loaded - the stage is handed over empty and
-        // flagged, and the generators / MMA / corner warps pass it on.
+        // lane, one tile ahead).  A tile whose responsibilities are all <= 1e-16 contributes
+        // nothing representable and never enters the pipeline; for the others the producer also
+        // publishes the weights (fp32, as the MMAs will see them) with the stage, so the
+        // generators read nothing from global memory.  Every item ends with an END entry
+        // (pent = -1) that lets the other roles close the item.
         {
             uint32_t g = 0;
             for (uint32_t it_idx = 0;; ++it_idx) {
@@ -1019,36 +1021,54 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 if (item < 0) break;
                 int k, t0, t1;
                 item_tiles(item, k, t0, t1);
-                auto tile_max = [&](int t) -> float {
+                auto load2 = [&](int t, double& r0, double& r1) {
                     const long long n = (long long)t * MT + 2 * lane;
                     const double* rp = respT + (size_t)k * Npad + n;
-                    const double r0 = (t < t1 && n < N) ? rp[0] : 0.0;
-                    const double r1 = (t < t1 && n + 1 < N) ? rp[1] : 0.0;
-                    return fmaxf(fmaxf((float)r0, (float)r1), 0.f);
+                    r0 = (t < t1 && n < N) ? rp[0] : 0.0;
+                    r1 = (t < t1 && n + 1 < N) ? rp[1] : 0.0;
                 };
-                float m_next = tile_max(t0);
-                for (int t = t0; t < t1; ++t, ++g) {
+                double a0, a1, nacc = 0.0;
+                load2(t0, a0, a1);
+                for (int t = t0; t < t1; ++t) {
+                    const float f0 = (float)a0, f1 = (float)a1;
+                    load2(t + 1, a0, a1);
+                    nacc += (double)f0 + (double)f1;
+                    const unsigned mx = __reduce_max_sync(
+                        0xffffffffu, __float_as_uint(fmaxf(fmaxf(f0, f1), 0.f)));
+                    if (__uint_as_float(mx) <= 1e-16f) continue;
                     const uint32_t s = g & 1u, u = g >> 1;
-                    const float m = m_next;
-                    m_next = tile_max(t + 1);
-                    const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                    const bool skip = __uint_as_float(mx) <= 1e-16f;
+                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
+                    *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) = make_float2(f0, f1);
+                    __syncwarp();
                     if (lane == 0) {
-                        mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                        pskip[s] = skip ? 1 : 0;
-                        if (!skip) {
-                            mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
-                            const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
-                                                 (size_t)(t & 1) * MT * G.DPB;
-                            unsigned char* dst = b_base + s * G.b_stage;
-                            bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
-                            bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
-                                     bars + MB_B_FULL + s);
-                        } else {
-                            mbar_arrive(bars + MB_B_FULL + s);
-                        }
+                        pent[s] = t;
+                        mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
+                        const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                             (size_t)(t & 1) * MT * G.DPB;
+                        unsigned char* dst = b_base + s * G.b_stage;
+                        bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
+                        bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
+                                 bars + MB_B_FULL + s);
                     }
                     __syncwarp();
+                    ++g;
+                }
+                {   // END of the item
+                    const uint32_t s = g & 1u, u = g >> 1;
+                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
+                    if (lane == 0) {
+                        pent[s] = -1;
+                        mbar_arrive(bars + MB_B_FULL + s);
+                    }
+                    __syncwarp();
+                    ++g;
+                }
+                // n_k of this item (all tiles, also the ones that never entered the pipeline)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
+                if (lane == 0) {
+                    npartial[(size_t)item * 2] = nacc;
+                    npartial[(size_t)item * 2 + 1] = 0.0;
                 }
             }
         }
@@ -1076,58 +1096,67 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             (void)swap_strides;
             long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
             const long long p_start = tick<PROF>();
-            bool group_has_data = false;
             uint32_t g = 0, f = 0;
             for (uint32_t it_idx = 0;; ++it_idx) {
-            const int item = next_item(it_idx);
-            if (item < 0) break;
-                int k, t0, t1;
-                item_tiles(item, k, t0, t1);
-                for (int t = t0; t < t1; ++t, ++g) {
+                const int item = next_item(it_idx);
+                if (item < 0) break;
+                int cnt = 0;                      // tiles accumulated since the last flush
+                for (;;) {
                     const uint32_t s = g & 1u, u = g >> 1;
-                    const int in_group = (t - t0) % M_FLUSH;
-                    const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
                     const uint32_t ts = f & 1u, tu = f >> 1;
                     const long long c0 = tick<PROF>();
-                    if (in_group == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
-                    const long long c1 = tick<PROF>();
-                    mbar_wait(bars + MB_A_FULL + s, u & 1u);
-                    const long long c2 = tick<PROF>();
                     mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                    const int tt = pent[s];
+                    const long long c1 = tick<PROF>();
+                    if (cnt == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
+                    const long long c2 = tick<PROF>();
+                    mbar_wait(bars + MB_A_FULL + s, u & 1u);
                     const long long c3 = tick<PROF>();
-                    p_tm += c1 - c0; p_a += c2 - c1; p_b += c3 - c2;
+                    p_b += c1 - c0; p_tm += c2 - c1; p_a += c3 - c2;
                     tc_fence_after();
+                    ++g;
+                    if (tt < 0) {
+                        // END: release the stage and close the item's last flush group
+                        if (lane == 0) {
+                            mbar_arrive(bars + MB_A_EMPTY + s);
+                            mbar_arrive(bars + MB_B_EMPTY + s);
+                            gflag[ts] = (cnt > 0 ? 1 : 0) | 2;
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        umma_commit(bars + MB_TM_FULL + ts);
+                        ++f;
+                        break;
+                    }
                     const uint32_t acc1 = tmem_base + ts * acc_cols;
                     const uint32_t acc2 = acc1 + (uint32_t)G.N1;
-                    if (in_group == 0) group_has_data = false;
-                    const bool skip = pskip[s] != 0 || swap_strides == 1;   // (1 = timing experiment: no MMAs)
                     const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
                     const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
-                    if (!skip) {
+                    if (swap_strides != 1) {      // (1 = timing experiment: no MMAs)
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         uint64_t da = (pass == 2) ? a_lo_d : a_hi_d;     // A lo in pass 2
                         uint64_t db = (pass == 1) ? b_lo_d : b_hi_d;     // B lo in pass 1
 #pragma unroll
                         for (int ks = 0; ks < MT / 16; ++ks) {
-                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (group_has_data ? 1u : 0u);
+                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (cnt > 0 ? 1u : 0u);
                             umma_f16(acc1, da, db, idesc1, accum);
                             if (has2) umma_f16(acc2, da + win_a, db + win_b, idesc2, accum);
                             da += step_a;
                             db += step_b;
                         }
                     }
-                    group_has_data = true;
                     }
                     umma_commit(bars + MB_A_EMPTY + s);
                     umma_commit(bars + MB_B_EMPTY + s);
-                    if (last) {
-                        // tell the epilogue whether this flush group accumulated anything
-                        if (lane == 0) group_empty[ts] = group_has_data ? 0 : 1;
+                    ++cnt;
+                    if (cnt == M_FLUSH) {
+                        if (lane == 0) gflag[ts] = 1;
                         __threadfence_block();
                         __syncwarp();
                         umma_commit(bars + MB_TM_FULL + ts);
                         ++f;
+                        cnt = 0;
                     }
                     p_issue += tick<PROF>() - c3;
                 }
@@ -1169,18 +1198,17 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
         for (uint32_t it_idx = 0;; ++it_idx) {
             const int item = next_item(it_idx);
             if (item < 0) break;
-            int k, t0, t1;
-            item_tiles(item, k, t0, t1);
-            for (int t = t0; t < t1; ++t, ++g) {
+            int cnt = 0;
+            for (;;) {
                 const uint32_t s = g & 1u, u = g >> 1;
-                const int in_group = (t - t0) % M_FLUSH;
-                const bool last = (in_group == M_FLUSH - 1) || (t == t1 - 1);
                 const long long c0 = tick<PROF>();
-                mbar_wait(bars + MB_A_FULL + s, u & 1u);
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                const int tt = pent[s];
+                mbar_wait(bars + MB_A_FULL + s, u & 1u);
                 const long long c1 = tick<PROF>();
                 c_wait += c1 - c0;
-                if (pskip[s] == 0 && swap_strides != 1) {
+                ++g;
+                if (tt >= 0 && swap_strides != 1) {
                     const uint32_t ab = a_s0 + s * G.a_stage + la, bb = b_s0 + s * G.b_stage;
 #pragma unroll
                     for (int kq = 0; kq < MT / 32; ++kq) {
@@ -1205,14 +1233,17 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_A_EMPTY + s);
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
-                if (last) {
+                if (tt >= 0) ++cnt;
+                if (cnt == M_FLUSH || (tt < 0 && cnt > 0)) {
 #pragma unroll
                     for (int i = 0; i < 12; ++i) {
                         cacc[i * 32 + lane] += acc[i];
                         acc[i] = 0.f;
                     }
+                    cnt = 0;
                 }
                 c_work += tick<PROF>() - c1;
+                if (tt < 0) break;
             }
             // rows 112..127 of the second accumulator block of this item's partial: warp 2 adds
             // warp 3's half and writes
@@ -1284,37 +1315,18 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 mu_a[e] = on_a ? mu32[(size_t)k * G.DA + featg_a * 8 + e] : 0.f;
                 mu_b[e] = on_b ? mu32[(size_t)k * G.DA + featg_b * 8 + e] : 0.f;
             }
-            double nacc = 0.0;          // per-thread sum of this thread's frame weights (gt < MT)
-            auto load_r = [&](int t) -> double {
-                const long long n = (long long)t * MT + gt;
-                return (gt < MT && t < t1 && n < N) ? respT[(size_t)k * Npad + n] : 0.0;
-            };
-            // publish the weights of a tile (fp32, as the MMAs will see them) and their maximum
-            auto publish_r = [&](double rv, uint32_t st) {
-                if (gt < MT) {      // generator warps 0 and 1, all lanes
-                    const float rf = (float)rv;
-                    r_s[st * MT + gt] = rf;
-                    nacc += (double)rf;
-                }
-            };
-            asm volatile("bar.sync 2, 256;" ::: "memory");   // previous item fully consumed
-            publish_r(load_r(t0), g & 1u);
-            double r_ahead = load_r(t0 + 1);      // weights are fetched two tiles ahead of use
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            for (int t = t0; t < t1; ++t, ++g) {
+            for (;;) {
                 const uint32_t s = g & 1u, u = g >> 1;
-                const double r_next = r_ahead;         // loaded one tile ago
-                r_ahead = load_r(t + 2);
                 const long long c0 = tick<PROF>();
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
+                const int tt = pent[s];           // tile of this entry, -1 = end of the item
                 const long long c1 = tick<PROF>();
                 mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
                 const long long c2 = tick<PROF>();
                 g_b += c1 - c0; g_a += c2 - c1;
-                const bool skip = pskip[s] != 0;      // the producer handed the stage over empty
                 const unsigned char* bh = b_base + s * G.b_stage;
                 unsigned char* ah = a_base + s * G.a_stage;
-                const float* rt = r_s + s * MT;
+                const float* rt = r_s + s * MT;   // published by the producer with the stage
                 auto convert = [&](uint32_t bo, uint32_t ao, float r, const float* mu8) {
                     const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
                     const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
@@ -1336,7 +1348,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     *reinterpret_cast<uint4*>(ah + ao) = oh;
                     *reinterpret_cast<uint4*>(ah + part_a + ao) = ol;
                 };
-                if (!skip && swap_strides != 2) {   // (2 = timing experiment: no generation)
+                if (tt >= 0 && swap_strides != 2) {   // (2 = timing experiment: no generation)
                     if (on_a) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
@@ -1350,21 +1362,10 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     mbar_arrive(bars + MB_A_FULL + s);
                     mbar_arrive(bars + MB_B_EMPTY + s);
                 }
-                const long long c3 = tick<PROF>();
-                g_gen += c3 - c2;
-                publish_r(r_next, s ^ 1u);                        // weights of the next tile
-                const long long c4 = tick<PROF>();
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                g_pub += c4 - c3; g_bar += tick<PROF>() - c4;
+                g_gen += tick<PROF>() - c2;
+                ++g;
+                if (tt < 0) break;
             }
-            // n_k of this item: fixed-order reduction of the per-thread sums (two warps)
-            if (gt < MT) {
-                double rs = nacc;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-                nacc = rs;
-            }
-            if (gt == 0 || gt == 32) npartial[(size_t)item * 2 + (gt >> 5)] = nacc;
         }
         if (prof != nullptr && blockIdx.x == 0 && gt == 64) {
             prof[8] = (unsigned long long)(tick<PROF>() - g_start);
@@ -1396,12 +1397,12 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
             for (int c = 0; c < 6; ++c)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
-            const int n_groups = (t1 - t0 + M_FLUSH - 1) / M_FLUSH;
-            for (int h = 0; h < n_groups; ++h, ++f) {
+            for (;;) {
                 const uint32_t ts = f & 1u, tu = f >> 1;
                 mbar_wait(bars + MB_TM_FULL + ts, tu & 1u);
                 tc_fence_after();
-                const bool empty = group_empty[ts] != 0;
+                const int fl = gflag[ts];         // bit 0: the group holds data, bit 1: last group
+                const bool empty = (fl & 1) == 0;
                 const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -1435,6 +1436,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + MB_TM_EMPTY + ts);
+                ++f;
+                if (fl & 2) break;
             }
             float* out = partial + (size_t)item * G.partial_len;
 #pragma unroll
