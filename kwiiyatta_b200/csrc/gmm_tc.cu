@@ -916,13 +916,40 @@ __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restri
     }
 }
 
+// flags[k][tile] = 1 when some frame of the 64-frame tile has weight > 1e-16 for component k
+// (as fp32, the form the MMAs see).  One warp per (component, 4 tiles): 8 lanes per tile, 8
+// consecutive frames per lane.
+__global__ void __launch_bounds__(256)
+mstats_tc_flags_kernel(long long N, long long Npad, int n_mtiles, int n_mt_pad, int K,
+                       const double* __restrict__ respT, unsigned char* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gpk = n_mt_pad / 4;
+    const int k = (int)(w / gpk);
+    if (k >= K) return;
+    const int tile = (int)(w - (long long)k * gpk) * 4 + (lane >> 3);
+    const long long n0 = (long long)tile * MT + (lane & 7) * 8;
+    float m = 0.f;
+    if (tile < n_mtiles) {
+        const double* rp = respT + (size_t)k * Npad + n0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (n0 + e < N) m = fmaxf(m, (float)rp[e]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    if ((lane & 7) == 0) flags[(size_t)k * n_mt_pad + tile] = (m > 1e-16f) ? 1 : 0;
+}
+
 template <bool PROF>
 __global__ void __launch_bounds__(640, 1)
 mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
                  const float* __restrict__ mu32, float* __restrict__ partial,
                  double* __restrict__ npartial, int swap_strides, int M_FLUSH,
-                 int* __restrict__ item_counter, unsigned long long* __restrict__ prof) {
+                 int* __restrict__ item_counter, const unsigned char* __restrict__ tflags,
+                 int n_mt_pad, unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     unsigned char* b_base = smem + G.off_b;
@@ -1008,9 +1035,10 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
       reg_dec<40>();
       if (warp == 0) {
         // ---------------- producer: packed frames (hi, unscaled lo) ----------------
-        // The whole warp looks at the tile's weights for this component first (two frames per
-        // lane, one tile ahead).  A tile whose responsibilities are all <= 1e-16 contributes
-        // nothing representable and never enters the pipeline; for the others the producer also
+        // mstats_tc_flags_kernel marked the tiles that carry weight for each component; the
+        // warp looks 32 of them up at a time.  A tile whose responsibilities are all <= 1e-16
+        // contributes nothing representable and never enters the pipeline; for the others the
+        // producer loads the weights (two frames per lane, one entry ahead) and also
         // publishes the weights (fp32, as the MMAs will see them) with the stage, so the
         // generators read nothing from global memory.  Every item ends with an END entry
         // (pent = -1) that lets the other roles close the item.
@@ -1024,34 +1052,40 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 auto load2 = [&](int t, double& r0, double& r1) {
                     const long long n = (long long)t * MT + 2 * lane;
                     const double* rp = respT + (size_t)k * Npad + n;
-                    r0 = (t < t1 && n < N) ? rp[0] : 0.0;
-                    r1 = (t < t1 && n + 1 < N) ? rp[1] : 0.0;
+                    r0 = (t >= 0 && n < N) ? rp[0] : 0.0;
+                    r1 = (t >= 0 && n + 1 < N) ? rp[1] : 0.0;
                 };
-                double a0, a1, nacc = 0.0;
-                load2(t0, a0, a1);
-                for (int t = t0; t < t1; ++t) {
-                    const float f0 = (float)a0, f1 = (float)a1;
-                    load2(t + 1, a0, a1);
-                    nacc += (double)f0 + (double)f1;
-                    const unsigned mx = __reduce_max_sync(
-                        0xffffffffu, __float_as_uint(fmaxf(fmaxf(f0, f1), 0.f)));
-                    if (__uint_as_float(mx) <= 1e-16f) continue;
-                    const uint32_t s = g & 1u, u = g >> 1;
-                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                    *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) = make_float2(f0, f1);
-                    __syncwarp();
-                    if (lane == 0) {
-                        pent[s] = t;
-                        mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
-                        const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
-                                             (size_t)(t & 1) * MT * G.DPB;
-                        unsigned char* dst = b_base + s * G.b_stage;
-                        bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
-                        bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
-                                 bars + MB_B_FULL + s);
+                const unsigned char* fk = tflags + (size_t)k * n_mt_pad;
+                double nacc = 0.0;
+                for (int tb = t0; tb < t1; tb += 32) {
+                    // 32 tiles per look-up: which of them carry weight at all
+                    const int tq = tb + lane;
+                    unsigned mask = __ballot_sync(0xffffffffu, tq < t1 && fk[tq] != 0);
+                    double a0 = 0.0, a1 = 0.0;
+                    if (mask) load2(tb + __ffs(mask) - 1, a0, a1);
+                    while (mask) {
+                        const int t = tb + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float f0 = (float)a0, f1 = (float)a1;
+                        load2(mask ? tb + __ffs(mask) - 1 : -1, a0, a1);   // next non-empty tile
+                        nacc += (double)f0 + (double)f1;
+                        const uint32_t s = g & 1u, u = g >> 1;
+                        mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
+                        *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) = make_float2(f0, f1);
+                        __syncwarp();
+                        if (lane == 0) {
+                            pent[s] = t;
+                            mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
+                            const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                                 (size_t)(t & 1) * MT * G.DPB;
+                            unsigned char* dst = b_base + s * G.b_stage;
+                            bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
+                            bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
+                                     bars + MB_B_FULL + s);
+                        }
+                        __syncwarp();
+                        ++g;
                     }
-                    __syncwarp();
-                    ++g;
                 }
                 {   // END of the item
                     const uint32_t s = g & 1u, u = g >> 1;
@@ -1063,7 +1097,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     __syncwarp();
                     ++g;
                 }
-                // n_k of this item (all tiles, also the ones that never entered the pipeline)
+                // n_k of this item
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
                 if (lane == 0) {
@@ -1542,6 +1576,7 @@ struct TcWorkspace {
     float* mpartial;
     double* npartial;
     int* item_counter;
+    unsigned char* tflags;
     double* mraw;
     int m_chunks, tiles_per_chunk, n_mtiles;
     size_t bytes;
@@ -1595,6 +1630,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
     w.npartial = c.take<double>(2 * (size_t)w.m_chunks * K);
     w.item_counter = c.take<int>(4);
+    w.tflags = c.take<unsigned char>((size_t)K * (size_t)((w.n_mtiles + 3) / 4 * 4));
     w.mraw = c.take<double>((size_t)K * (G.partial_len + 1));
     w.bytes = align_up(c.used, 256);
     return w;
@@ -1718,6 +1754,13 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
     KW_CUDA_CHECK(cudaMemsetAsync(w.item_counter, 0, sizeof(int), st));
+    const int n_mt_pad = (w.n_mtiles + 3) / 4 * 4;
+    {
+        const long long warps = (long long)K * (n_mt_pad / 4);
+        tc::mstats_tc_flags_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+            N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags);
+        KW_CUDA_CHECK(cudaGetLastError());
+    }
     static int swap_strides = -1, m_flush = 2;
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
@@ -1734,11 +1777,11 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
     if (prof_on)
         tc::mstats_tc_kernel<true><<<grid, 640, G.total, st>>>(
             N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, prof_dev);
+            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, w.tflags, n_mt_pad, prof_dev);
     else
         tc::mstats_tc_kernel<false><<<grid, 640, G.total, st>>>(
             N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, nullptr);
+            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, w.tflags, n_mt_pad, nullptr);
     if (prof_on) {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
