@@ -110,6 +110,29 @@ def build_dtw_inputs(first_pair, n_pairs):
 # --------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def capture_stdout():
+    """Rank 0 must print ONE JSON line on stdout: send everything else that lands on fd 1
+    (NCCL's version banner, library chatter) to stderr and keep the real stdout for the line."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -400,7 +423,7 @@ def run_b200(args):
             },
         },
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -536,7 +559,7 @@ def run_reference(args):
                                   f'frames, K={N_MIX_CONVERT}, {cv_dt:.1f} s'},
         },
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -553,6 +576,7 @@ def main():
     args = ap.parse_args()
     # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner / debug output on stderr
     os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    capture_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
