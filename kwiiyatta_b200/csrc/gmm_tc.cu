@@ -955,7 +955,6 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     unsigned char* b_base = smem + G.off_b;
     unsigned char* a_base = smem + G.off_a;
     float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
-    float* mu_s = reinterpret_cast<float*>(smem + G.off_mu);
     volatile int* gflag = reinterpret_cast<volatile int*>(smem + G.off_flags + 32);       // [2 TMEM stages]
     volatile int* pent = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);        // [2 stages] tile of the entry, -1 = end of item
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
