@@ -378,7 +378,13 @@ def run_b200(args):
         'gpu_launches': (10 if tc else 6) * K,
         'roofline': {
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
-            'unit': 'TFLOP/s', 'frac': dom_tflops / peak, 'traffic': None,
+            'unit': 'TFLOP/s', 'frac': dom_tflops / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel
+            # in the ncu --set full capture of this workload (profiles/ncu_r1d_mstats_tc.txt,
+            # profiles/ncu_r1c_estep_tc.txt); algorithmic: packed X 113 MB + resp 90 MB in
+            'traffic': ({'mstats_tc_kernel': 204.4e6 + 75.6e6, 'estep_tc_kernel': 116.5e6 + 54.3e6}
+                        .get(dominant) if n_frames == 176323 else None),
+            'traffic_unit': 'bytes per launch (ncu, 1 GPU)',
             'peak_source': f"{peaks['source']} bf16_tflops_sustained",
             'algorithmic': '2*N*K*D^2 flop per launch (half of the 4*N*K*D^2 EM iteration); '
                            'duration = CUDA events around the C-ABI entry that launches it',
