@@ -793,6 +793,7 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
     const int q = lane >> 3, r = lane & 7;      // window sector and row-in-sector of this lane
     int i = tx - 1, j = ty - 1, n = 0, prev_i = -1, prev_j = -1;
     int si = -1, sj = -1;                        // anchor (bottom-right sector) of the window
+    int bi = 0, bj = 0;                          // path point buffered by this lane (level 0)
     uint32_t w = 0u;
     while (i >= 0 && j >= 0 && n < tx + ty) {
         const int ci = i >> 3, cj = j >> 4;
@@ -802,14 +803,14 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
             const int ii = si - (q & 1), jj = sj - (q >> 1);
             w = (ii >= 0 && jj >= 0) ? __ldcg(bpp + ((size_t)ii * ncg + jj) * 8 + r) : 0u;
         }
-        if (lane == 0) {
-            if (level == 0) {
-                out[2 * (cap - 1 - n)] = i;
-                out[2 * (cap - 1 - n) + 1] = j;
-            } else if (i != prev_i) {
-                last[i] = j;
-                if (prev_i >= 0) first[prev_i] = prev_j;
-            }
+        if (level == 0) {
+            // lane n % 32 keeps the point; every 32 steps the warp stores its 32 points at once
+            if (lane == (n & 31)) { bi = i; bj = j; }
+            if ((n & 31) == 31)
+                reinterpret_cast<int2*>(out)[cap - 1 - (n - 31 + lane)] = make_int2(bi, bj);
+        } else if (lane == 0 && i != prev_i) {
+            last[i] = j;
+            if (prev_i >= 0) first[prev_i] = prev_j;
         }
         prev_i = i;
         prev_j = j;
@@ -826,6 +827,8 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
         }
         ++n;
     }
+    if (level == 0 && lane < (n & 31))       // the points since the last full group of 32
+        reinterpret_cast<int2*>(out)[cap - 1 - ((n & ~31) + lane)] = make_int2(bi, bj);
     if (lane == 0) {
         if (level > 0 && prev_i >= 0) first[prev_i] = prev_j;
         if (level == 0) {
