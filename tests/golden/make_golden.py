@@ -74,8 +74,35 @@ def mlpg_case():
     np.savez_compressed(os.path.join(HERE, 'mlpg.npz'), **out)
 
 
+def em_scale_case():
+    """sklearn's own fit to convergence (tol = 1e-3, the reference's default) of the 64-mix model
+    on the joint frames of 60 synthetic pairs (N ~ 21 k, D = 144): minutes of CPU, so it is
+    stored instead of recomputed by the GPU test.  Covariances are kept as their diagonals plus
+    a fixed random sample of entries (the full array is 10 MB)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from util import oracle_joint_array
+    x, _ = oracle_joint_array(60)
+    resp0 = gmm_ref.kmeans_like_resp(x, 64, 0)
+    ref = gmm_ref.sklearn_em(x, resp0, max_iter=100, tol=1e-3)
+    cov = ref['covariances']
+    idx = np.random.default_rng(20260104).integers(0, cov.size, 20000)
+    np.savez_compressed(os.path.join(HERE, 'em_scale.npz'), n_frames=len(x),
+                        x_checksum=float(x.sum()), labels0=resp0.argmax(1).astype(np.int16),
+                        weights=ref['weights'], means=ref['means'],
+                        cov_diag=np.einsum('kii->ki', cov), cov_idx=idx,
+                        cov_sample=cov.ravel()[idx],
+                        lower_bounds=np.array(ref['lower_bounds']), n_iter=ref['n_iter'],
+                        converged=ref['converged'])
+
+
 if __name__ == '__main__':
-    dtw_cases()
-    em_case()
-    mlpg_case()
+    which = sys.argv[1:] or ['dtw', 'em', 'mlpg', 'em_scale']
+    if 'dtw' in which:
+        dtw_cases()
+    if 'em' in which:
+        em_case()
+    if 'mlpg' in which:
+        mlpg_case()
+    if 'em_scale' in which:
+        em_scale_case()
     print('golden fixtures written to', HERE)
