@@ -60,8 +60,8 @@ void launch_reduce_fixed(const double* in, long long n, double extra, double* ou
 size_t tc_workspace_bytes(long long N, int K, int D);
 int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
                    size_t workspace_bytes, cudaStream_t st);
-int mstats_tc(long long N, int K, int D, const double* resp, const double* centres, double* stats,
-              void* workspace, size_t workspace_bytes, cudaStream_t st);
+int mstats_tc(long long N, const double* X, int K, int D, const double* resp, const double* centres,
+              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
              const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
              void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -833,7 +833,7 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
         return KW_ERR_WORKSPACE;
     }
     if (precision == 1)
-        return mstats_tc(N, K, D, resp_dev, centres_dev, stats_dev,
+        return mstats_tc(N, x_dev, K, D, resp_dev, centres_dev, stats_dev,
                          static_cast<char*>(workspace_dev) + w.bytes, workspace_bytes - w.bytes,
                          st);
     return mstats_fp64(N, x_dev, K, D, resp_dev, centres_dev, w.partial, stats_dev, RESP_FLOOR, st);

@@ -957,6 +957,12 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
     volatile int* gflag = reinterpret_cast<volatile int*>(smem + G.off_flags + 32);       // [2 TMEM stages]
     volatile int* pent = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);        // [2 stages] tile of the entry, -1 = end of item
+    // Per-tile power-of-two weight scale.  A = r (x' - mu') is fp16: with small responsibilities
+    // it drops into the subnormal range and loses its low part, so the producer scales the
+    // tile's weights to max r in [0.5, 1) and the flush multiplies the tile's sums back
+    // (pinv: by B stage, ginv: by TMEM stage; both exact powers of two).
+    volatile float* pinv = reinterpret_cast<volatile float*>(smem + G.off_flags + 16);    // [2 B stages]
+    volatile float* ginv = reinterpret_cast<volatile float*>(smem + G.off_flags + 24);    // [2 TMEM stages]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
     // warp index through a shuffle so the compiler knows the role branches are warp-uniform
@@ -1066,13 +1072,24 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         const int t = tb + __ffs(mask) - 1;
                         mask &= mask - 1;
                         const float f0 = (float)a0, f1 = (float)a1;
+                        const double a0w = a0, a1w = a1;                    // n_k sums the doubles
                         load2(mask ? tb + __ffs(mask) - 1 : -1, a0, a1);   // next non-empty tile
-                        nacc += (double)f0 + (double)f1;
+                        nacc += a0w + a1w;
+                        float fm = fmaxf(f0, f1);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, o));
+                        // fm > 1e-16 (the tile is flagged non-empty): 2^-ex fm in [0.5, 1)
+                        int ex;
+                        (void)frexpf(fm, &ex);
+                        const float up = ldexpf(1.f, -ex);
                         const uint32_t s = g & 1u, u = g >> 1;
                         mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                        *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) = make_float2(f0, f1);
+                        *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) =
+                            make_float2(f0 * up, f1 * up);
                         __syncwarp();
                         if (lane == 0) {
+                            pinv[s] = ldexpf(1.f, ex);
                             pent[s] = t;
                             mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
                             const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
@@ -1140,6 +1157,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const long long c0 = tick<PROF>();
                     mbar_wait(bars + MB_B_FULL + s, u & 1u);
                     const int tt = pent[s];
+                    const float tile_inv = pinv[s];
                     const long long c1 = tick<PROF>();
                     if (cnt == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
                     const long long c2 = tick<PROF>();
@@ -1166,10 +1184,14 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
                     const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
                     if (swap_strides != 1) {      // (1 = timing experiment: no MMAs)
+                    // The accumulator truncates (round toward zero) on every MMA, a loss in
+                    // proportion to what it already holds: the two small cross passes
+                    // (A_hi B_lo, A_lo B_hi; 2^-11 of the main term) go first, so with one tile per
+                    // flush only the four A_hi B_hi MMAs truncate at full magnitude.
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        uint64_t da = (pass == 2) ? a_lo_d : a_hi_d;     // A lo in pass 2
-                        uint64_t db = (pass == 1) ? b_lo_d : b_hi_d;     // B lo in pass 1
+                        uint64_t da = (pass == 1) ? a_lo_d : a_hi_d;     // A lo in pass 1
+                        uint64_t db = (pass == 0) ? b_lo_d : b_hi_d;     // B lo in pass 0
 #pragma unroll
                         for (int ks = 0; ks < MT / 16; ++ks) {
                             const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (cnt > 0 ? 1u : 0u);
@@ -1183,8 +1205,11 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     umma_commit(bars + MB_A_EMPTY + s);
                     umma_commit(bars + MB_B_EMPTY + s);
                     ++cnt;
-                    if (cnt == M_FLUSH) {
-                        if (lane == 0) gflag[ts] = 1;
+                    if (cnt == M_FLUSH) {      // M_FLUSH is 1: the flush undoes this tile's scale
+                        if (lane == 0) {
+                            gflag[ts] = 1;
+                            ginv[ts] = tile_inv;
+                        }
                         __threadfence_block();
                         __syncwarp();
                         umma_commit(bars + MB_TM_FULL + ts);
@@ -1237,6 +1262,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 const long long c0 = tick<PROF>();
                 mbar_wait(bars + MB_B_FULL + s, u & 1u);
                 const int tt = pent[s];
+                const float tile_inv = pinv[s];
                 mbar_wait(bars + MB_A_FULL + s, u & 1u);
                 const long long c1 = tick<PROF>();
                 c_wait += c1 - c0;
@@ -1270,7 +1296,7 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 if (cnt == M_FLUSH || (tt < 0 && cnt > 0)) {
 #pragma unroll
                     for (int i = 0; i < 12; ++i) {
-                        cacc[i * 32 + lane] += acc[i];
+                        cacc[i * 32 + lane] = fmaf(acc[i], tile_inv, cacc[i * 32 + lane]);
                         acc[i] = 0.f;
                     }
                     cnt = 0;
@@ -1436,6 +1462,8 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                 tc_fence_after();
                 const int fl = gflag[ts];         // bit 0: the group holds data, bit 1: last group
                 const bool empty = (fl & 1) == 0;
+                const float inv = empty ? 0.f : ginv[ts];
+                const float2 inv2 = make_float2(inv, inv);
                 const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -1445,9 +1473,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
-                            const float2 t = __fadd2_rn(
-                                make_float2(acc[c][j], acc[c][j + 1]),
-                                make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                            const float2 t = __ffma2_rn(
+                                make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2,
+                                make_float2(acc[c][j], acc[c][j + 1]));
                             acc[c][j] = t.x;
                             acc[c][j + 1] = t.y;
                         }
@@ -1459,9 +1487,9 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        const float2 t = __fadd2_rn(
-                            make_float2(acc[5][j], acc[5][j + 1]),
-                            make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                        const float2 t = __ffma2_rn(
+                            make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2,
+                            make_float2(acc[5][j], acc[5][j + 1]));
                         acc[5][j] = t.x;
                         acc[5][j + 1] = t.y;
                     }
@@ -1516,11 +1544,18 @@ __global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
 
 // Raw sums -> the statistics vector kw_gmm_mstep_finalize expects, centred on centres[k]:
 //   n_k,  sum r (x - c_k),  sum r (x - c_k)(x - c_k)^T   (float64).  grid (K, slices).
+// `gain` undoes the mean truncation loss of the tensor core's fp32 accumulator: every MMA rounds
+// the accumulator toward zero, which on sums of like-signed products (the diagonal, correlated
+// pairs, the first moments around a far centre) is a relative loss of about half an ulp per MMA
+// at the magnitude the accumulator has reached.  With one tile per flush and the cross passes
+// first that is 4 MMAs at 1/4 .. 1 of the tile's sum: -0.7e-7 .. -1.0e-7 relative measured
+// (tools/debug_mstats.py), hence gain = 1 + 0.65 * 2^-23.  Sums of mixed-sign products lose less,
+// but they are small to begin with.
 __global__ void mstats_tc_post_kernel(int K, int D, int DP, const double* __restrict__ raw,
                                       const double* __restrict__ xinfo,
                                       const float* __restrict__ mu32,
                                       const double* __restrict__ centres,
-                                      double* __restrict__ stats) {
+                                      double* __restrict__ stats, double gain) {
     const MstepGeom G = mstep_geom(DP);
     const int k = blockIdx.x;
     const double* sh = raw + (size_t)k * (G.partial_len + 1);
@@ -1528,8 +1563,8 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, const double* __rest
     const double* a2 = sh + 128 * G.N1;
     const double nk = sh[G.partial_len];
     auto sab = [&](int i, int j) -> double {      // needs i < 128 or j >= 128
-        if (i < 128) return a1[i * G.N1 + j];
-        return a2[(i - (DP - 128)) * G.N2 + (j - 128)];
+        if (i < 128) return gain * a1[i * G.N1 + j];
+        return gain * a2[(i - (DP - 128)) * G.N2 + (j - 128)];
     };
     auto mc = [&](int i) -> double { return sab(i, DP); };
     const float* muk = mu32 + (size_t)k * G.DA;
@@ -1737,8 +1772,8 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
 }
 
 // M-step statistics on the tensor cores (frames packed by pack_frames_tc).
-int mstats_tc(long long N, int K, int D, const double* resp, const double* centres, double* stats,
-              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int mstats_tc(long long N, const double* X, int K, int D, const double* resp, const double* centres,
+              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     TcWorkspace w;
     int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
     if (rc != KW_OK) return rc;
@@ -1760,12 +1795,11 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
             N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags);
         KW_CUDA_CHECK(cudaGetLastError());
     }
-    static int swap_strides = -1, m_flush = 2;
+    static int swap_strides = -1;
+    const int m_flush = 1;     // one tile per TMEM flush: the flush carries the tile's weight scale
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
         swap_strides = e != nullptr ? atoi(e) : 0;
-        const char* f = getenv("KW_TC_MFLUSH");   // tiles accumulated in TMEM between flushes
-        if (f != nullptr && atoi(f) > 0) m_flush = atoi(f);
     }
     static unsigned long long* prof_dev = nullptr;
     static int prof_on = -1;
@@ -1793,7 +1827,7 @@ int mstats_tc(long long N, int K, int D, const double* resp, const double* centr
         K, G.partial_len, w.m_chunks, w.mpartial, w.npartial, w.mraw);
     KW_CUDA_CHECK(cudaGetLastError());
     tc::mstats_tc_post_kernel<<<dim3(K, 8), 256, 0, st>>>(K, D, DP, w.mraw, w.xinfo, w.mu32,
-                                                          centres, stats);
+                                                          centres, stats, 1.0 + 0.65 / 8388608.0);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }

@@ -21,7 +21,26 @@ import numpy as np
 from . import _lib
 from .delta import DELTA_WINDOWS, check_windows
 
-PRECISIONS = {'fp64': 0, 'tc': 1, 0: 0, 1: 1}
+PRECISIONS = {'fp64': 0, 'tc': 1, 0: 0, 1: 1, 'auto': -1}
+TC_MAX_DIM = 144          # the tcgen05 kernels hold one frame row of <= 144 features
+TC_MIN_FRAMES_PER_DIM = 8
+
+
+def resolve_precision(precision, n_frames, n_components, dim):
+    """'auto' -> the tensor-core path when the fit is large enough to need it and well enough
+    determined for it.  The split-fp16 statistics carry a relative error of about 1e-7 of
+    ||Sigma_k||; what the next E-step sees is that error times the condition number of Sigma_k,
+    and a component estimated from only a few frames per dimension is ill-conditioned by
+    construction.  With at least TC_MIN_FRAMES_PER_DIM frames per component and dimension on
+    average (configs[1]: 176 k frames, K = 64, D = 144 -> 19) the fit stays within the 1e-5
+    tolerance; below that the problem is also small enough for the FP64 CUDA-core kernels
+    (N < 8 K D frames)."""
+    code = PRECISIONS[precision]
+    if code >= 0:
+        return code
+    if dim > TC_MAX_DIM:
+        return 0
+    return 1 if n_frames >= TC_MIN_FRAMES_PER_DIM * n_components * dim else 0
 
 
 class ConvergenceWarning(UserWarning):
@@ -42,7 +61,7 @@ class GaussianMixture:
     def __init__(self, n_components=1, covariance_type='full', tol=1e-3, reg_covar=1e-6,
                  max_iter=100, n_init=1, init_params='kmeans', weights_init=None,
                  means_init=None, precisions_init=None, random_state=None, warm_start=False,
-                 verbose=0, verbose_interval=10, precision='fp64', resp_init=None,
+                 verbose=0, verbose_interval=10, precision='auto', resp_init=None,
                  process_group=None, device=None, reorder_every=10):
         if covariance_type != 'full':
             raise NotImplementedError("only covariance_type='full' is built "
@@ -63,7 +82,8 @@ class GaussianMixture:
         self.random_state = random_state
         self.verbose = verbose
         self.verbose_interval = verbose_interval
-        self.precision = PRECISIONS[precision]
+        self.precision_request = precision
+        self.precision = PRECISIONS[precision]      # -1 ('auto') until the frames are seen
         self.resp_init = resp_init
         self.process_group = process_group
         self.device = device
@@ -76,6 +96,9 @@ class GaussianMixture:
         self._x_src = None
         self._x_used = None
         self._iters_done = 0
+        # per-stage precision (diagnostics: tools/tc_error_split.py); a precision-1 workspace
+        # also holds what the FP64 kernels need
+        self._precision_e = self._precision_m = self.precision
 
     # ------------------------------------------------------------------ device plumbing
     def _alloc(self, torch, n, d, dev):
@@ -129,7 +152,7 @@ class GaussianMixture:
         rc = _lib.lib().kw_gmm_estep(
             n, x.data_ptr(), self.n_components, d, self._means[self._cur].data_ptr(),
             self._pc.data_ptr(), self._aux.data_ptr(), self._resp.data_ptr(),
-            self._stats.data_ptr(), self.precision, self._ws.data_ptr(), self._ws_bytes,
+            self._stats.data_ptr(), self._precision_e, self._ws.data_ptr(), self._ws_bytes,
             _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_estep')
 
@@ -138,7 +161,7 @@ class GaussianMixture:
         n, d = x.shape
         rc = _lib.lib().kw_gmm_mstep_accumulate(
             n, x.data_ptr(), self.n_components, d, self._resp.data_ptr(), centres.data_ptr(),
-            self._stats.data_ptr(), self.precision, self._ws.data_ptr(), self._ws_bytes,
+            self._stats.data_ptr(), self._precision_m, self._ws.data_ptr(), self._ws_bytes,
             _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_mstep_accumulate')
 
@@ -204,6 +227,15 @@ class GaussianMixture:
         if self.process_group is None and n < k:
             raise ValueError('Expected n_samples >= n_components '
                              f'but got n_components = {k}, n_samples = {n}')
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size(self.process_group) > 1
+        count = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+        if multi:
+            dist.all_reduce(count, group=self.process_group)
+        if self.precision_request == 'auto':
+            self.precision = resolve_precision('auto', int(count.item()), k, d)
+            self._precision_e = self._precision_m = self.precision
         self._alloc(torch, n, d, dev)
         self._x_src, self._x_used, self._iters_done = x, None, 0
         if self.verbose:
@@ -215,12 +247,8 @@ class GaussianMixture:
         else:
             self._pack(torch, x)
         centre = x.sum(dim=0, keepdim=True)
-        count = torch.tensor([float(n)], dtype=torch.float64, device=dev)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and \
-                dist.get_world_size(self.process_group) > 1:
+        if multi:
             dist.all_reduce(centre, group=self.process_group)
-            dist.all_reduce(count, group=self.process_group)
         centres0 = (centre / count).expand(k, d).contiguous()
         self._stats.zero_()
         self._stats[-1] = float(n)
@@ -340,6 +368,8 @@ class GaussianMixture:
         self._resp = torch.empty((k, self._npad), dtype=torch.float64, device=x.device)
         self._stats = torch.zeros(lib.kw_gmm_stats_len(k, d), dtype=torch.float64,
                                   device=x.device)
+        if self.precision < 0:      # 'auto' on a model that was loaded, not fitted: FP64 posteriors
+            self.precision = self._precision_e = self._precision_m = 0
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=x.device)
         self._pack(torch, x)
@@ -398,8 +428,10 @@ class B200GMMFeatureConverter(FeatureConverter):
         key = (bool(diff), bool(mlpg))
         if key not in self._paramgen:
             windows = DELTA_WINDOWS if mlpg else DELTA_WINDOWS[0:1]   # gmm.py:29-31
+            # 'auto': the tensor-core posterior re-checks near-ties in FP64, so the mixture
+            # sequence (and with it the FP64 MLPG output) is the FP64 one at any size
             self._paramgen[key] = MLPG(self.gmm, windows=windows, diff=diff,
-                                       precision=self.gmm.precision)
+                                       precision=self.gmm.precision_request)
         return self._paramgen[key]
 
     def convert(self, feature, mlpg=True, diff=False):

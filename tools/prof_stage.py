@@ -20,7 +20,8 @@ from kwiiyatta_b200.mlpg import MLPG  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('stage', choices=['em', 'dtw', 'dtw_long', 'convert'])
+    ap.add_argument('stage', choices=['em', 'em_real', 'dtw', 'dtw_long', 'convert'])
+    ap.add_argument('--iters', type=int, default=12)
     ap.add_argument('--precision', default='tc')
     ap.add_argument('--reps', type=int, default=2)
     ap.add_argument('--pairs', type=int, default=503)
@@ -44,6 +45,27 @@ def main():
         yd = torch.from_numpy(np.concatenate([y for _, y in feats])).to(dev)
         for _ in range(a.reps):
             kfd.fastdtw_batch_device(xd, yd, tx, ty, radius=radius, dist=2)
+        torch.cuda.synchronize()
+    elif a.stage == 'em_real':
+        # the bench workload itself: joint frames of 503 pairs, labels from 5 Lloyd passes
+        from kwiiyatta_b200 import kmeans
+        kw.set_pad_silence(lambda f, n: f)
+        pairs = [synth.make_padded_pair(i) for i in range(a.pairs)]
+        x = kw.joint_array_from_pairs(pairs, pad_silence=True, pad_len=synth.PAD_LEN)
+        n, k = len(x), 64
+        xd0 = torch.from_numpy(x).to(dev)
+        lab = kmeans.kmeans_labels(xd0, k, seed=0, n_lloyd=5)
+        resp0 = torch.zeros((n, k), dtype=torch.float64, device=dev)
+        resp0[torch.arange(n, device=dev), lab] = 1.0
+        gm = kw.GaussianMixture(n_components=k, max_iter=1, tol=0.0, resp_init=resp0,
+                                precision=a.precision, device=dev)
+        xd = gm.initialize(xd0)
+        for _ in range(a.iters):
+            gm.em_iteration(xd)
+        torch.cuda.synchronize()
+        print('PROFILE MARK')
+        for _ in range(a.reps):
+            gm.em_iteration(xd)
         torch.cuda.synchronize()
     elif a.stage == 'em':
         rng = np.random.default_rng(0)
