@@ -24,6 +24,7 @@ from .delta import DELTA_WINDOWS, check_windows
 PRECISIONS = {'fp64': 0, 'tc': 1, 0: 0, 1: 1, 'auto': -1}
 TC_MAX_DIM = 144          # the tcgen05 kernels hold one frame row of <= 144 features
 TC_MIN_FRAMES_PER_DIM = 8
+TC_MIN_WORK = 2e10        # N K D^2 below which the FP64 kernels take about a millisecond anyway
 
 
 def resolve_precision(precision, n_frames, n_components, dim):
@@ -34,13 +35,15 @@ def resolve_precision(precision, n_frames, n_components, dim):
     construction.  With at least TC_MIN_FRAMES_PER_DIM frames per component and dimension on
     average (configs[1]: 176 k frames, K = 64, D = 144 -> 19) the fit stays within the 1e-5
     tolerance; below that the problem is also small enough for the FP64 CUDA-core kernels
-    (N < 8 K D frames)."""
+    (N < 8 K D frames), and so is anything under TC_MIN_WORK."""
     code = PRECISIONS[precision]
     if code >= 0:
         return code
     if dim > TC_MAX_DIM:
         return 0
-    return 1 if n_frames >= TC_MIN_FRAMES_PER_DIM * n_components * dim else 0
+    enough_frames = n_frames >= TC_MIN_FRAMES_PER_DIM * n_components * dim
+    enough_work = float(n_frames) * n_components * dim * dim >= TC_MIN_WORK
+    return 1 if enough_frames and enough_work else 0
 
 
 class ConvergenceWarning(UserWarning):

@@ -18,6 +18,7 @@ ORDER = 24
 PAD_LEN = 100
 FS = 16000
 FRAME_PERIOD = 5
+SPECTRUM_LEN = 33
 
 
 class SynthFeature:
@@ -46,6 +47,15 @@ class SynthFeature:
         return self.mel_cepstrum.order
 
     @property
+    def spectrum_envelope(self):
+        """Stand-in spectrum: the mel-cepstrum zero-padded to SPECTRUM_LEN columns (only its
+        all-zero trailing frames matter to the path: TrimmedDataset,
+        kwiiyatta/converter/dataset.py:49-52)."""
+        out = np.zeros((len(self.f0), SPECTRUM_LEN))
+        out[:, :self.mel_cepstrum.data.shape[1]] = self.mel_cepstrum.data
+        return out
+
+    @property
     def frame_len(self):
         return len(self.f0)
 
@@ -62,6 +72,21 @@ class SynthFeature:
             raise TypeError('SynthFeature supports slice / index-array access only')
         return SynthFeature(self.mel_cepstrum.data[key], self.f0[key], self.is_voiced[key],
                             self.fs, self.frame_period)
+
+
+def feature(f):
+    """Stand-in for ``kwiiyatta.feature(Feature)``: an independent copy."""
+    return SynthFeature(f.mel_cepstrum.data.copy(), f.f0.copy(), f.is_voiced.copy(), f.fs,
+                        f.frame_period)
+
+
+def resample(mel_cepstrum, fs):
+    """Stand-in for ``kwiiyatta.resample``: synthetic features exist at one rate only."""
+    if fs != mel_cepstrum.fs:
+        raise ValueError('synthetic mel-cepstra cannot be resampled (feature producer is out '
+                         'of scope)')
+    import copy
+    return copy.copy(mel_cepstrum)
 
 
 def pad_silence(feature, frame_len=PAD_LEN, rng=None):
