@@ -99,18 +99,24 @@ def test_reordering_does_not_change_the_fit(cuda, joint60, reorder_every):
 
 @pytest.mark.parametrize('reorder_every', [0, 1, 3])
 def test_reordering_medium_dim(cuda, reorder_every):
-    """20 k x 48, K = 16: several re-sorts inside one fit, soft posteriors (overlapping blobs)."""
+    """20 k x 48, K = 16, one component per (overlapping) cluster: soft posteriors, several
+    re-sorts inside one fit, every component well determined (1 250 frames in 48 dimensions,
+    cond(Sigma_k) ~ 4e2) -- held to TOL itself.  (With the 0.3-noise mixing matrices of
+    ``_blobs`` cond(Sigma_k) reaches 4e6 and the 1e-7 statistics error of the tensor cores,
+    times that, is visible in the likelihood: tools/debug_estep.py.)"""
     rng = np.random.default_rng(11)
-    x = _blobs(rng, 20000, 48, 16, sep=0.6)
-    resp0 = gmm_ref.kmeans_like_resp(x, 16, 1)
+    centres = rng.standard_normal((16, 48)) * 0.4
+    lab = rng.integers(0, 16, 20000)
+    a = rng.standard_normal((16, 48, 48)) * 0.1 + np.eye(48)
+    x = centres[lab] + np.einsum('nij,nj->ni', a[lab], rng.standard_normal((20000, 48)))
+    resp0 = np.zeros((20000, 16))
+    resp0[np.arange(20000), lab] = 1.0
     ref = gmm_ref.sklearn_em(x, resp0, max_iter=8, tol=0.0)
     gm = _fit(x, resp0, max_iter=8, tol=0.0, precision='tc', reorder_every=reorder_every)
-    # components overlap and some share a cluster: held to the backward-error statement
-    _assert_fit_close(gm, ref, TOL, _backward_error_allowance(x, resp0, ref, max_iter=8, tol=0.0))
-    # one iteration of the same problem (kernel accuracy without the dynamics) is inside TOL
-    ref1 = gmm_ref.numpy_em(x, resp0, max_iter=1, tol=0.0)
-    gm1 = _fit(x, resp0, max_iter=1, tol=0.0, precision='tc', reorder_every=reorder_every)
-    _assert_fit_close(gm1, ref1, TOL)
+    _assert_fit_close(gm, ref, TOL)
+    soft = np.exp(gmm_ref.e_step(x, ref['weights'], ref['means'],
+                                 ref['precisions_cholesky'])[1])
+    assert ((soft > 1e-3) & (soft < 0.999)).sum() > 100        # the posteriors really are soft
 
 
 def test_eight_iterations_backward_error(cuda):
