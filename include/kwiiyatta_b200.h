@@ -53,6 +53,12 @@ int kw_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
  *   precision : 0 = fp64 exact (paths bit-exact to the oracle), 1 = fp32 local distances
  *               (direct differences and sqrt in fp32, DP sums in fp64; path cost within 1e-6
  *               relative of the fp64 result, paths may differ on near-ties).
+ *   tie_mode  : which of fastdtw 0.3.2's two back-ends decides between equal candidates:
+ *               0 = pure Python (fastdtw.py: candidates compared after the local distance is
+ *               added, first minimum in the order (i-1,j), (i,j-1), (i-1,j-1));
+ *               1 = Cython (_fastdtw.pyx as recalled in SURVEY.md 8a: predecessors compared
+ *               before the addition, the diagonal wins ties, then (i,j-1), then (i-1,j)).
+ *               The two give the same path whenever margin_dev (below) is above rounding.
  * Outputs (device):
  *   cost_dev[n_pairs]            accumulated distance D[tx][ty];
  *   path_dev                     int32 (i, j) pairs; pair p owns the region of (tx[p]+ty[p]) points
@@ -61,15 +67,23 @@ int kw_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
  *   path_begin_dev[n_pairs]      index (within the region) of the first path point;
  *   path_len_dev[n_pairs]        number of path points;
  *   cells_dev[n_pairs]           window cells evaluated, summed over resolution levels (may be NULL).
+ *   margin_dev[2 * n_pairs]      (may be NULL; precision 0 only) smallest decision margin on the
+ *                                returned path: at every cell of the path, the runner-up minus
+ *                                the winner among the values the cell rule compared (+inf where
+ *                                only one predecessor exists).  [2p] = finest level (the returned
+ *                                path itself), [2p+1] = minimum over all resolution levels (the
+ *                                coarser paths only shape the search window).  A margin far above
+ *                                the rounding of the sums (1e-13 relative) means the path does not
+ *                                depend on the tie order or on the last bit of a local distance.
  * ------------------------------------------------------------------------------------------ */
 size_t kw_dtw_workspace_bytes(int n_pairs, const int32_t* tx_host, const int32_t* ty_host,
                               int feat_dim, int radius);
 
 int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_dev,
                  const int32_t* tx_host, const int32_t* ty_host, int feat_dim,
-                 int radius, int p_norm, int precision,
+                 int radius, int p_norm, int precision, int tie_mode,
                  double* cost_dev, int32_t* path_dev, int32_t* path_begin_dev,
-                 int32_t* path_len_dev, int64_t* cells_dev,
+                 int32_t* path_len_dev, int64_t* cells_dev, double* margin_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

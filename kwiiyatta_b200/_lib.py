@@ -23,8 +23,8 @@ SIGNATURES = {
     'kw_last_error': (_c.c_char_p, []),
     'kw_device_info': (_i, [_i, _vp, _vp, _vp, _vp]),
     'kw_dtw_workspace_bytes': (_sz, [_i, _vp, _vp, _i, _i]),
-    'kw_dtw_batch': (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
-                          _vp, _sz, _vp]),
+    'kw_dtw_batch': (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                          _vp, _vp, _sz, _vp]),
     'kw_delta_features': (_i, [_i, _vp, _i64, _i, _vp, _vp, _vp]),
     'kw_gmm_stats_len': (_sz, [_i, _i]),
     'kw_gmm_resp_len': (_sz, [_i64, _i]),

@@ -44,7 +44,7 @@ __global__ void delta_kernel(int n_utts, const int64_t* __restrict__ off, long l
 
 using namespace kw;
 
-extern "C" int kw_abi_version(void) { return 1; }
+extern "C" int kw_abi_version(void) { return 2; }
 
 extern "C" const char* kw_last_error(void) { return g_error; }
 

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include <climits>
+#include <limits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -76,19 +77,10 @@ struct DtwPlan {
 // 2 * (span of the coarser path over 2 radius + 1 rows) + 4 radius + 2 columns wide: 8 radius + 2
 // for a diagonal path; wider ones spill into the sweep's inline path.
 static int dist_wcap(int radius) { return radius < 0 ? 0 : std::max(64, 12 * radius + 16); }
-static bool split_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("KW_DTW_SPLIT");
-        v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
-    }
-    return v != 0;
-}
-
 static int make_plan(int n_pairs, const int32_t* tx, const int32_t* ty, int radius, int F,
                      DtwPlan& plan) {
     plan.descs.resize(n_pairs);
-    plan.wcap = split_enabled() ? dist_wcap(radius) : 0;
+    plan.wcap = dist_wcap(radius);
     long long xrow = 0, yrow = 0, path = 0;
     for (int p = 0; p < n_pairs; ++p) {
         PairDesc& d = plan.descs[p];
@@ -167,6 +159,7 @@ struct DtwWorkspace {
     int* rowj;
     uint32_t* bp;
     double* brow;
+    double* browm;     // running margins of the boundary rows (margin variants only)
     double2* dist;
     int2* win;
     size_t bytes;
@@ -182,6 +175,7 @@ static DtwWorkspace carve(const DtwPlan& plan, void* base) {
     w.rowj = c.take<int>(plan.n_rowj + 1);
     w.bp = c.take<uint32_t>(plan.n_bp);
     w.brow = c.take<double>(plan.n_brow);
+    w.browm = c.take<double>(plan.n_brow);
     w.dist = c.take<double2>(plan.n_dist);
     w.win = c.take<int2>(plan.n_win + 1);
     w.bytes = align_up(c.used, 256);
@@ -264,23 +258,68 @@ __device__ __forceinline__ double dist_fin(float s) {
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 
+// One DP cell.  TIE = 0: fastdtw's pure-Python back-end -- the three candidates are compared
+// AFTER the local distance is added and the first minimum wins in the order up (i-1, j), left
+// (i, j-1), diagonal.  TIE = 1: the order of its Cython back-end as recalled in SURVEY.md
+// section 8a -- the predecessors are compared BEFORE the addition and the diagonal wins ties,
+// then left, then up.  Back-pointer codes: 0 = up, 1 = left, 2 = diagonal.
+// MARGIN: also the decision margin (runner-up minus winner among the compared values, +inf with
+// a single finite candidate) and its running minimum along the winning path, so that
+// m(tx-1, ty-1) is the smallest margin of any decision ON THE RETURNED PATH: when it is far above
+// the rounding of the sums, neither the tie order nor the last-bit rounding of the local
+// distances can change the path.
+template <int TIE, bool MARGIN>
+__device__ __forceinline__ void dtw_cell(double up, double left, double diag, double dt,
+                                         double mup, double mleft, double mdiag, double& v,
+                                         uint32_t& code, double& m) {
+    double cu, cl, cd;
+    if (TIE == 0) {
+        cu = __dadd_rn(up, dt);
+        cl = __dadd_rn(left, dt);
+        cd = __dadd_rn(diag, dt);
+        v = cu;
+        code = 0u;
+        if (cl < v) { v = cl; code = 1u; }
+        if (cd < v) { v = cd; code = 2u; }
+    } else {
+        cu = up;
+        cl = left;
+        cd = diag;
+        double best = cd;
+        code = 2u;
+        if (cl < best) { best = cl; code = 1u; }
+        if (cu < best) { best = cu; code = 0u; }
+        v = __dadd_rn(best, dt);
+    }
+    if (MARGIN) {
+        const double win = code == 0u ? cu : (code == 1u ? cl : cd);
+        const double other = code == 0u ? fmin(cl, cd) : (code == 1u ? fmin(cu, cd) : fmin(cu, cl));
+        const double here = (win < CUDART_INF) ? other - win : CUDART_INF;
+        const double along = code == 0u ? mup : (code == 1u ? mleft : mdiag);
+        m = fmin(here, along);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Windowed DP for one resolution level.
 // ---------------------------------------------------------------------------------------
-template <int FP, int NT, int P, typename T>
+template <int FP, int NT, int P, typename T, int TIE, bool MARGIN>
 __global__ void __launch_bounds__(NT)
 dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
               int radius, int F, const double* __restrict__ xpyr,
               const double* __restrict__ ypyr, const int* __restrict__ rowj,
               uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost,
-              unsigned long long* __restrict__ cells, int only_full) {
+              unsigned long long* __restrict__ cells, int only_full,
+              double* __restrict__ browm, double* __restrict__ margin) {
     constexpr int CH = NT;
     constexpr int RING = 2 * NT;
     constexpr int RS = RING + 1;
     extern __shared__ double smem[];
     double* xch = smem;            // 2 * NT: lower-row D values, double-buffered by step parity
     double* brs = xch + 2 * NT;    // RING: previous strip's last row, staged with the y ring
-    T* ys = reinterpret_cast<T*>(brs + RING);   // FP * RS, k-major ring of y columns
+    double* xchm = brs + RING;     // MARGIN: the same two exchanges for the running margins
+    double* brsm = xchm + (MARGIN ? 2 * NT : 0);
+    T* ys = reinterpret_cast<T*>(brsm + (MARGIN ? RING : 0));   // FP * RS, k-major ring of y columns
     __shared__ unsigned long long cell_count;
 
     const int pair = order[blockIdx.x];
@@ -298,6 +337,7 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
     const int tiles_x = (ty + 15) >> 4;
     uint32_t* bp_pair = bp + d.bp_off;
     double* brow_pair = brow + d.brow_off;
+    double* browm_pair = MARGIN ? browm + d.brow_off : nullptr;
     const double INF = CUDART_INF;
 
     auto window = [&](int a, int& lo, int& hi) {
@@ -342,17 +382,24 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
         if (i0 > 0) window(i0 - 1, plo, phi);
         const double* brow_in = brow_pair + ((strip & 1) ? 0 : ty);
         double* brow_out = brow_pair + ((strip & 1) ? ty : 0);
+        const double* browm_in = MARGIN ? browm_pair + ((strip & 1) ? 0 : ty) : nullptr;
+        double* browm_out = MARGIN ? browm_pair + ((strip & 1) ? ty : 0) : nullptr;
         const bool writes_boundary = (t == NT - 1) && (i0 + 2 * NT < tx);
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
+        double ma_prev = INF, mb_prev = INF, mdiag_in = INF;
         if (t == 0) {
             const int jm = jstart - 1;
-            if (i0 == 0)
+            if (i0 == 0) {
                 diag_in = (jm == -1) ? 0.0 : INF;  // virtual origin D[0][0] = 0
-            else
-                diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
+            } else {
+                const bool in = jm >= plo && jm <= phi;
+                diag_in = in ? __ldcg(brow_in + jm) : INF;
+                if (MARGIN) mdiag_in = in ? __ldcg(browm_in + jm) : INF;
+            }
         }
         xch[NT + t] = INF;  // parity 1 is read at step 0
+        if (MARGIN) xchm[NT + t] = INF;
         uint32_t wa = 0u, wb = 0u;
         __syncthreads();
 
@@ -366,17 +413,21 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
                 }
                 {
                     const int j = jbase + t;
-                    brs[j & (RING - 1)] =
-                        (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                    const bool in = i0 > 0 && j >= plo && j <= phi;
+                    brs[j & (RING - 1)] = in ? __ldcg(brow_in + j) : INF;
+                    if (MARGIN) brsm[j & (RING - 1)] = in ? __ldcg(browm_in + j) : INF;
                 }
                 __syncthreads();
             }
             const int j = jstart + s - t;
             const double up_in =
                 (t == 0) ? brs[j & (RING - 1)] : xch[((s + 1) & 1) * NT + t - 1];
+            double mup_in = INF;
+            if (MARGIN)
+                mup_in = (t == 0) ? brsm[j & (RING - 1)] : xchm[((s + 1) & 1) * NT + t - 1];
             const bool act_a = (j >= loa) && (j <= hia);
             const bool act_b = (j >= lob) && (j <= hib);
-            double va = INF, vb = INF;
+            double va = INF, vb = INF, ma = INF, mb = INF;
             if (act_a || act_b) {
                 T sa = (T)0, sb = (T)0;
                 const T* yp = ys + (j & (RING - 1));
@@ -388,38 +439,51 @@ dtw_dp_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order,
                 }
                 if (act_a) {
                     const double dt = dist_fin<P>(sa);
-                    double best = __dadd_rn(up_in, dt);
-                    uint32_t code = 0u;
-                    double c = __dadd_rn(va_prev, dt);
-                    if (c < best) { best = c; code = 1u; }
-                    c = __dadd_rn(diag_in, dt);
-                    if (c < best) { best = c; code = 2u; }
-                    va = best;
+                    uint32_t code;
+                    dtw_cell<TIE, MARGIN>(up_in, va_prev, diag_in, dt, mup_in, ma_prev, mdiag_in,
+                                          va, code, ma);
                     wa |= code << (2 * (j & 15));
                     if ((j & 15) == 15 || j == hia) { bp_pair[bp_word(ia, j, tiles_x)] = wa; wa = 0u; }
-                    if (ia == tx - 1 && j == ty - 1) cost[pair] = va;
+                    if (ia == tx - 1 && j == ty - 1) {
+                        cost[pair] = va;
+                        if (MARGIN) {
+                            if (level == 0) margin[2 * pair] = ma;
+                            margin[2 * pair + 1] = fmin(margin[2 * pair + 1], ma);
+                        }
+                    }
                     ++my_cells;
                 }
                 if (act_b) {
                     const double dt = dist_fin<P>(sb);
-                    double best = __dadd_rn(va, dt);
-                    uint32_t code = 0u;
-                    double c = __dadd_rn(vb_prev, dt);
-                    if (c < best) { best = c; code = 1u; }
-                    c = __dadd_rn(va_prev, dt);
-                    if (c < best) { best = c; code = 2u; }
-                    vb = best;
+                    uint32_t code;
+                    dtw_cell<TIE, MARGIN>(va, vb_prev, va_prev, dt, ma, mb_prev, ma_prev, vb, code,
+                                          mb);
                     wb |= code << (2 * (j & 15));
                     if ((j & 15) == 15 || j == hib) { bp_pair[bp_word(ib, j, tiles_x)] = wb; wb = 0u; }
-                    if (ib == tx - 1 && j == ty - 1) cost[pair] = vb;
-                    if (writes_boundary) __stcg(brow_out + j, vb);
+                    if (ib == tx - 1 && j == ty - 1) {
+                        cost[pair] = vb;
+                        if (MARGIN) {
+                            if (level == 0) margin[2 * pair] = mb;
+                            margin[2 * pair + 1] = fmin(margin[2 * pair + 1], mb);
+                        }
+                    }
+                    if (writes_boundary) {
+                        __stcg(brow_out + j, vb);
+                        if (MARGIN) __stcg(browm_out + j, mb);
+                    }
                     ++my_cells;
                 }
             }
             xch[(s & 1) * NT + t] = vb;
+            if (MARGIN) xchm[(s & 1) * NT + t] = mb;
             va_prev = va;
             vb_prev = vb;
             diag_in = up_in;
+            if (MARGIN) {
+                ma_prev = ma;
+                mb_prev = mb;
+                mdiag_in = mup_in;
+            }
             __syncthreads();
         }
     }
@@ -539,23 +603,26 @@ __device__ __noinline__ double slow_dist(const double* __restrict__ xT,
 // ring filled by cp.async 24 steps ahead (the slices were just written by dtw_dist_kernel and
 // mostly live in DRAM).
 // ---------------------------------------------------------------------------------------
-template <int P, typename T>
+template <int P, typename T, int TIE, bool MARGIN>
 __global__ void __launch_bounds__(32 * DPW_NW)
 dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order, int level,
                int F, int wcap, const double* __restrict__ xpyr, const double* __restrict__ ypyr,
                const int2* __restrict__ win, const double2* __restrict__ dist,
-               uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost) {
+               uint32_t* __restrict__ bp, double* __restrict__ brow, double* __restrict__ cost,
+               double* __restrict__ browm, double* __restrict__ margin) {
     constexpr int RD = 16, PD = 12;       // ring slots per lane, prefetch distance (steps)
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ double2 ring_all[DPW_NW][RD][32];   // local distances in flight: [step % RD][lane]
     __shared__ unsigned long long prog_s[DPW_NB];  // (strip << 32 | last finished boundary column + 1)
     __shared__ double bch_all[DPW_NW][32];         // boundary-row chunk of each warp, for its lane 0
+    __shared__ double bchm_all[MARGIN ? DPW_NW : 1][32];   // ... and its running margins
     const int pair = order[blockIdx.x];
     const PairDesc& d = descs[pair];
     if (level >= d.nlev - 1) return;
     const int t = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2 (*ring)[32] = ring_all[warp];
     double* bch = bch_all[warp];
+    double* bchm = bchm_all[MARGIN ? warp : 0];
     volatile unsigned long long* prog = prog_s;
     if (threadIdx.x < DPW_NB) prog_s[threadIdx.x] = 0ull;
     __syncthreads();
@@ -567,6 +634,7 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
     const int tiles_x = (ty + 15) >> 4;
     uint32_t* bp_pair = bp + d.bp_off;
     double* brow_pair = brow + d.brow_off;
+    double* browm_pair = MARGIN ? browm + d.brow_off : nullptr;
     const double INF = CUDART_INF;
 
     // Strips are pipelined over the CTA's warps: warp w takes strips w, w + NW, ...; strip k
@@ -599,6 +667,9 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         }
         const double* brow_in = brow_pair + (size_t)((strip + DPW_NB - 1) % DPW_NB) * ty;
         double* brow_out = brow_pair + (size_t)(strip % DPW_NB) * ty;
+        const double* browm_in =
+            MARGIN ? browm_pair + (size_t)((strip + DPW_NB - 1) % DPW_NB) * ty : nullptr;
+        double* browm_out = MARGIN ? browm_pair + (size_t)(strip % DPW_NB) * ty : nullptr;
         const bool writes_boundary = (t == 31) && (i0 + 64 < tx);
         volatile unsigned long long* prog_in = prog + (strip + DPW_NB - 1) % DPW_NB;
         volatile unsigned long long* prog_out = prog + strip % DPW_NB;
@@ -649,18 +720,23 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         };
 
         double va_prev = INF, vb_prev = INF, diag_in = INF;
+        double ma_prev = INF, mb_prev = INF, mdiag_in = INF;
         wait_boundary(jstart + 31);
         if (t == 0) {
             const int jm = jstart - 1;
-            if (i0 == 0)
+            if (i0 == 0) {
                 diag_in = (jm == -1) ? 0.0 : INF;  // virtual origin D[0][0] = 0
-            else
-                diag_in = (jm >= plo && jm <= phi) ? __ldcg(brow_in + jm) : INF;
+            } else {
+                const bool in = jm >= plo && jm <= phi;
+                diag_in = in ? __ldcg(brow_in + jm) : INF;
+                if (MARGIN) mdiag_in = in ? __ldcg(browm_in + jm) : INF;
+            }
         }
         unsigned long long qa = 0ull, qb = 0ull;
         double ha[4], hb[4];                  // D of the last four steps (for the final cell)
+        double hma[4], hmb[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ha[q] = hb[q] = INF;
+        for (int q = 0; q < 4; ++q) ha[q] = hb[q] = hma[q] = hmb[q] = INF;
         int e_done = -1;                      // last column group already stored
         __syncwarp();                         // the previous strip's reads of the ring are done
 #pragma unroll
@@ -676,8 +752,10 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
                 // staged for lane 0
                 if (s0 > 0) wait_boundary(jstart + s0 + 31);
                 const int j = jstart + s0 + t;
+                const bool in = i0 > 0 && j >= plo && j <= phi;
                 __syncwarp();
-                bch[t] = (i0 > 0 && j >= plo && j <= phi) ? __ldcg(brow_in + j) : INF;
+                bch[t] = in ? __ldcg(brow_in + j) : INF;
+                if (MARGIN) bchm[t] = in ? __ldcg(browm_in + j) : INF;
                 __syncwarp();
             }
             asm volatile("cp.async.wait_group %0;" ::"n"(PD / 4 - 1) : "memory");
@@ -686,43 +764,47 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
             asm volatile("cp.async.commit_group;" ::: "memory");
             // this iteration's distances and (for lane 0) boundary values, ahead of the chain
             const unsigned slot0 = ring_base + ((unsigned)(s0 & (RD - 1)) << 9);
-            double da[4], db[4], bq[4];
+            double da[4], db[4], bq[4], bqm[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(da[q]), "=d"(db[q])
                              : "r"(slot0 + (unsigned)q * 512u) : "memory");
                 bq[q] = bch[(s0 + q) & 31];
+                bqm[q] = MARGIN ? bchm[(s0 + q) & 31] : INF;
             }
             const int cbase = col0 + s0;              // window-relative column of step s0
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 double up_in = __shfl_up_sync(FULL, vb_prev, 1);
                 up_in = (t == 0) ? bq[q] : up_in;
-                // row a
-                double best = __dadd_rn(up_in, da[q]);
-                double cnd = __dadd_rn(va_prev, da[q]);
-                const bool a1 = cnd < best;
-                best = a1 ? cnd : best;
-                cnd = __dadd_rn(diag_in, da[q]);
-                const bool a2 = cnd < best;
-                const double va = a2 ? cnd : best;
-                qa = (qa >> 2) | ((unsigned long long)(a2 ? 2u : (a1 ? 1u : 0u)) << 62);
-                // row b
-                best = __dadd_rn(va, db[q]);
-                cnd = __dadd_rn(vb_prev, db[q]);
-                const bool b1 = cnd < best;
-                best = b1 ? cnd : best;
-                cnd = __dadd_rn(va_prev, db[q]);
-                const bool b2 = cnd < best;
-                const double vb = b2 ? cnd : best;
-                qb = (qb >> 2) | ((unsigned long long)(b2 ? 2u : (b1 ? 1u : 0u)) << 62);
-                if (writes_boundary && (unsigned)(cbase + q) < (unsigned)width)
+                double mup_in = INF;
+                if (MARGIN) {
+                    mup_in = __shfl_up_sync(FULL, mb_prev, 1);
+                    mup_in = (t == 0) ? bqm[q] : mup_in;
+                }
+                double va, vb, ma = INF, mb = INF;
+                uint32_t ca, cb;
+                dtw_cell<TIE, MARGIN>(up_in, va_prev, diag_in, da[q], mup_in, ma_prev, mdiag_in, va,
+                                      ca, ma);
+                qa = (qa >> 2) | ((unsigned long long)ca << 62);
+                dtw_cell<TIE, MARGIN>(va, vb_prev, va_prev, db[q], ma, mb_prev, ma_prev, vb, cb, mb);
+                qb = (qb >> 2) | ((unsigned long long)cb << 62);
+                if (writes_boundary && (unsigned)(cbase + q) < (unsigned)width) {
                     __stcg(brow_out + lo + cbase + q, vb);
+                    if (MARGIN) __stcg(browm_out + lo + cbase + q, mb);
+                }
                 ha[q] = va;
                 hb[q] = vb;
                 va_prev = va;
                 vb_prev = vb;
                 diag_in = up_in;
+                if (MARGIN) {
+                    hma[q] = ma;
+                    hmb[q] = mb;
+                    ma_prev = ma;
+                    mb_prev = mb;
+                    mdiag_in = mup_in;
+                }
             }
             if ((s0 & 15) == 12) {
                 // every 16 steps (all lanes together): store the column group that was
@@ -757,11 +839,16 @@ dtw_dpw_kernel(const PairDesc* __restrict__ descs, const int* __restrict__ order
         // D[tx-1][ty-1]: the last row's last column, reached n_steps - 1 - (padding) steps in
         if (strip == n_strips - 1 && t == tl) {
             const int pad = (n_steps - 1) - (hil - jstart + tl);      // 0..3
-            double fa = ha[3], fb = hb[3];
+            double fa = ha[3], fb = hb[3], fma_ = hma[3], fmb_ = hmb[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-                if (pad == 3 - q) { fa = ha[q]; fb = hb[q]; }
+                if (pad == 3 - q) { fa = ha[q]; fb = hb[q]; fma_ = hma[q]; fmb_ = hmb[q]; }
             cost[pair] = (il == ia) ? fa : fb;
+            if (MARGIN) {
+                const double mfin = (il == ia) ? fma_ : fmb_;
+                if (level == 0) margin[2 * pair] = mfin;
+                margin[2 * pair + 1] = fmin(margin[2 * pair + 1], mfin);
+            }
         }
     }
 }
@@ -838,40 +925,76 @@ dtw_backtrace_kernel(const PairDesc* __restrict__ descs, int n_pairs, int level,
     }
 }
 
-template <int FP, int NT, int P, typename T>
-static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
-                     double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
+// Variant of the cell rule and of what is carried along (see dtw_cell).
+struct SweepOpts {
+    int tie;            // 0 = pure-Python order, 1 = Cython order
+    double* margin;     // nullptr, or 2 doubles per pair (level 0, minimum over all levels)
+};
+
+__global__ void dtw_fill_kernel(double* __restrict__ p, long long n, double v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+template <int FP, int NT, int P, typename T, int TIE, bool MARGIN>
+static int launch_dp_v(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
+                       double* cost, unsigned long long* cells, int only_full, double* margin,
+                       cudaStream_t st) {
     constexpr int RS = 2 * NT + 1;
-    const size_t smem = sizeof(double) * (2 * NT + 2 * NT) + sizeof(T) * (size_t)FP * RS;
-    auto kern = dtw_dp_kernel<FP, NT, P, T>;
+    const size_t smem = sizeof(double) * (size_t)(2 * NT + 2 * NT) * (MARGIN ? 2 : 1) +
+                        sizeof(T) * (size_t)FP * RS;
+    auto kern = dtw_dp_kernel<FP, NT, P, T, TIE, MARGIN>;
     KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     kern<<<n_pairs, NT, smem, st>>>(w.descs, w.order, level, radius, F, w.xpyr, w.ypyr, w.rowj,
-                                    w.bp, w.brow, cost, cells, only_full);
+                                    w.bp, w.brow, cost, cells, only_full, w.browm, margin);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
 
+// The margin variants exist for exact (double) local distances only.
+template <int FP, int NT, int P, typename T>
+static int launch_dp(int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
+                     double* cost, unsigned long long* cells, int only_full, SweepOpts o,
+                     cudaStream_t st) {
+    if constexpr (std::is_same<T, double>::value) {
+        if (o.margin != nullptr) {
+            if (o.tie == 0)
+                return launch_dp_v<FP, NT, P, T, 0, true>(n_pairs, w, level, radius, F, cost, cells,
+                                                          only_full, o.margin, st);
+            return launch_dp_v<FP, NT, P, T, 1, true>(n_pairs, w, level, radius, F, cost, cells,
+                                                      only_full, o.margin, st);
+        }
+    }
+    if (o.tie == 0)
+        return launch_dp_v<FP, NT, P, T, 0, false>(n_pairs, w, level, radius, F, cost, cells,
+                                                   only_full, nullptr, st);
+    return launch_dp_v<FP, NT, P, T, 1, false>(n_pairs, w, level, radius, F, cost, cells,
+                                               only_full, nullptr, st);
+}
+
 template <int FP, int P, typename T>
 static int launch_dp_nt(int nt, int n_pairs, const DtwWorkspace& w, int level, int radius, int F,
-                        double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
+                        double* cost, unsigned long long* cells, int only_full, SweepOpts o,
+                        cudaStream_t st) {
     if (nt == 32)
-        return launch_dp<FP, 32, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
+        return launch_dp<FP, 32, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
     if (nt == 64)
-        return launch_dp<FP, 64, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
-    return launch_dp<FP, 128, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, st);
+        return launch_dp<FP, 64, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
+    return launch_dp<FP, 128, P, T>(n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
 }
 
 template <int P, typename T>
 static int launch_dp_fp(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
-                        double* cost, unsigned long long* cells, int only_full, cudaStream_t st) {
+                        double* cost, unsigned long long* cells, int only_full, SweepOpts o,
+                        cudaStream_t st) {
     if (F <= 8)
-        return launch_dp_nt<8, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+        return launch_dp_nt<8, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
     if (F <= 16)
-        return launch_dp_nt<16, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+        return launch_dp_nt<16, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
     if (F <= 26)
-        return launch_dp_nt<26, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
-    return launch_dp_nt<32, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, st);
+        return launch_dp_nt<26, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
+    return launch_dp_nt<32, P, T>(nt, n_pairs, w, level, radius, F, cost, cells, only_full, o, st);
 }
 
 // Banded level: local distances, then the sweep over them.
@@ -889,20 +1012,36 @@ static int launch_dist(int n_pairs, const DtwWorkspace& w, int level, int radius
     return KW_OK;
 }
 
+template <int P, typename T, int TIE, bool MARGIN>
+static void launch_dpw_v(int n_pairs, const DtwWorkspace& w, int level, int F, int wcap,
+                         double* cost, double* margin, cudaStream_t st) {
+    dtw_dpw_kernel<P, T, TIE, MARGIN><<<n_pairs, 32 * DPW_NW, 0, st>>>(
+        w.descs, w.order, level, F, wcap, w.xpyr, w.ypyr, w.win, w.dist, w.bp, w.brow, cost,
+        w.browm, margin);
+}
+
 template <int P, typename T>
-static int launch_banded(int F, int nt, int n_pairs, const DtwWorkspace& w, int level, int radius,
-                         int wcap, int max_tx, int max_ty, double* cost,
-                         unsigned long long* cells, cudaStream_t st) {
+static int launch_banded(int F, int n_pairs, const DtwWorkspace& w, int level, int radius,
+                         int wcap, int max_tx, double* cost, unsigned long long* cells,
+                         SweepOpts o, cudaStream_t st) {
     int rc;
     if (F <= 8) rc = launch_dist<8, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
     else if (F <= 16) rc = launch_dist<16, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
     else if (F <= 26) rc = launch_dist<26, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
     else rc = launch_dist<32, P, T>(n_pairs, w, level, radius, F, wcap, max_tx, cells, st);
     if (rc != KW_OK) return rc;
-    (void)nt;
-    (void)max_ty;
-    dtw_dpw_kernel<P, T><<<n_pairs, 32 * DPW_NW, 0, st>>>(w.descs, w.order, level, F, wcap, w.xpyr, w.ypyr,
-                                                 w.win, w.dist, w.bp, w.brow, cost);
+    bool done = false;
+    if constexpr (std::is_same<T, double>::value) {
+        if (o.margin != nullptr) {
+            if (o.tie == 0) launch_dpw_v<P, T, 0, true>(n_pairs, w, level, F, wcap, cost, o.margin, st);
+            else launch_dpw_v<P, T, 1, true>(n_pairs, w, level, F, wcap, cost, o.margin, st);
+            done = true;
+        }
+    }
+    if (!done) {
+        if (o.tie == 0) launch_dpw_v<P, T, 0, false>(n_pairs, w, level, F, wcap, cost, nullptr, st);
+        else launch_dpw_v<P, T, 1, false>(n_pairs, w, level, F, wcap, cost, nullptr, st);
+    }
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
@@ -921,10 +1060,10 @@ extern "C" size_t kw_dtw_workspace_bytes(int n_pairs, const int32_t* tx_host,
 
 extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_dev,
                             const int32_t* tx_host, const int32_t* ty_host, int feat_dim,
-                            int radius, int p_norm, int precision, double* cost_dev,
-                            int32_t* path_dev, int32_t* path_begin_dev, int32_t* path_len_dev,
-                            int64_t* cells_dev, void* workspace_dev, size_t workspace_bytes,
-                            void* stream) {
+                            int radius, int p_norm, int precision, int tie_mode,
+                            double* cost_dev, int32_t* path_dev, int32_t* path_begin_dev,
+                            int32_t* path_len_dev, int64_t* cells_dev, double* margin_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_pairs == 0) return KW_OK;
     KW_REQUIRE(n_pairs > 0, "n_pairs must be >= 0");
@@ -936,6 +1075,12 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
     }
     KW_REQUIRE(precision == 0 || precision == 1,
                "DTW precision must be 0 (fp64 exact) or 1 (fp32 local distances)");
+    KW_REQUIRE(tie_mode == 0 || tie_mode == 1,
+               "DTW tie_mode must be 0 (pure-Python order) or 1 (Cython order)");
+    if (margin_dev != nullptr && precision != 0) {
+        set_error("decision margins are reported for precision 0 (exact local distances) only");
+        return KW_ERR_UNSUPPORTED;
+    }
     DtwPlan plan;
     int rc = make_plan(n_pairs, tx_host, ty_host, radius, feat_dim, plan);
     if (rc != KW_OK) return rc;
@@ -950,6 +1095,12 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
                                   cudaMemcpyHostToDevice, st));
     if (cells_dev != nullptr)
         KW_CUDA_CHECK(cudaMemsetAsync(cells_dev, 0, sizeof(int64_t) * n_pairs, st));
+    if (margin_dev != nullptr) {
+        dtw_fill_kernel<<<(2 * n_pairs + 255) / 256, 256, 0, st>>>(margin_dev, 2LL * n_pairs,
+                                                                  std::numeric_limits<double>::infinity());
+        KW_CUDA_CHECK(cudaGetLastError());
+    }
+    const SweepOpts opts{tie_mode, margin_dev};
     for (int l = 0; l < plan.maxlev; ++l) {
         dtw_pyramid_kernel<<<dim3(n_pairs, 2), 256, 0, st>>>(w.descs, l, feat_dim, x_dev, y_dev,
                                                              w.xpyr, w.ypyr);
@@ -957,31 +1108,24 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
     }
     for (int l = plan.maxlev - 1; l >= 0; --l) {
         const int mtx = plan.level_max_tx[l];
-        static int nt_env = -1;
-        if (nt_env < 0) {
-            const char* e = getenv("KW_DTW_NT");
-            nt_env = e != nullptr ? atoi(e) : 0;
-        }
-        int nt = (mtx <= 64) ? 32 : ((mtx <= 128 || radius >= 0) ? 64 : 128);
-        if (nt_env == 32 || nt_env == 64 || nt_env == 128) nt = std::min(nt, nt_env);
+        const int nt = (mtx <= 64) ? 32 : ((mtx <= 128 || radius >= 0) ? 64 : 128);
         unsigned long long* cells = reinterpret_cast<unsigned long long*>(cells_dev);
         const bool split = plan.wcap > 0;
         if (split && plan.level_has_band[l]) {
-            const int ntb = std::min(nt, 64);
             if (precision == 0) {
                 if (p_norm == 2)
-                    rc = launch_banded<2, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                  mtx, plan.level_max_ty[l], cost_dev, cells, st);
+                    rc = launch_banded<2, double>(feat_dim, n_pairs, w, l, radius, plan.wcap, mtx,
+                                                  cost_dev, cells, opts, st);
                 else
-                    rc = launch_banded<1, double>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                  mtx, plan.level_max_ty[l], cost_dev, cells, st);
+                    rc = launch_banded<1, double>(feat_dim, n_pairs, w, l, radius, plan.wcap, mtx,
+                                                  cost_dev, cells, opts, st);
             } else {
                 if (p_norm == 2)
-                    rc = launch_banded<2, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                 mtx, plan.level_max_ty[l], cost_dev, cells, st);
+                    rc = launch_banded<2, float>(feat_dim, n_pairs, w, l, radius, plan.wcap, mtx,
+                                                 cost_dev, cells, opts, st);
                 else
-                    rc = launch_banded<1, float>(feat_dim, ntb, n_pairs, w, l, radius, plan.wcap,
-                                                 mtx, plan.level_max_ty[l], cost_dev, cells, st);
+                    rc = launch_banded<1, float>(feat_dim, n_pairs, w, l, radius, plan.wcap, mtx,
+                                                 cost_dev, cells, opts, st);
             }
             if (rc != KW_OK) return rc;
         }
@@ -990,17 +1134,17 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
             if (precision == 0) {
                 if (p_norm == 2)
                     rc = launch_dp_fp<2, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
-                                                 cells, only_full, st);
+                                                 cells, only_full, opts, st);
                 else
                     rc = launch_dp_fp<1, double>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
-                                                 cells, only_full, st);
+                                                 cells, only_full, opts, st);
             } else {
                 if (p_norm == 2)
                     rc = launch_dp_fp<2, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
-                                                cells, only_full, st);
+                                                cells, only_full, opts, st);
                 else
                     rc = launch_dp_fp<1, float>(feat_dim, nt, n_pairs, w, l, radius, cost_dev,
-                                                cells, only_full, st);
+                                                cells, only_full, opts, st);
             }
         }
         if (rc != KW_OK) return rc;

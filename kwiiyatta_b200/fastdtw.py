@@ -40,9 +40,11 @@ def _prep(x):
 class DtwBatchResult:
     """Device-resident result of a batched alignment."""
 
-    def __init__(self, cost, path, path_begin, path_len, cells, tx, ty):
+    def __init__(self, cost, path, path_begin, path_len, cells, tx, ty, margin=None):
         self.cost, self.path, self.path_begin, self.path_len, self.cells = (
             cost, path, path_begin, path_len, cells)
+        # (n, 2) smallest decision margin on the path: finest level, all levels (or None)
+        self.margin = margin
         self.tx, self.ty = tx, ty
         region = (tx.astype(np.int64) + ty.astype(np.int64))
         self.region_off = np.concatenate(([0], np.cumsum(region)))
@@ -60,11 +62,18 @@ class DtwBatchResult:
         return out
 
 
-def fastdtw_batch_device(x_dev, y_dev, tx, ty, radius=1, dist=2, precision=0):
+TIE_MODES = {'python': 0, 'cython': 1, 0: 0, 1: 1}
+
+
+def fastdtw_batch_device(x_dev, y_dev, tx, ty, radius=1, dist=2, precision=0, tie_mode='python',
+                         with_margin=False):
     """Batched FastDTW on device-resident, row-concatenated float64 inputs.
 
     x_dev (sum tx, F), y_dev (sum ty, F) CUDA tensors; tx / ty host int arrays.
-    ``radius < 0`` = exhaustive DTW.  Returns a DtwBatchResult (device tensors)."""
+    ``radius < 0`` = exhaustive DTW.  ``tie_mode``: which fastdtw back-end's tie order to follow
+    ('python', the default and what the oracle restates, or 'cython').  ``with_margin``: also
+    return the smallest decision margin on each path (``result.margin``, (n, 2): the returned
+    path, all resolution levels).  Returns a DtwBatchResult (device tensors)."""
     torch = _lib.require_cuda()
     lib = _lib.lib()
     tx = np.ascontiguousarray(tx, dtype=np.int32)
@@ -83,18 +92,21 @@ def fastdtw_batch_device(x_dev, y_dev, tx, ty, radius=1, dist=2, precision=0):
     begin = torch.empty(n, dtype=torch.int32, device=dev)
     length = torch.empty(n, dtype=torch.int32, device=dev)
     cells = torch.empty(n, dtype=torch.int64, device=dev)
+    margin = torch.empty((n, 2), dtype=torch.float64, device=dev) if with_margin else None
     rc = lib.kw_dtw_batch(n, x_dev.data_ptr(), y_dev.data_ptr(), tx.ctypes.data,
                           ty.ctypes.data, f, int(radius), p_norm, int(precision),
-                          cost.data_ptr(), path.data_ptr(), begin.data_ptr(),
-                          length.data_ptr(), cells.data_ptr(), ws.data_ptr(), ws_bytes,
-                          _lib.stream_ptr(torch))
+                          TIE_MODES[tie_mode], cost.data_ptr(), path.data_ptr(),
+                          begin.data_ptr(), length.data_ptr(), cells.data_ptr(),
+                          _lib.ptr(margin), ws.data_ptr(), ws_bytes, _lib.stream_ptr(torch))
     _lib.check(rc, 'kw_dtw_batch')
-    return DtwBatchResult(cost, path, begin, length, cells, tx, ty)
+    return DtwBatchResult(cost, path, begin, length, cells, tx, ty, margin)
 
 
-def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None):
+def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None, tie_mode='python',
+                  with_margin=False):
     """``pairs``: sequence of (x, y) host arrays.  Returns a list of
-    ``(distance, path ndarray (L, 2))`` in the same order."""
+    ``(distance, path ndarray (L, 2))`` in the same order; with ``with_margin`` a pair
+    ``(that list, margins ndarray (n, 2))``."""
     torch = _lib.require_cuda()
     if len(pairs) == 0:
         return []
@@ -113,7 +125,11 @@ def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None):
     ty = np.array([len(y) for y in ys], dtype=np.int32)
     x_dev = _lib.gather_to_device(torch, xs, dev, 'dtw_x')
     y_dev = _lib.gather_to_device(torch, ys, dev, 'dtw_y')
-    return fastdtw_batch_device(x_dev, y_dev, tx, ty, radius, dist, precision).to_host()
+    res = fastdtw_batch_device(x_dev, y_dev, tx, ty, radius, dist, precision, tie_mode,
+                               with_margin)
+    if with_margin:
+        return res.to_host(), res.margin.cpu().numpy()
+    return res.to_host()
 
 
 def fastdtw(x, y, radius=1, dist=None):

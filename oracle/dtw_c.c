@@ -12,6 +12,12 @@
  * Window: one inclusive column interval [lo, hi] per row, derived from the coarser path
  *   (closed form of the radius expansion + 2x projection; see window_intervals in
  *   oracle/fastdtw_ref.py).
+ * The rule above is fastdtw's pure-Python back-end (tie rule 0).  kwo_fastdtw_ex takes a general
+ *   tie rule: the preference order of the three predecessors (a permutation of 0 = up, 1 = left,
+ *   2 = diag) and whether they are compared before or after the local distance is added, so that
+ *   tests can show the returned path to be the same under EVERY such rule (the Cython back-end
+ *   of fastdtw 0.3.2, whose exact rule cannot be read here, is one of them), and reports the
+ *   smallest decision margin on the returned path (see include/kwiiyatta_b200.h, margin_dev).
  * Local distance p=2: sqrt(sum_k (x_k - y_k)^2), summed left to right; use_fma selects
  *   s = fma(d, d, s) (what the CUDA path computes) or s = s + d*d (what a Python float
  *   loop computes).  p=1: sum_k |x_k - y_k|.
@@ -39,9 +45,14 @@ static double local_dist(const double* a, const double* b, int F, int p, int use
 
 /* DP over rows with inclusive windows lo[i]..hi[i] (both non-decreasing).
  * path_out receives (i,j) pairs in forward order; returns path length. */
+typedef struct {
+    int order[3];   /* preference order of the candidates: 0 = up, 1 = left, 2 = diag */
+    int before;     /* 1: compare the predecessors before adding the local distance */
+} TieRule;
+
 static int dp_window(const double* x, int Tx, const double* y, int Ty, int F, int p, int use_fma,
                      const int32_t* lo, const int32_t* hi, double* cost, int32_t* path_out,
-                     int64_t* cells) {
+                     int64_t* cells, const TieRule* tie, double* margin) {
     int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(Tx + 1));
     int64_t total = 0;
     for (int i = 0; i < Tx; ++i) { off[i] = total; total += (int64_t)(hi[i] - lo[i] + 1); }
@@ -50,30 +61,43 @@ static int dp_window(const double* x, int Tx, const double* y, int Ty, int F, in
     uint8_t* bp = (uint8_t*)malloc((size_t)total);
     double* prev = (double*)malloc(sizeof(double) * (size_t)(Ty + 1));
     double* cur = (double*)malloc(sizeof(double) * (size_t)(Ty + 1));
+    double* mprev = (double*)malloc(sizeof(double) * (size_t)(Ty + 1));   /* running margins */
+    double* mcur = (double*)malloc(sizeof(double) * (size_t)(Ty + 1));
     int plo = 0, phi = -1; /* previous row's window; row -1 is the virtual row */
     for (int i = 0; i < Tx; ++i) {
         const int l = lo[i], h = hi[i];
         for (int j = l; j <= h; ++j) {
-            double up, left, diag;
+            double pred[3], pm[3];       /* 0 = up, 1 = left, 2 = diag */
             if (i == 0) {
-                up = INFINITY;
-                diag = (j == 0) ? 0.0 : INFINITY;
+                pred[0] = INFINITY; pm[0] = INFINITY;
+                pred[2] = (j == 0) ? 0.0 : INFINITY; pm[2] = INFINITY;
             } else {
-                up = (j >= plo && j <= phi) ? prev[j] : INFINITY;
-                diag = (j - 1 >= plo && j - 1 <= phi) ? prev[j - 1] : INFINITY;
+                const int in_up = (j >= plo && j <= phi), in_dg = (j - 1 >= plo && j - 1 <= phi);
+                pred[0] = in_up ? prev[j] : INFINITY;      pm[0] = in_up ? mprev[j] : INFINITY;
+                pred[2] = in_dg ? prev[j - 1] : INFINITY;  pm[2] = in_dg ? mprev[j - 1] : INFINITY;
             }
-            left = (j - 1 >= l) ? cur[j - 1] : INFINITY;
+            pred[1] = (j - 1 >= l) ? cur[j - 1] : INFINITY;
+            pm[1] = (j - 1 >= l) ? mcur[j - 1] : INFINITY;
             const double dt = local_dist(x + (size_t)i * F, y + (size_t)j * F, F, p, use_fma);
-            double best = up + dt; uint8_t code = 0;
-            double c = left + dt; if (c < best) { best = c; code = 1; }
-            c = diag + dt;        if (c < best) { best = c; code = 2; }
-            cur[j] = best;
-            bp[off[i] + (j - l)] = code;
+            double cand[3];
+            for (int q = 0; q < 3; ++q) cand[q] = tie->before ? pred[q] : pred[q] + dt;
+            int code = tie->order[0];
+            for (int q = 1; q < 3; ++q)
+                if (cand[tie->order[q]] < cand[code]) code = tie->order[q];
+            cur[j] = tie->before ? cand[code] + dt : cand[code];
+            double other = INFINITY;
+            for (int q = 0; q < 3; ++q)
+                if (q != code && cand[q] < other) other = cand[q];
+            const double here = (cand[code] < INFINITY) ? other - cand[code] : INFINITY;
+            mcur[j] = here < pm[code] ? here : pm[code];
+            bp[off[i] + (j - l)] = (uint8_t)code;
         }
         double* t = prev; prev = cur; cur = t;
+        t = mprev; mprev = mcur; mcur = t;
         plo = l; phi = h;
     }
     *cost = (Ty - 1 >= plo && Ty - 1 <= phi) ? prev[Ty - 1] : INFINITY;
+    if (margin) *margin = (Ty - 1 >= plo && Ty - 1 <= phi) ? mprev[Ty - 1] : INFINITY;
     /* backtrace */
     int n = 0, i = Tx - 1, j = Ty - 1;
     while (i >= 0 && j >= 0) {
@@ -90,12 +114,13 @@ static int dp_window(const double* x, int Tx, const double* y, int Ty, int F, in
             path_out[2 * b] = ti; path_out[2 * b + 1] = tj;
         }
     }
-    free(off); free(bp); free(prev); free(cur);
+    free(off); free(bp); free(prev); free(cur); free(mprev); free(mcur);
     return n;
 }
 
 static int fastdtw_rec(const double* x, int Tx, const double* y, int Ty, int F, int radius, int p,
-                       int use_fma, double* cost, int32_t* path_out, int64_t* cells) {
+                       int use_fma, double* cost, int32_t* path_out, int64_t* cells,
+                       const TieRule* tie, double* margin_all) {
     int32_t* lo = (int32_t*)malloc(sizeof(int32_t) * (size_t)Tx);
     int32_t* hi = (int32_t*)malloc(sizeof(int32_t) * (size_t)Tx);
     int n;
@@ -113,7 +138,8 @@ static int fastdtw_rec(const double* x, int Tx, const double* y, int Ty, int F, 
                 ys[(size_t)i * F + k] = (y[(size_t)(2 * i) * F + k] + y[(size_t)(2 * i + 1) * F + k]) / 2;
         int32_t* cpath = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(cx + cy + 2));
         double ccost;
-        int cn = fastdtw_rec(xs, cx, ys, cy, F, radius, p, use_fma, &ccost, cpath, cells);
+        int cn = fastdtw_rec(xs, cx, ys, cy, F, radius, p, use_fma, &ccost, cpath, cells, tie,
+                             margin_all);
         free(xs); free(ys);
         if (cn <= 0) { free(cpath); free(lo); free(hi); return -1; }
         int32_t* first_j = (int32_t*)malloc(sizeof(int32_t) * (size_t)cx);
@@ -136,19 +162,34 @@ static int fastdtw_rec(const double* x, int Tx, const double* y, int Ty, int F, 
         free(cpath); free(first_j); free(last_j);
     }
     int64_t c = 0;
-    n = dp_window(x, Tx, y, Ty, F, p, use_fma, lo, hi, cost, path_out, &c);
+    double m = INFINITY;
+    n = dp_window(x, Tx, y, Ty, F, p, use_fma, lo, hi, cost, path_out, &c, tie, &m);
     if (cells) *cells += c;
+    /* margin_all[0]: this (finally: the finest) level; [1]: minimum over all levels so far */
+    margin_all[0] = m;
+    if (m < margin_all[1]) margin_all[1] = m;
     free(lo); free(hi);
     return n;
 }
 
 /* radius < 0: exhaustive DTW.  path_out: capacity 2*(Tx+Ty) int32.  cells_out: sum of
  * window sizes over all resolution levels.  Returns path length, or -1 on a malformed window. */
+int kwo_fastdtw_ex(const double* x, int Tx, const double* y, int Ty, int F, int radius, int p,
+                   int use_fma, const int32_t* tie_order, int tie_before, double* cost,
+                   int32_t* path_out, int64_t* cells_out, double* margin_out) {
+    int64_t cells = 0;
+    double margins[2] = {INFINITY, INFINITY};
+    TieRule tie = {{tie_order[0], tie_order[1], tie_order[2]}, tie_before};
+    if (Tx <= 0 || Ty <= 0) { *cost = 0.0; if (cells_out) *cells_out = 0; return 0; }
+    int n = fastdtw_rec(x, Tx, y, Ty, F, radius, p, use_fma, cost, path_out, &cells, &tie, margins);
+    if (cells_out) *cells_out = cells;
+    if (margin_out) { margin_out[0] = margins[0]; margin_out[1] = margins[1]; }
+    return n;
+}
+
 int kwo_fastdtw(const double* x, int Tx, const double* y, int Ty, int F, int radius, int p,
                 int use_fma, double* cost, int32_t* path_out, int64_t* cells_out) {
-    int64_t cells = 0;
-    if (Tx <= 0 || Ty <= 0) { *cost = 0.0; if (cells_out) *cells_out = 0; return 0; }
-    int n = fastdtw_rec(x, Tx, y, Ty, F, radius, p, use_fma, cost, path_out, &cells);
-    if (cells_out) *cells_out = cells;
-    return n;
+    const int32_t python_order[3] = {0, 1, 2};
+    return kwo_fastdtw_ex(x, Tx, y, Ty, F, radius, p, use_fma, python_order, 0, cost, path_out,
+                          cells_out, NULL);
 }

@@ -17,11 +17,33 @@ def lib():
             ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.kwo_fastdtw_ex.restype = ctypes.c_int
+        _lib.kwo_fastdtw_ex.argtypes = [
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
 
 
-def fastdtw(x, y, radius=1, dist=2, use_fma=True, return_cells=False):
-    """(distance, path[(L,2) int32]) - radius < 0 means exhaustive DTW."""
+# Tie rules: (preference order over 0 = up (i-1, j), 1 = left (i, j-1), 2 = diagonal; compare
+# before the local distance is added?).  'python' is fastdtw.py's; 'cython' is _fastdtw.pyx's as
+# recalled in SURVEY.md section 8a (the one kw_dtw_batch's tie_mode = 1 implements).
+TIE_RULES = {'python': ((0, 1, 2), False), 'cython': ((2, 1, 0), True)}
+
+
+def all_tie_rules():
+    """Every preference order, compared before or after the addition (12 rules)."""
+    import itertools
+    return [(order, before) for order in itertools.permutations((0, 1, 2))
+            for before in (False, True)]
+
+
+def fastdtw(x, y, radius=1, dist=2, use_fma=True, return_cells=False, tie='python',
+            return_margin=False):
+    """(distance, path[(L,2) int32]) - radius < 0 means exhaustive DTW.  ``tie``: a name in
+    TIE_RULES or an (order, before) pair.  ``return_margin`` appends the smallest decision
+    margin on the path, (finest level, minimum over all levels)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     if x.ndim == 1:
@@ -39,14 +61,20 @@ def fastdtw(x, y, radius=1, dist=2, use_fma=True, return_cells=False):
     path = np.empty((tx + ty + 2, 2), dtype=np.int32)
     cost = ctypes.c_double()
     cells = ctypes.c_int64()
-    n = lib().kwo_fastdtw(x.ctypes.data, tx, y.ctypes.data, ty, x.shape[1],
-                          int(radius), p, int(bool(use_fma)),
-                          ctypes.byref(cost), path.ctypes.data, ctypes.byref(cells))
+    order, before = TIE_RULES[tie] if isinstance(tie, str) else tie
+    order = np.array(order, dtype=np.int32)
+    margin = np.empty(2, dtype=np.float64)
+    n = lib().kwo_fastdtw_ex(x.ctypes.data, tx, y.ctypes.data, ty, x.shape[1],
+                             int(radius), p, int(bool(use_fma)), order.ctypes.data,
+                             int(bool(before)), ctypes.byref(cost), path.ctypes.data,
+                             ctypes.byref(cells), margin.ctypes.data)
     if n < 0:
         raise RuntimeError('malformed window')
     out = (cost.value, path[:n].copy())
     if return_cells:
         out = out + (cells.value,)
+    if return_margin:
+        out = out + (margin,)
     return out
 
 

@@ -202,3 +202,63 @@ def test_batch_rejects_mixed_feature_dims(cuda):
     rng = np.random.default_rng(3)
     with pytest.raises(ValueError, match='same number of features'):
         kfd.fastdtw_batch([_rand_pair(rng, 10, 12, 3), _rand_pair(rng, 10, 12, 2)], radius=1, dist=2)
+
+
+def _corpus_pairs(n):
+    out = []
+    for i in range(n):
+        a, b = synth.make_padded_pair(i)
+        out.append((make_feature(a, a.fs), make_feature(b, b.fs)))
+    return out
+
+
+@pytest.mark.parametrize('tie_mode', ['python', 'cython'])
+@pytest.mark.parametrize('radius', [1, 32, -1])
+def test_tie_modes_on_exact_ties(cuda, tie_mode, radius):
+    """Integer-valued sequences (exact ties everywhere): each tie mode of kw_dtw_batch reproduces
+    the oracle under the same rule, bit for bit, and the margin of such a path is 0."""
+    rng = np.random.default_rng(17)
+    pairs = [(rng.integers(0, 3, (tx, f)).astype(float), rng.integers(0, 3, (ty, f)).astype(float))
+             for tx, ty, f in [(40, 45, 1), (130, 90, 2), (257, 300, 1), (64, 64, 3), (5, 9, 1)]]
+    got, margins = kfd.fastdtw_batch(pairs, radius=radius, dist=2, tie_mode=tie_mode,
+                                     with_margin=True)
+    for (x, y), (cost, path), m in zip(pairs, got, margins):
+        ecost, epath, em = dtw_c.fastdtw(x, y, radius=radius, dist=2, tie=tie_mode,
+                                         return_margin=True)
+        assert np.array_equal(path, epath) and cost == ecost
+        assert np.array_equal(m, em)
+    assert (margins[:4, 0] == 0.0).all()
+    # the two modes really are different rules
+    other = kfd.fastdtw_batch(pairs, radius=radius, dist=2,
+                              tie_mode='cython' if tie_mode == 'python' else 'python')
+    assert any(not np.array_equal(a[1], b[1]) for a, b in zip(got, other))
+
+
+def test_decision_margin_on_the_corpus(cuda):
+    """configs[0-1] inputs: both tie modes return the same paths, and the smallest decision
+    margin on every path equals the oracle's and is far above the rounding of the sums -- the
+    path is pinned without the fastdtw package (kwiiyatta/vocoder/align.py:71)."""
+    pairs = _corpus_pairs(24)
+    for radius in (32, 1):
+        got, margins = kfd.fastdtw_batch(pairs, radius=radius, dist=2, with_margin=True)
+        cy = kfd.fastdtw_batch(pairs, radius=radius, dist=2, tie_mode='cython')
+        for (x, y), (cost, path), (ccost, cpath), m in zip(pairs, got, cy, margins):
+            ecost, epath, em = dtw_c.fastdtw(x, y, radius=radius, dist=2, return_margin=True)
+            assert np.array_equal(path, epath) and cost == ecost
+            assert np.array_equal(cpath, path) and abs(ccost - cost) <= 64 * np.spacing(cost)
+            assert np.allclose(m, em, rtol=0, atol=16 * np.spacing(cost))
+            assert m[1] <= m[0] and m[1] > 1e4 * np.spacing(cost)
+    # margins are reported for exact local distances only
+    with pytest.raises(NotImplementedError):
+        kfd.fastdtw_batch(pairs[:1], radius=32, dist=2, precision=1, with_margin=True)
+
+
+def test_margin_variant_returns_the_same_paths(cuda):
+    rng = np.random.default_rng(5)
+    pairs = [_rand_pair(rng, tx, ty, 6) for tx, ty in [(300, 280), (129, 257), (70, 400), (3, 5)]]
+    for radius in (2, -1):
+        plain = kfd.fastdtw_batch(pairs, radius=radius, dist=2)
+        with_m, margins = kfd.fastdtw_batch(pairs, radius=radius, dist=2, with_margin=True)
+        for (c1, p1), (c2, p2) in zip(plain, with_m):
+            assert c1 == c2 and np.array_equal(p1, p2)
+        assert (margins > 0).all()

@@ -82,3 +82,57 @@ def test_golden_fixtures():
         x, y, r = g[f'x{i}'], g[f'y{i}'], int(g[f'radius{i}'])
         cost, path = dtw_c.fastdtw(x, y, r, 2, use_fma=False)
         assert np.array_equal(path, g[f'path{i}']) and cost == float(g[f'cost{i}'])
+
+
+def _corpus_features(n):
+    from kwiiyatta_b200 import synth
+    from oracle import align_ref
+    out = []
+    for i in range(n):
+        a, b = synth.make_padded_pair(i)
+        out.append((align_ref.make_feature(a.mel_cepstrum.data, a.f0, a.is_voiced),
+                    align_ref.make_feature(b.mel_cepstrum.data, b.f0, b.is_voiced)))
+    return out
+
+
+def test_path_does_not_depend_on_the_tie_rule_or_the_rounding():
+    """The pin SURVEY.md sections 7 / 8b ask for in place of the (absent) fastdtw package: on the
+    silence-padded synthetic corpus the path is the same under all 12 tie rules (3! preference
+    orders x compared before / after the local distance is added; the pure-Python and the Cython
+    back-end of fastdtw 0.3.2 are two of them) and under all three roundings of the local
+    distance (fma, separate multiply-add, BLAS dot), because the smallest decision margin on the
+    path is many orders of magnitude above the rounding of the sums."""
+    for x, y in _corpus_features(10):
+        cost, path, margin = dtw_c.fastdtw(x, y, radius=32, dist=2, return_margin=True)
+        ulp = np.spacing(cost)
+        assert margin[0] > 1e4 * ulp and margin[1] > 1e4 * ulp
+        assert margin[1] <= margin[0]
+        for rule in dtw_c.all_tie_rules():
+            c, p = dtw_c.fastdtw(x, y, radius=32, dist=2, tie=rule)
+            assert np.array_equal(p, path) and abs(c - cost) <= 64 * ulp
+        c, p = dtw_c.fastdtw(x, y, radius=32, dist=2, use_fma=False)
+        assert np.array_equal(p, path)
+    # radius 1 (the reference's own tests call fastdtw(..., radius=1, dist=2),
+    # tests/kwiiyatta/test_vocoder.py:281-286)
+    for x, y in _corpus_features(3):
+        cost, path, margin = dtw_c.fastdtw(x, y, radius=1, dist=2, return_margin=True)
+        assert margin[1] > 1e4 * np.spacing(cost)
+        for rule in dtw_c.all_tie_rules():
+            assert np.array_equal(dtw_c.fastdtw(x, y, radius=1, dist=2, tie=rule)[1], path)
+
+
+def test_tie_rules_do_differ_on_exact_ties():
+    """The margin is not vacuous: integer-valued sequences tie exactly, the margin is 0 and
+    the rules return different (equally cheap) paths."""
+    rng = np.random.default_rng(8)
+    x = rng.integers(0, 3, (40, 1)).astype(float)
+    y = rng.integers(0, 3, (45, 1)).astype(float)
+    results = {}
+    for rule in dtw_c.all_tie_rules():
+        cost, path, margin = dtw_c.fastdtw(x, y, radius=-1, dist=2, tie=rule, return_margin=True)
+        assert margin[0] == 0.0
+        results[rule] = (cost, path.tobytes())
+    assert len({c for c, _ in results.values()}) == 1          # same optimal cost
+    assert len({p for _, p in results.values()}) > 1           # different optimal paths
+    py = dtw_c.fastdtw(x, y, radius=-1, dist=2, tie='python')[1]
+    assert [tuple(t) for t in py.tolist()] == fastdtw_ref.dtw(x, y, 2, 'seq')[1]
