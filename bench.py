@@ -20,6 +20,12 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the CPU arm uses every host core whatever the launcher exported (torchrun sets
+    # OMP_NUM_THREADS=1); must happen before numpy loads its BLAS
+    for _var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_var] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -31,6 +37,28 @@ N_MIX_CONVERT = 128
 N_UTTS = 1200
 UTT_FRAMES = 600
 RADIUS = 32
+LONG_PAIRS = 256          # configs[3]: 256 pairs of 4096 x 4096 frames, unconstrained
+LONG_FRAMES = 4096
+CPU_EM_FRAMES = 12000     # frames of the CPU arms' EM sample
+CPU_EM_ITERS = 10
+
+
+def lloyd_labels(x, k, seed, passes=5):
+    """Initial hard labels shared by the GPU arm and the CPU arms: ``k`` distinct frames drawn
+    with ``default_rng(seed)`` as centres, ``passes`` Lloyd passes in numpy (the reference
+    initialises with KMeans; sklearn's own is version dependent, so both arms get this one)."""
+    rng = np.random.default_rng(seed)
+    centres = x[rng.choice(len(x), size=k, replace=False)].copy()
+    x2 = (x * x).sum(1)
+    lab = None
+    for _ in range(passes):
+        d2 = x2[:, None] - 2.0 * (x @ centres.T) + (centres * centres).sum(1)[None]
+        lab = d2.argmin(1)
+        for j in range(k):
+            m = lab == j
+            if m.any():
+                centres[j] = x[m].mean(0)
+    return lab
 
 
 def measured_peaks():
@@ -177,27 +205,44 @@ def run_b200(args):
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timed_loop(fn, flush):
-        """W warm-up + K timed steps; per-step CUDA events on the launching stream, L2 flushed
-        between steps when asked; returns max-over-ranks total ms of the K steps."""
+        """W warm-up + K timed steps, CUDA events on the launching stream, barrier + synchronize
+        on both sides; returns max-over-ranks total ms of the K steps.  With ``flush`` the L2 is
+        overwritten between steps (outside the timed intervals, so each step is timed on its
+        own); without it the K steps are enqueued back to back between one pair of events."""
         for _ in range(W):
             fn()
         barrier()
-        total = 0.0
-        for _ in range(K):
-            if flush:
+        if flush:
+            total = 0.0
+            for _ in range(K):
                 flush_buf.fill_(1)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                total += e0.elapsed_time(e1)
+        else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            for _ in range(K):
+                fn()
             e1.record()
             e1.synchronize()
-            total += e0.elapsed_time(e1)
+            total = e0.elapsed_time(e1)
         barrier()
         return max_over_ranks(total)
 
     # ---------------- inputs (this rank's shard: pairs [rank*503, (rank+1)*503)) -----------
-    n_pairs = args.pairs
-    padded, feats = build_dtw_inputs(rank * n_pairs, n_pairs)
+    if args.total_pairs:
+        # strong scaling (configs[2]: 5 030 pairs over the ranks): contiguous blocks of pairs
+        lo = args.total_pairs * rank // world
+        hi = args.total_pairs * (rank + 1) // world
+        first_pair, n_pairs = lo, hi - lo
+    else:
+        first_pair, n_pairs = rank * args.pairs, args.pairs
+    padded, feats = build_dtw_inputs(first_pair, n_pairs)
     tx = np.array([len(x) for x, _ in feats], dtype=np.int32)
     ty = np.array([len(y) for _, y in feats], dtype=np.int32)
     x_host = np.concatenate([x for x, _ in feats])
@@ -232,11 +277,9 @@ def run_b200(args):
     kw.set_pad_silence(lambda f, n: f)     # the synthetic features are already padded
     x_joint = kw.joint_array_from_pairs(padded, pad_silence=True, pad_len=synth.PAD_LEN)
     n_frames, dim = x_joint.shape
-    # initial hard labels: a few Lloyd passes (the reference initialises with KMeans), computed
-    # outside every timed region
-    from kwiiyatta_b200 import kmeans
-    labels0 = kmeans.kmeans_labels(torch.from_numpy(x_joint).to(dev), N_MIX_EM, seed=rank,
-                                   n_lloyd=5).cpu().numpy()
+    # initial hard labels: five Lloyd passes (the reference initialises with KMeans), computed
+    # outside every timed region by the function the CPU arms use too
+    labels0 = lloyd_labels(x_joint, N_MIX_EM, seed=first_pair)
 
     def make_gm(max_iter):
         resp0 = torch.zeros((n_frames, N_MIX_EM), dtype=torch.float64, device=dev)
@@ -246,12 +289,31 @@ def run_b200(args):
 
     gm = make_gm(1)
     xj_dev = gm.initialize(x_joint)
-    gm.em_iteration(xj_dev)
+    lb_first = gm.em_iteration(xj_dev)
     gm._estep(torch, xj_dev)
     density = float((gm._resp[:, :n_frames] > 1e-16).sum().item()) / n_frames
+    # the same first iteration on the FP64 kernels (not timed): the benchmarked path is checked
+    # against it here as well as in tests/test_gpu_gmm_scale.py
+    check = None
+    if args.precision == 'tc' and world == 1:
+        g64 = kw.GaussianMixture(n_components=N_MIX_EM, max_iter=1, tol=0.0, device=dev,
+                                 precision='fp64', resp_init=make_gm(1).resp_init)
+        x64 = g64.initialize(x_joint)
+        lb64 = g64.em_iteration(x64)
+        g64.em_iteration(x64)
+        gm.em_iteration(xj_dev)
+        mu_tc, mu_64 = gm._means[gm._cur], g64._means[g64._cur]
+        check = {'lower_bound_tc': lb_first, 'lower_bound_fp64': lb64,
+                 'lower_bound_rel_diff': abs(lb_first - lb64) / abs(lb64),
+                 'means_rel_diff_after_2_iterations':
+                     float((mu_tc - mu_64).abs().max() / mu_64.abs().max()),
+                 'tolerance': 1e-5}
+        del g64, x64
+        torch.cuda.empty_cache()
 
     # ---------------- stage 2 (headline): EM iteration -------------------------------------
-    em_ms = timed_loop(lambda: gm.em_iteration(xj_dev), flush=False)
+    em_ms = timed_loop(lambda: gm.em_iteration_async(xj_dev), flush=False)
+    lb_last = gm.last_lower_bound()
     frames_total = sum_over_ranks(n_frames)
     em_value = frames_total * K / (em_ms / 1e3)
     # per-entry-point timing for the roofline (E-step and M-step statistics)
@@ -289,9 +351,56 @@ def run_b200(args):
     em_e2e = frames_total * e2e_iters / (em_e2e_ms / 1e3)
     model_bytes = sum(a.nbytes for a in (conv.gmm.weights_, conv.gmm.means_,
                                          conv.gmm.covariances_, conv.gmm.precisions_cholesky_))
-    del conv, x_pinned, r0
+    del conv, r0
+    # the fit a user gets: reference defaults (tol = 1e-3, max_iter = 100, KMeans initialisation,
+    # here kwiiyatta_b200.kmeans on the device), timed whole with host buffers
+    fit = None
+    if world == 1:
+        conv = kw.B200GMMFeatureConverter(components=N_MIX_EM, random_state=0, verbose=0,
+                                          device=dev, precision=args.precision)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            conv._train(x_pinned)
+        torch.cuda.synchronize()
+        fit_s = time.perf_counter() - t0
+        fit = {'seconds': fit_s, 'n_iter': int(conv.gmm.n_iter_),
+               'converged': bool(conv.gmm.converged_),
+               'lower_bound': float(conv.gmm.lower_bound_),
+               'frames_per_s_per_iter': n_frames * conv.gmm.n_iter_ / fit_s,
+               'note': "B200GMMFeatureConverter(components=64)._train(host array): "
+                       "init_params='kmeans' on the device, tol=1e-3, max_iter=100"}
+        del conv
+    del x_pinned
     gm._resp = None
+    gm._ws = None
+    del gm, xj_dev
     torch.cuda.empty_cache()
+
+    # ---------------- configs[3]: long unconstrained DTW, 256 pairs of 4096 x 4096 ----------
+    long_stage = None
+    if args.long_pairs > 0:
+        lx, ly = [], []
+        for i in range(8):
+            a, b = synth.make_pair(i, length=LONG_FRAMES)
+            from kwiiyatta_b200.alignment import make_feature as _mf
+            lx.append(_mf(a, a.fs))
+            ly.append(_mf(b, b.fs))
+        n_long = args.long_pairs
+        ltx = np.full(n_long, LONG_FRAMES, dtype=np.int32)
+        lrng = np.random.default_rng(77 + rank)
+        lx_dev = torch.from_numpy(np.concatenate(
+            [lx[i % 8] + lrng.normal(0, 0.01, lx[0].shape) for i in range(n_long)])).to(dev)
+        ly_dev = torch.from_numpy(np.concatenate(
+            [ly[i % 8] + lrng.normal(0, 0.01, ly[0].shape) for i in range(n_long)])).to(dev)
+        long_ms = timed_loop(lambda: kfd.fastdtw_batch_device(lx_dev, ly_dev, ltx, ltx, -1, 2),
+                             flush=True)
+        long_cells = sum_over_ranks(float(n_long) * LONG_FRAMES * LONG_FRAMES)
+        long_stage = {'ms': long_ms / K, 'cells': long_cells,
+                      'value': long_cells * K / (long_ms / 1e3), 'pairs_per_gpu': n_long}
+        del lx_dev, ly_dev
+        torch.cuda.empty_cache()
 
     # ---------------- stage 3: conversion (configs[4]) -------------------------------------
     n_utts = args.utts
@@ -331,7 +440,7 @@ def run_b200(args):
     # ---------------- CPU baseline (bounded samples, rank 0, N = 1 only) -------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baselines(feats, x_joint, labels0, (w, m, c), src_list, em_iters=2)
+        cpu = cpu_baselines(feats, x_joint, (w, m, c), src_list)
 
     em_tflops = 2 * flops_half / (em_ms / K / 1e3) / 1e12
     tc = args.precision == 'tc'
@@ -353,7 +462,7 @@ def run_b200(args):
         'warmup': W,
         'ms_per_step': em_ms / K,
         'higher_is_better': True,
-        'scaling': 'weak',
+        'scaling': 'strong' if args.total_pairs else 'weak',
         'vs_baseline': None,
         'dtype': 'f64' if args.precision == 'fp64' else 'f16x2-split (fp32 accumulate) + f64',
         'data': 'synthetic',
@@ -361,9 +470,14 @@ def run_b200(args):
             'workload': 'configs[1]: 503 synthetic ATR503-shaped pairs per GPU -> FastDTW r=32 '
                         '-> (N,144) joint frames -> 64-mix full-cov EM iteration; stages.convert '
                         'is configs[4] (128-mix, 720k frames)',
-            'pairs_per_gpu': n_pairs, 'frames_per_gpu': int(n_frames), 'dim': int(dim),
+            'pairs_per_gpu': n_pairs, 'total_pairs': args.total_pairs or n_pairs * world,
+            'frames_per_gpu': int(n_frames), 'dim': int(dim),
             'n_components': N_MIX_EM, 'precision': args.precision,
-            'init': 'hard labels from 5 Lloyd passes (KMeans-style, as the reference initialises)',
+            'init': 'hard labels from 5 numpy Lloyd passes (bench.lloyd_labels, the same '
+                    'function the CPU arms use; the reference initialises with KMeans)',
+            'timing': 'EM: K iterations enqueued back to back between one pair of CUDA events '
+                      '(em_iteration_async: no host read-back inside the timed region); DTW / '
+                      'convert: per-step events with an L2 flush between steps',
             'mean_components_per_frame_above_1e-16': density,
             'l2': 'EM inputs (X 8*N*144 B + resp) exceed L2; DTW/convert stages flush L2 with a '
                   '256 MiB write between timed steps',
@@ -395,7 +509,30 @@ def run_b200(args):
         },
         'cpu_baseline': cpu['em'] if cpu else None,
         'clocks': clock_info,
+        'parity_check': check,
+        'lower_bound_after_timed_steps': lb_last,
+        'e2e_fit': fit,
+        # the other two stages' headline figures as flat keys (details under "stages")
+        'dtw_cells_per_s': dtw_cells_per_s,
+        'dtw_roofline_frac': dtw_cells_per_s / world / dtw_peak,
+        'dtw_e2e_cells_per_s': dtw_e2e,
+        'dtw_long_cells_per_s': long_stage['value'] if long_stage else None,
+        'dtw_long_roofline_frac': (long_stage['value'] / world / dtw_peak) if long_stage else None,
+        'convert_frames_per_s': conv_value,
+        'convert_roofline_frac': conv_flops / (conv_ms / K / 1e3) / 1e12 / world / peak,
+        'convert_e2e_frames_per_s': conv_e2e,
         'stages': {
+            'dtw_long': None if long_stage is None else {
+                'metric': 'DTW cells/s', 'value': long_stage['value'], 'unit': 'cells/s',
+                'ms_per_step': long_stage['ms'], 'cells_per_step': long_stage['cells'],
+                'workload': f"configs[3]: {long_stage['pairs_per_gpu']} pairs per GPU of "
+                            f'{LONG_FRAMES} x {LONG_FRAMES} frames, 26-dim, unconstrained '
+                            '(radius < 0), exact fp64 local distances',
+                'roofline': {'bound': 'fp64 issue', 'achieved': long_stage['value'] / world,
+                             'peak': dtw_peak, 'unit': 'cells/s per GPU',
+                             'frac': long_stage['value'] / world / dtw_peak,
+                             'model': 'SMs x 64 FP64 lanes x f_max / 72 FP64-pipe ops per cell'},
+            },
             'dtw': {
                 'metric': 'DTW cells/s', 'value': dtw_cells_per_s, 'unit': 'cells/s',
                 'ms_per_step': dtw_ms / K, 'cells_per_step': cells_total,
@@ -458,18 +595,45 @@ def cpu_dtw(feats, n_sample, procs):
     return cells / dt, cells, dt
 
 
-def cpu_em(x, labels, n_sample, iters):
+def cpu_em(x, n_sample, iters):
     from oracle import gmm_ref
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        threadpool_limits = None
     xs = np.ascontiguousarray(x[:n_sample])
+    labels = lloyd_labels(xs, N_MIX_EM, seed=0)
     resp0 = np.zeros((len(xs), N_MIX_EM))
-    resp0[np.arange(len(xs)), labels[:len(xs)]] = 1.0
+    resp0[np.arange(len(xs)), labels] = 1.0
+    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    gmm_ref.sklearn_em(xs, resp0, max_iter=iters, tol=0.0)
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=cores):
+            gmm_ref.sklearn_em(xs, resp0, max_iter=iters, tol=0.0)
+    else:
+        gmm_ref.sklearn_em(xs, resp0, max_iter=iters, tol=0.0)
     dt = time.perf_counter() - t0
     return len(xs) * iters / dt, dt
 
 
+def _convert_worker(job):
+    from oracle import mlpg_ref
+    (w, m, c), srcs = job
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=1)      # one BLAS thread per worker process
+    except ImportError:
+        limit = None
+    model = mlpg_ref.split_joint(w, m, c, False)
+    for s in srcs:
+        mlpg_ref.transform_vectorised(s, w, m, c, model=model)
+    del limit
+    return sum(len(s) for s in srcs)
+
+
 def cpu_convert(model, src_list, n_sample):
+    """Faithful per-frame restatement on one core, and the vectorised variant over all cores."""
+    import multiprocessing as mp
     from oracle import mlpg_ref
     w, m, c = model
     t0 = time.perf_counter()
@@ -478,36 +642,51 @@ def cpu_convert(model, src_list, n_sample):
         mlpg_ref.transform(s, w, m, c)
         frames += len(s)
     dt = time.perf_counter() - t0
-    return frames / dt, dt
-
-
-def cpu_baselines(feats, x_joint, labels0, model, src_list, em_iters):
     cores = os.cpu_count() or 1
-    n_em = min(len(x_joint), 12000)
-    em_v, em_dt = cpu_em(x_joint, labels0, n_em, em_iters)
+    per = 2
+    jobs = [(model, src_list[i * per:(i + 1) * per]) for i in range(cores)
+            if src_list[i * per:(i + 1) * per]]
+    t1 = time.perf_counter()
+    with mp.get_context('fork').Pool(len(jobs)) as pool:
+        vframes = sum(pool.map(_convert_worker, jobs))
+    vdt = time.perf_counter() - t1
+    return frames / dt, dt, vframes / vdt, vdt, len(jobs)
+
+
+def cpu_baselines(feats, x_joint, model, src_list):
+    cores = os.cpu_count() or 1
+    n_em = min(len(x_joint), CPU_EM_FRAMES)
+    em_v, em_dt = cpu_em(x_joint, n_em, CPU_EM_ITERS)
     n_dtw = min(len(feats), 4 * cores)
     dtw_v, dtw_cells, dtw_dt = cpu_dtw(feats, n_dtw, cores)
-    cv_v, cv_dt = cpu_convert(model, src_list, 2)
+    cv_v, cv_dt, cvv_v, cvv_dt, cv_procs = cpu_convert(model, src_list, 2)
     return {
         'em': {'value': em_v, 'unit': 'frames/s/iter', 'cores': cores, 'kind': 'reference',
                'sample': f'sklearn {__import__("sklearn").__version__} GaussianMixture.fit '
                          f'(the library the reference calls), first {n_em} frames, K={N_MIX_EM}, '
-                         f'{em_iters} iterations, injected init, BLAS threads = all cores, '
-                         f'{em_dt:.1f} s'},
+                         f'{CPU_EM_ITERS} iterations, labels from bench.lloyd_labels, BLAS '
+                         f'threads = all cores, {em_dt:.1f} s'},
         'dtw': {'value': dtw_v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
                 'sample': f'C restatement of FastDTW (oracle/dtw_c.c), {n_dtw} pairs over '
                           f'{cores} processes, {dtw_dt:.2f} s'},
-        'convert': {'value': cv_v, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
-                    'sample': f'faithful per-frame MLPG restatement (oracle/mlpg_ref.py), '
-                              f'2 utterances x {UTT_FRAMES} frames, K={N_MIX_CONVERT}, '
-                              f'{cv_dt:.1f} s'},
+        'convert': {'value': cvv_v, 'unit': 'frames/s', 'cores': cv_procs, 'kind': 'port',
+                    'sample': f'vectorised numpy MLPG restatement '
+                              f'(oracle/mlpg_ref.transform_vectorised), {cv_procs} processes x 2 '
+                              f'utterances x {UTT_FRAMES} frames, K={N_MIX_CONVERT}, {cvv_dt:.1f} s',
+                    'faithful_per_frame': {
+                        'value': cv_v, 'cores': 1,
+                        'sample': f'per-frame restatement (oracle/mlpg_ref.transform), 2 '
+                                  f'utterances, {cv_dt:.1f} s'}},
     }
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path on this box's host cores: sklearn's
-    GaussianMixture.fit for EM (what kwiiyatta/converter/gmm.py:25-26 calls), and the oracle
-    restatements of fastdtw / nnmnkwii MLPG (absent third-party packages) for the stages."""
+    GaussianMixture.fit for EM (what kwiiyatta/converter/gmm.py:25-26 calls) with all host
+    threads, and the oracle restatements of fastdtw / nnmnkwii MLPG (absent third-party
+    packages) for the other two stages.  A step = one EM iteration over a bounded sample of the
+    configs[1] workload: the first CPU_EM_FRAMES joint frames, same initialisation function as
+    the GPU arm."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -516,53 +695,62 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
     cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
-    n_pairs_sample = max(cores, 16)
-    padded, feats = build_dtw_inputs(0, n_pairs_sample)
-    # joint frames of the sample through the oracle chain
-    chunks = []
-    for (a, b), (xf, yf) in zip(padded, feats):
+    # joint frames through the oracle chain until the sample is full
+    chunks, feats, total, i = [], [], 0, 0
+    while total < CPU_EM_FRAMES and i < N_PAIRS:
+        (a, b), = build_dtw_inputs(i, 1)[0]
+        xf, yf = align_ref.make_feature(a.mel_cepstrum.data, a.f0, a.is_voiced), \
+            align_ref.make_feature(b.mel_cepstrum.data, b.f0, b.is_voiced)
+        feats.append((xf, yf))
         _, path = dtw_c.fastdtw(xf, yf, radius=RADIUS, dist=2)
         p = align_ref.trim_even_path(align_ref.strict_filter(path, xf, yf), a.frame_len,
                                      b.frame_len, synth.PAD_LEN)
         src = delta_ref.delta_features(a.mel_cepstrum.data[p[0]][:, 1:])
         tgt = delta_ref.delta_features(b.mel_cepstrum.data[p[1]][:, 1:])
         chunks.append(delta_ref.remove_zeros_frames(np.hstack((src, tgt))))
+        total += len(chunks[-1])
+        i += 1
     x = np.concatenate(chunks)
-    n_em = min(len(x), 12000)
-    labels0 = np.random.default_rng(0).integers(0, N_MIX_EM, len(x))
+    n_em = min(len(x), CPU_EM_FRAMES)
     if W > 0:
-        cpu_em(x, labels0, n_em, 1)
-    em_v, em_dt = cpu_em(x, labels0, n_em, K)
+        cpu_em(x, n_em, W)
+    em_v, em_dt = cpu_em(x, n_em, K)
     dtw_v, _, dtw_dt = cpu_dtw(feats, len(feats), cores)
     w, m, c = synth.make_joint_gmm(N_MIX_CONVERT, seed=0)
     srcs = [delta_ref.delta_features(s) for s in
-            synth.make_source_utterances(2, frames=UTT_FRAMES)]
-    cv_v, cv_dt = cpu_convert((w, m, c), srcs, 2)
+            synth.make_source_utterances(2 * cores, frames=UTT_FRAMES)]
+    cv_v, cv_dt, cvv_v, cvv_dt, cv_procs = cpu_convert((w, m, c), srcs, 2)
     import sklearn
     sample = (f'sklearn {sklearn.__version__} GaussianMixture.fit on the first {n_em} joint '
-              f'frames of {n_pairs_sample} synthetic pairs, K={N_MIX_EM}, {K} iterations, '
-              f'injected init, BLAS threads = all cores')
+              f'frames of the corpus ({len(feats)} pairs), K={N_MIX_EM}, {K} iterations after '
+              f'{W} warm-up iterations, labels from bench.lloyd_labels, BLAS threads = {cores}')
     out = {
         'impl': 'reference',
         'metric': 'GMM-EM frames/s/iter', 'value': em_v, 'unit': 'frames/s/iter',
         'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': em_dt / K * 1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'higher_is_better': True, 'scaling': 'strong' if args.total_pairs else 'weak',
+        'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': 'configs[1] bounded sample: ' + sample,
-                   'n_components': N_MIX_EM, 'dim': int(x.shape[1])},
+                   'n_components': N_MIX_EM, 'dim': int(x.shape[1]), 'frames': int(n_em)},
         'cpu_baseline': {'value': em_v, 'unit': 'frames/s/iter', 'cores': cores,
                          'kind': 'reference', 'sample': sample},
         'e2e': {'value': em_v, 'unit': 'frames/s/iter', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
+        'dtw_cells_per_s': dtw_v,
+        'convert_frames_per_s': cvv_v,
         'stages': {
             'dtw': {'metric': 'DTW cells/s', 'value': dtw_v, 'unit': 'cells/s', 'kind': 'port',
                     'cores': cores,
                     'sample': f'oracle/dtw_c.c FastDTW r={RADIUS}, {len(feats)} pairs over '
                               f'{cores} processes, {dtw_dt:.2f} s'},
-            'convert': {'metric': 'MLPG converted frames/s', 'value': cv_v, 'unit': 'frames/s',
-                        'kind': 'port', 'cores': 1,
-                        'sample': f'oracle/mlpg_ref.py per-frame restatement, 2 x {UTT_FRAMES} '
-                                  f'frames, K={N_MIX_CONVERT}, {cv_dt:.1f} s'},
+            'convert': {'metric': 'MLPG converted frames/s', 'value': cvv_v, 'unit': 'frames/s',
+                        'kind': 'port', 'cores': cv_procs,
+                        'sample': f'oracle/mlpg_ref.transform_vectorised, {cv_procs} processes x '
+                                  f'2 x {UTT_FRAMES} frames, K={N_MIX_CONVERT}, {cvv_dt:.1f} s',
+                        'faithful_per_frame': {'value': cv_v, 'cores': 1,
+                                               'sample': f'oracle/mlpg_ref.transform, 2 x '
+                                                         f'{UTT_FRAMES} frames, {cv_dt:.1f} s'}},
         },
     }
     emit(out)
@@ -576,7 +764,11 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='tc', choices=['fp64', 'tc'],
                     help='tc = split-fp16 tcgen05 contractions (default), fp64 = CUDA-core DFMA')
-    ap.add_argument('--pairs', type=int, default=N_PAIRS, help='pairs per GPU')
+    ap.add_argument('--pairs', type=int, default=N_PAIRS, help='pairs per GPU (weak scaling)')
+    ap.add_argument('--total-pairs', type=int, default=0,
+                    help='strong scaling: this many pairs split over the ranks (configs[2]: 5030)')
+    ap.add_argument('--long-pairs', type=int, default=LONG_PAIRS,
+                    help='configs[3] stage: pairs of 4096 x 4096 frames per GPU (0 = skip)')
     ap.add_argument('--utts', type=int, default=N_UTTS, help='conversion utterances per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

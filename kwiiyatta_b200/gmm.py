@@ -120,6 +120,11 @@ class GaussianMixture:
         self._resp = torch.zeros((k, self._npad), **f64)   # component-major
         self._ws_bytes = lib.kw_gmm_workspace_bytes(n, k, d, self.precision)
         self._ws = torch.empty(max(self._ws_bytes, 1), dtype=torch.uint8, device=dev)
+        # two slots of pinned host memory for the per-iteration scalars (sum log p, n) and the
+        # finalisation flags: copied asynchronously, read half an iteration later
+        self._host_tail = torch.empty((2, 2), dtype=torch.float64).pin_memory()
+        self._host_info = torch.empty((2, k), dtype=torch.int32).pin_memory()
+        self._tickets = 0
 
     def _pack(self, torch, x):
         n, d = x.shape
@@ -185,13 +190,16 @@ class GaussianMixture:
         _lib.check(rc, 'kw_gmm_mstep_finalize')
         self._cur ^= 1
 
+    @staticmethod
+    def _raise_ill_defined():
+        raise ValueError(
+            'Fitting the mixture model failed because some components have ill-defined '
+            'empirical covariance (for instance caused by singleton or collapsed '
+            'samples). Try to decrease the number of components, or increase reg_covar.')
+
     def _check_info(self):
-        info = self._info.cpu().numpy()
-        if info.any():
-            raise ValueError(
-                'Fitting the mixture model failed because some components have ill-defined '
-                'empirical covariance (for instance caused by singleton or collapsed '
-                'samples). Try to decrease the number of components, or increase reg_covar.')
+        if self._info.cpu().numpy().any():
+            self._raise_ill_defined()
 
     # ------------------------------------------------------------------ initialisation
     def _initial_resp(self, torch, x):
@@ -264,41 +272,62 @@ class GaussianMixture:
         return x
 
     def fit(self, X, y=None):
+        """sklearn's fit loop (sklearn/mixture/_base.py:265-278: E-step, M-step, stop when the
+        lower bound of the E-step moved by less than ``tol``), without a host synchronisation on
+        the critical path: the statistics of iteration i + 1 are enqueued BEFORE the host reads
+        iteration i's lower bound, and iteration i + 1 is finalised (the only step that changes
+        the parameters) only once iteration i is known not to have converged.  ``n_iter_``,
+        ``converged_``, ``lower_bounds_`` and the parameters are those of the plain loop."""
+        torch = _lib.require_cuda()
         x = self.initialize(X)
-        lower_bound = -np.inf
         self.lower_bounds_ = []
         self.converged_ = False
-        n_iter = 0
-        for n_iter in range(1, self.max_iter + 1):
-            prev = lower_bound
-            lower_bound = self.em_iteration(x)
+        state = {'prev': -np.inf, 'n_iter': 0}
+
+        def conclude(n_iter, ticket):
+            """Read iteration ``n_iter``'s lower bound; True when the fit stops there."""
+            lower_bound = self._resolve(ticket)
             self.lower_bounds_.append(lower_bound)
-            change = lower_bound - prev
+            change = lower_bound - state['prev']
+            state['prev'] = lower_bound
+            state['n_iter'] = n_iter
             if self.verbose and n_iter % self.verbose_interval == 0:
                 print(f'  Iteration {n_iter}')
             if self.iter_callback is not None:
                 self.iter_callback(self, n_iter, lower_bound)
             if abs(change) < self.tol:
                 self.converged_ = True
-                break
+            return self.converged_
+
+        pending = None
+        for n_iter in range(1, self.max_iter + 1):
+            centres, ticket = self._enqueue_statistics(torch, x)
+            if pending is not None and conclude(*pending):
+                pending = None
+                break           # this iteration's statistics are dropped, nothing was changed
+            self._finalize(torch, centres, weight_norm=0)
+            pending = (n_iter, ticket)
+        if pending is not None:
+            conclude(*pending)
+        self._check_info()
         if self.verbose:
             print(f'Initialization converged: {self.converged_}')
         if not self.converged_ and self.max_iter > 0:
             warnings.warn('Best performing initialization did not converge. Try different '
                           'init parameters, or increase max_iter, tol, or check for '
                           'degenerate data.', ConvergenceWarning)
-        self.n_iter_ = n_iter
-        self.lower_bound_ = lower_bound
+        self.n_iter_ = state['n_iter']
+        self.lower_bound_ = state['prev']
         self._publish()
         self._resp = None
         self._ws = None
         self._x_src = self._x_used = None
         return self
 
-    def em_iteration(self, x):
-        """One EM iteration on device-resident frames ``x`` (E-step, sufficient statistics,
-        all-reduce across ranks, finalisation).  Returns the lower bound of the E-step."""
-        torch = _lib.require_cuda()
+    def _enqueue_statistics(self, torch, x):
+        """E-step, sufficient statistics and their all-reduce for the current parameters, all
+        enqueued; the iteration's scalars travel to pinned host memory behind them.  Returns the
+        centres the statistics are taken around and a ticket for ``_resolve``."""
         centres = self._means[self._cur]
         self._estep(torch, x)
         self._iters_done += 1
@@ -306,10 +335,39 @@ class GaussianMixture:
             self._reorder(torch, x.shape[0])
         self._accumulate(torch, x, centres)
         self._allreduce(torch)
-        tail = self._stats[-2:].cpu().numpy()
-        self._finalize(torch, centres, weight_norm=0)
-        self._check_info()
+        slot = self._tickets & 1
+        self._tickets += 1
+        self._host_tail[slot].copy_(self._stats[-2:], non_blocking=True)
+        self._host_info[slot].copy_(self._info, non_blocking=True)   # of the LAST finalisation
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(x.device))
+        return centres, (slot, event)
+
+    def _resolve(self, ticket):
+        slot, event = ticket
+        event.synchronize()
+        if self._host_info[slot].numpy().any():
+            self._raise_ill_defined()
+        tail = self._host_tail[slot].numpy()
         return float(tail[0] / tail[1])
+
+    def em_iteration(self, x):
+        """One EM iteration on device-resident frames ``x`` (E-step, sufficient statistics,
+        all-reduce across ranks, finalisation).  Returns the lower bound of the E-step."""
+        torch = _lib.require_cuda()
+        centres, ticket = self._enqueue_statistics(torch, x)
+        self._finalize(torch, centres, weight_norm=0)
+        return self._resolve(ticket)
+
+    def em_iteration_async(self, x):
+        """``em_iteration`` without reading anything back: the caller synchronises (and may call
+        ``last_lower_bound``) when it needs to."""
+        torch = _lib.require_cuda()
+        centres, self._last_ticket = self._enqueue_statistics(torch, x)
+        self._finalize(torch, centres, weight_norm=0)
+
+    def last_lower_bound(self):
+        return self._resolve(self._last_ticket)
 
     def _override_init(self, torch):
         """means_init / weights_init replace the initial M-step's values (sklearn

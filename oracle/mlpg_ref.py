@@ -131,3 +131,53 @@ def transform_frames_soft(src, weights, means, covariances, diff=False):
             em[m] = model['tgt_means'][m] + model['cyx'][m] @ xx
         out[i] = post[i] @ em
     return out
+
+
+def transform_vectorised(src, weights, means, covariances, diff=False, model=None):
+    """The same conversion written the way a numpy user would for speed (SURVEY.md section 8d asks
+    for this beside the faithful per-frame loop as the CPU baseline): frames grouped by mixture,
+    one solve per mixture (A_m = S_yx S_xx^-1), banded systems of all static dimensions assembled
+    with array operations and solved by scipy's banded Cholesky.  ``model`` = split_joint(...)
+    to amortise the slicing over utterances."""
+    src = np.asarray(src, dtype=np.float64)
+    if model is None:
+        model = split_joint(weights, means, covariances, diff)
+    t, fd = src.shape
+    sd = fd // len(DELTA_WINDOWS)
+    mix, _ = predict(src, model)
+    e = np.empty((t, fd))
+    dv = np.empty((t, fd))
+    for m in np.unique(mix):
+        rows = mix == m
+        a = np.linalg.solve(model['cxx'][m], model['cyx'][m].T).T          # S_yx S_xx^-1
+        e[rows] = model['tgt_means'][m] + (src[rows] - model['src_means'][m]) @ a.T
+        dv[rows] = (np.diag(model['cyy'][m]) - np.diag(model['cyx'][m])
+                    / np.diag(model['cxx'][m]) * np.diag(model['cxy'][m]))
+    prec = 1.0 / dv
+    pm = prec * e
+    # window coefficients at offsets -1, 0, +1 (DELTA_WINDOWS), zero padded at the edges
+    coeff = np.zeros((len(DELTA_WINDOWS), 3))
+    for w, (l, _, c) in enumerate(DELTA_WINDOWS):
+        coeff[w, 1 - l:1 - l + len(c)] = c
+    y = np.empty((t, sd))
+    ab = np.zeros((3, t))
+    for k in range(sd):
+        ab[:] = 0.0
+        b = np.zeros(t)
+        for w in range(len(DELTA_WINDOWS)):
+            p = prec[:, w * sd + k]
+            q = pm[:, w * sd + k]
+            for oa in (-1, 0, 1):                  # row r touches column r + oa
+                ca = coeff[w, oa + 1]
+                if ca == 0.0:
+                    continue
+                r = np.arange(max(0, -oa), min(t, t - oa))
+                np.add.at(b, r + oa, ca * q[r])
+                for ob in (-1, 0, 1):
+                    cb = coeff[w, ob + 1]
+                    if cb == 0.0 or ob < oa:
+                        continue
+                    rr = r[(r + ob >= 0) & (r + ob < t)]
+                    np.add.at(ab[ob - oa], rr + oa, ca * cb * p[rr])
+        y[:, k] = scipy.linalg.solveh_banded(ab, b, lower=True)
+    return y

@@ -69,3 +69,17 @@ def test_golden_fixture():
                                           diff=bool(diff), return_internals=True)
         assert np.array_equal(mix, g[f'mix_diff{diff}'])
         assert np.abs(y - g[f'y_diff{diff}']).max() <= 1e-10
+
+
+def test_vectorised_variant_equals_the_per_frame_restatement():
+    """bench.py times both as CPU baselines; they are the same function."""
+    w, m, c = synth.make_joint_gmm(8, seed=4)
+    model = mlpg_ref.split_joint(w, m, c, diff=True)
+    for frames in (1, 2, 3, 40, 173):
+        src = delta_ref.delta_features(
+            synth.make_source_utterances(1, frames=max(frames, 2))[0][:frames])
+        for diff in (False, True):
+            exp = mlpg_ref.transform(src, w, m, c, diff=diff)
+            got = mlpg_ref.transform_vectorised(src, w, m, c, diff=diff,
+                                                model=model if diff else None)
+            assert np.abs(got - exp).max() <= 1e-10
