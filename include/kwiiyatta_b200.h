@@ -192,6 +192,16 @@ int kw_convert_soft_batch(int64_t total_frames, const double* src_dev, int n_com
                           int dim_half, const double* prepared_dev, double* out_dev,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Hand-off to the MLSA differential filter: mel-cepstrum -> MLSA filter coefficients,
+ * pysptk.mc2b(mc, alpha) as called at kwiiyatta/filter/mlsa.py:24-29 on the converted
+ * (difference) mel-cepstra: b[M] = mc[M], b[m] = mc[m] - alpha b[m+1].  mc_dev and b_dev are
+ * (total_frames, width) with width = order + 1; zero_power != 0 treats column 0 of the input as
+ * zero (mlsa.py:23 removes the power coefficient first).  In place (b_dev == mc_dev) is allowed.
+ * ------------------------------------------------------------------------------------------ */
+int kw_mc2b(int64_t total_frames, int width, double alpha, int zero_power,
+            const double* mc_dev, double* b_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,8 @@ from . import alignment, fastdtw, hooks
 from .alignment import (align_even, align_even_many, align_many, dtw_feature, dtw_feature_many,
                         make_feature, project_path, project_path_iter, set_pad_silence)
 from .converter import (DeltaFeatureConverter, MapFeatureConverter, MelCepstrumConverter,
-                        MelCepstrumFeatureConverter)
+                        MelCepstrumFeatureConverter, load_converter, save_converter)
+from .mlsa import mc2b, mc2b_many
 from .dataset import (AlignedDataset, Dataset, DeltaFeatureDataset, MapDataset,
                       MelCepstrumDataset, ParallelDataset, TrimmedDataset, align_dataset,
                       joint_array_from_pairs, make_dataset_to_array, map_dataset)
@@ -51,4 +52,5 @@ __all__ = ['fastdtw', 'hooks', 'align', 'align_even', 'align_even_many', 'align_
            'make_dataset_to_array', 'joint_array_from_pairs',
            'MelCepstrumConverter', 'MelCepstrumFeatureConverter', 'DeltaFeatureConverter',
            'MapFeatureConverter', 'B200GMMFeatureConverter', 'FeatureConverter',
+           'save_converter', 'load_converter', 'mc2b', 'mc2b_many',
            'GaussianMixture', 'MLPG', 'DELTA_WINDOWS', 'delta_features']

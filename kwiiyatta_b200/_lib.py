@@ -40,6 +40,7 @@ SIGNATURES = {
     'kw_convert_prepare': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'kw_convert_soft_workspace_bytes': (_sz, [_i64, _i, _i]),
     'kw_convert_soft_batch': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'kw_mc2b': (_i, [_i64, _i, _dbl, _i, _vp, _vp, _vp]),
     'kw_convert_workspace_bytes': (_sz, [_i64, _i, _i, _i]),
     'kw_convert_batch': (_i, [_i, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz,
                               _vp]),
@@ -99,6 +100,29 @@ def ptr(t):
 
 def stream_ptr(torch):
     return torch.cuda.current_stream().cuda_stream
+
+
+def device_guard(device_of):
+    """Decorator: run the call with the CUDA device of its data current, so the C-ABI launches
+    (which go to ``torch.cuda.current_stream()`` of the CURRENT device) land on the GPU that
+    owns the pointers.  ``device_of(self_or_first_arg, *args)`` returns a torch device or None
+    (= leave the current device alone)."""
+    import functools
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def guarded(*args, **kwargs):
+            dev = device_of(*args)
+            if dev is None:
+                return fn(*args, **kwargs)
+            torch = require_cuda()
+            dev = torch.device(dev)
+            if dev.type != 'cuda' or dev.index is None:
+                return fn(*args, **kwargs)
+            with torch.cuda.device(dev):
+                return fn(*args, **kwargs)
+        return guarded
+    return wrap
 
 
 # Pinned staging buffers for the host -> device copy of a batch, kept between calls (pinning is

@@ -91,3 +91,34 @@ def MelCepstrumConverter(use_delta=True, mcep_fs=None, Converter=B200GMMFeatureC
     if use_delta:
         converter = DeltaFeatureConverter(converter)
     return MelCepstrumFeatureConverter(converter, mcep_fs=mcep_fs)
+
+
+def save_converter(converter, path):
+    """Persist a trained ``MelCepstrumConverter(...)`` chain: the back-end's model plus what the
+    layers learned while training (order, sampling rate, frame period)."""
+    layers = {'use_delta': False}
+    node = converter
+    while isinstance(node, MapFeatureConverter):
+        if isinstance(node, MelCepstrumFeatureConverter):
+            layers.update(order=node.order, fs=node.fs,
+                          mcep_fs=-1 if node.mcep_fs is None else node.mcep_fs)
+        if isinstance(node, DeltaFeatureConverter):
+            layers.update(use_delta=True, frame_period=node.frame_period)
+        node = node.base
+    np.savez(path, **node.state_dict(), **{'layer_' + k: v for k, v in layers.items()})
+
+
+def load_converter(path, Converter=B200GMMFeatureConverter, **kwargs):
+    with np.load(path) as data:
+        state = {k: data[k] for k in data.files}
+    layers = {k[6:]: state.pop(k) for k in list(state) if k.startswith('layer_')}
+    backend = Converter(components=int(state['n_components']), verbose=0, **kwargs)
+    backend.load_state_dict(state)
+    node = backend
+    if bool(layers['use_delta']):
+        node = DeltaFeatureConverter(node)
+        node.frame_period = layers['frame_period'].item()
+    mcep_fs = int(layers['mcep_fs'])
+    node = MelCepstrumFeatureConverter(node, mcep_fs=None if mcep_fs < 0 else mcep_fs)
+    node.order, node.fs = int(layers['order']), int(layers['fs'])
+    return node

@@ -40,6 +40,24 @@ __global__ void delta_kernel(int n_utts, const int64_t* __restrict__ off, long l
     o[2 * dim + d] = __dadd_rn(__dadd_rn(xm, __dmul_rn(-2.0, xc)), xp);
 }
 
+// SPTK mc2b as pysptk.mc2b(mc, alpha) computes it (call site kwiiyatta/filter/mlsa.py:24-29):
+// b[M] = mc[M], b[m] = mc[m] - alpha b[m+1]; with zero_power the input's column 0 is taken as 0
+// first (the reference removes the power coefficient before the MLSA filter, mlsa.py:23).
+// One thread per frame.
+__global__ void mc2b_kernel(long long total, int width, double alpha, int zero_power,
+                            const double* __restrict__ in, double* __restrict__ out) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= total) return;
+    const double* mc = in + n * width;
+    double* b = out + n * width;
+    double next = 0.0;
+    for (int m = width - 1; m >= 0; --m) {
+        const double c = (m == 0 && zero_power) ? 0.0 : mc[m];
+        next = (m == width - 1) ? c : __dsub_rn(c, __dmul_rn(alpha, next));
+        b[m] = next;
+    }
+}
+
 }  // namespace kw
 
 using namespace kw;
@@ -71,6 +89,17 @@ extern "C" int kw_delta_features(int n_utts, const int64_t* off_dev, int64_t tot
     const long long n = (long long)total_frames * dim;
     delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_utts, off_dev, total_frames, dim,
                                                               in_dev, out_dev);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
+extern "C" int kw_mc2b(int64_t total_frames, int width, double alpha, int zero_power,
+                       const double* mc_dev, double* b_dev, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total_frames == 0) return KW_OK;
+    KW_REQUIRE(total_frames > 0 && width > 0, "kw_mc2b: bad sizes");
+    mc2b_kernel<<<(unsigned)((total_frames + 127) / 128), 128, 0, st>>>(
+        total_frames, width, alpha, zero_power, mc_dev, b_dev);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }

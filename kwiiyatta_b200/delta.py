@@ -18,6 +18,7 @@ def check_windows(windows):
         raise NotImplementedError('only kwiiyatta DELTA_WINDOWS are built into the kernels')
 
 
+@_lib.device_guard(lambda x_dev, *a: x_dev.device)
 def delta_features_device(x_dev, offsets_dev, n_utts):
     """x_dev (sum T, dim) float64 CUDA tensor, offsets (n_utts + 1) int64 -> (sum T, 3 dim)."""
     torch = _lib.require_cuda()

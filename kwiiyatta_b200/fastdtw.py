@@ -65,6 +65,7 @@ class DtwBatchResult:
 TIE_MODES = {'python': 0, 'cython': 1, 0: 0, 1: 1}
 
 
+@_lib.device_guard(lambda x_dev, *a: x_dev.device)
 def fastdtw_batch_device(x_dev, y_dev, tx, ty, radius=1, dist=2, precision=0, tie_mode='python',
                          with_margin=False):
     """Batched FastDTW on device-resident, row-concatenated float64 inputs.

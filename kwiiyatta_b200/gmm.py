@@ -58,6 +58,9 @@ def _as_device(x, torch, device):
     return t.contiguous()
 
 
+_on_own_device = _lib.device_guard(lambda self, *a: self.device)
+
+
 class GaussianMixture:
     covariance_type = 'full'
 
@@ -225,6 +228,7 @@ class GaussianMixture:
         return r
 
     # ------------------------------------------------------------------ public API
+    @_on_own_device
     def initialize(self, X):
         """Move the frames to the device, allocate the model and run the initial M-step
         (GaussianMixture._initialize).  Returns the device tensor of frames."""
@@ -271,6 +275,7 @@ class GaussianMixture:
         self._check_info()
         return x
 
+    @_on_own_device
     def fit(self, X, y=None):
         """sklearn's fit loop (sklearn/mixture/_base.py:265-278: E-step, M-step, stop when the
         lower bound of the E-step moved by less than ``tol``), without a host synchronisation on
@@ -351,6 +356,7 @@ class GaussianMixture:
         tail = self._host_tail[slot].numpy()
         return float(tail[0] / tail[1])
 
+    @_on_own_device
     def em_iteration(self, x):
         """One EM iteration on device-resident frames ``x`` (E-step, sufficient statistics,
         all-reduce across ranks, finalisation).  Returns the lower bound of the E-step."""
@@ -359,6 +365,7 @@ class GaussianMixture:
         self._finalize(torch, centres, weight_norm=0)
         return self._resolve(ticket)
 
+    @_on_own_device
     def em_iteration_async(self, x):
         """``em_iteration`` without reading anything back: the caller synchronises (and may call
         ``last_lower_bound``) when it needs to."""
@@ -395,6 +402,7 @@ class GaussianMixture:
         pc = self.precisions_cholesky_
         return np.einsum('kij,klj->kil', pc, pc)
 
+    @_on_own_device
     def set_parameters(self, weights, means, covariances):
         """Load an existing model (e.g. a fitted sklearn GaussianMixture's attributes)."""
         torch = _lib.require_cuda()
@@ -419,6 +427,7 @@ class GaussianMixture:
         self._publish()
         return self
 
+    @_on_own_device
     def _posterior(self, X):
         torch = _lib.require_cuda()
         x = _as_device(X, torch, self._weights.device)
@@ -483,6 +492,41 @@ class B200GMMFeatureConverter(FeatureConverter):
     def _train(self, dataarray, **kwargs):
         self._paramgen = {}
         self.gmm.fit(dataarray, **kwargs)
+
+    # ---- model persistence (the reference keeps the trained model in memory only,
+    # kwiiyatta/convert_voice.py:15-20)
+    def state_dict(self):
+        """The fitted model and its hyper-parameters as plain numpy arrays / scalars."""
+        g = self.gmm
+        return {'weights': g.weights_, 'means': g.means_, 'covariances': g.covariances_,
+                'n_components': g.n_components, 'max_iter': g.max_iter, 'tol': g.tol,
+                'reg_covar': g.reg_covar,
+                'random_state': -1 if g.random_state is None else g.random_state,
+                'n_iter': getattr(g, 'n_iter_', 0), 'converged': getattr(g, 'converged_', False),
+                'lower_bound': getattr(g, 'lower_bound_', float('nan'))}
+
+    def load_state_dict(self, state):
+        g = self.gmm
+        g.set_parameters(np.asarray(state['weights']), np.asarray(state['means']),
+                         np.asarray(state['covariances']))
+        g.max_iter, g.tol, g.reg_covar = int(state['max_iter']), float(state['tol']), \
+            float(state['reg_covar'])
+        rs = int(state['random_state'])
+        g.random_state = None if rs < 0 else rs
+        g.n_iter_, g.converged_ = int(state['n_iter']), bool(state['converged'])
+        g.lower_bound_ = float(state['lower_bound'])
+        self._paramgen = {}
+        return self
+
+    def save(self, path):
+        np.savez(path, **self.state_dict())
+
+    @classmethod
+    def load(cls, path, **kwargs):
+        with np.load(path) as state:
+            state = {k: state[k] for k in state.files}
+        conv = cls(components=int(state['n_components']), verbose=0, **kwargs)
+        return conv.load_state_dict(state)
 
     def _mlpg(self, diff, mlpg=True):
         from .mlpg import MLPG

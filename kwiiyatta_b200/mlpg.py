@@ -6,6 +6,9 @@ from . import _lib
 from .delta import DELTA_WINDOWS, check_windows
 
 
+_on_own_device = _lib.device_guard(lambda self, *a: getattr(self, '_dev', None))
+
+
 class MLPG:
     """``MLPG(gmm, windows, diff).transform(src)``.  ``gmm`` is anything with ``weights_``,
     ``means_`` and ``covariances_`` (our GaussianMixture or sklearn's).  The sliced model
@@ -15,6 +18,14 @@ class MLPG:
     def __init__(self, gmm, windows=None, swap=False, diff=False, precision='auto',
                  device=None):
         torch = _lib.require_cuda()
+        self._dev = torch.device('cuda' if device is None else device)
+        if self._dev.index is not None:
+            with torch.cuda.device(self._dev):
+                self._setup(torch, gmm, windows, swap, diff, precision)
+        else:
+            self._setup(torch, gmm, windows, swap, diff, precision)
+
+    def _setup(self, torch, gmm, windows, swap, diff, precision):
         if windows is None:
             windows = DELTA_WINDOWS
         if len(windows) > 1:
@@ -28,7 +39,7 @@ class MLPG:
             raise AssertionError("covariance_type must be 'full'")
         self.windows = windows
         self.diff = bool(diff)
-        dev = torch.device('cuda' if device is None else device)
+        dev = self._dev
         means = np.ascontiguousarray(gmm.means_, dtype=np.float64)
         self.num_mixtures, d = means.shape
         self.dim_half = d // 2
@@ -53,8 +64,8 @@ class MLPG:
         if info.cpu().numpy().any():
             raise np.linalg.LinAlgError('source covariance of some mixture is not positive '
                                         'definite')
-        self._dev = dev
 
+    @_on_own_device
     def transform_device(self, src_dev, offsets_dev, n_utts, max_frames, return_mix=False):
         """src_dev (sum T, dim_half) float64 CUDA tensor, offsets int64 (n_utts + 1)."""
         torch = _lib.require_cuda()
@@ -73,6 +84,7 @@ class MLPG:
         _lib.check(rc, 'kw_convert_batch')
         return (out, mix) if return_mix else out
 
+    @_on_own_device
     def transform_many(self, features):
         torch = _lib.require_cuda()
         feats = [np.ascontiguousarray(f, dtype=np.float64) for f in features]
@@ -88,6 +100,7 @@ class MLPG:
         out = self.transform_device(src, off_dev, len(feats), int(lens.max()))
         return _lib.scatter_to_host(torch, out, off, 'mlpg_out')
 
+    @_on_own_device
     def transform_soft(self, src):
         """MLPGBase.transform: per-frame soft-posterior conditional mean, (T, dim_half)."""
         torch = _lib.require_cuda()

@@ -110,3 +110,39 @@ def test_errors(cuda):
         MLPG(_Model(w, m, c), windows=delta_ref.DELTA_WINDOWS[:2])
     with pytest.raises(ValueError):
         MLPG(_Model(w, m, c)).transform(np.zeros((5, 71)))
+
+
+def test_mc2b_hand_off_to_the_mlsa_filter(cuda):
+    """pysptk.mc2b as called at kwiiyatta/filter/mlsa.py:23-29 (power coefficient zeroed first)."""
+    import kwiiyatta_b200 as kw
+    from oracle import mlsa_ref
+    rng = np.random.default_rng(9)
+    mceps = [rng.standard_normal((t, 25)) for t in (1, 7, 300)] + [np.zeros((0, 25))]
+    got = kw.mc2b_many(mceps, alpha=0.41)
+    for m, g in zip(mceps, got):
+        zeroed = np.hstack((np.zeros((len(m), 1)), m[:, 1:]))
+        assert np.array_equal(g, mlsa_ref.mc2b(zeroed, 0.41))
+    assert np.array_equal(kw.mc2b(mceps[1], 0.55, zero_power=False),
+                          mlsa_ref.mc2b(mceps[1], 0.55))
+
+
+def test_converter_persistence_round_trip(cuda, tmp_path):
+    """save_converter / load_converter: the reloaded chain converts identically (the reference
+    keeps its model in memory only, kwiiyatta/convert_voice.py:15-20)."""
+    import warnings
+    import kwiiyatta_b200 as kw
+    w, m, c = synth.make_joint_gmm(4, seed=8)
+    conv = kw.MelCepstrumConverter(components=4, verbose=0)
+    conv.base.base.gmm.set_parameters(w, m, c)
+    conv.order, conv.fs, conv.base.frame_period = synth.ORDER, synth.FS, synth.FRAME_PERIOD
+    path = str(tmp_path / 'model.npz')
+    kw.save_converter(conv, path)
+    again = kw.load_converter(path)
+    assert (again.order, again.fs, again.frame_period) == (conv.order, conv.fs, conv.frame_period)
+    assert np.array_equal(again.gmm.covariances_, c)
+    mcep = synth.make_pair(4)[0].mel_cepstrum
+    for kwargs in ({}, {'diff': True}, {'mlpg': False}):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            assert np.array_equal(conv.convert(mcep, **kwargs).data,
+                                  again.convert(mcep, **kwargs).data)

@@ -83,3 +83,14 @@ def test_vectorised_variant_equals_the_per_frame_restatement():
             got = mlpg_ref.transform_vectorised(src, w, m, c, diff=diff,
                                                 model=model if diff else None)
             assert np.abs(got - exp).max() <= 1e-10
+
+
+def test_mc2b_recursion_inverts():
+    from oracle import mlsa_ref
+    rng = np.random.default_rng(3)
+    mc = rng.standard_normal((50, 25))
+    for alpha in (0.0, 0.41, 0.55):
+        b = mlsa_ref.mc2b(mc, alpha)
+        assert np.abs(mlsa_ref.b2mc(b, alpha) - mc).max() <= 1e-14
+        assert np.array_equal(b[:, -1], mc[:, -1])
+    assert np.array_equal(mlsa_ref.mc2b(mc, 0.0), mc)
