@@ -193,6 +193,46 @@ int kw_convert_soft_batch(int64_t total_frames, const double* src_dev, int n_com
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-array assembly on the device: from mel-cepstra to the (N, 2*3*order) matrix
+ * GaussianMixture.fit receives, without the joint frames visiting the host.
+ *
+ * kw_dtw_features   make_feature (kwiiyatta/vocoder/align.py:20-58) for n_utts utterances
+ *                   concatenated in mcep_dev (total_frames, width = order + 1), int64 frame offsets
+ *                   off_dev[n_utts + 1]:  out (total_frames, width + 1) = [power flag, voicing flag,
+ *                   mcep[1:]].  voiced_dev: one byte per frame (NULL = no voicing flag);
+ *                   power_mode 0: power_weight where c0 >= threshold_dev[utt] (the caller computes
+ *                   the per-utterance threshold: max / median / min of c0 -/+ the offset, or the
+ *                   fixed value), 1: raw c0, 2: zero.
+ * kw_path_select    strict filter (align.py:73-94, with the :78 quirk: x's VOICING flag is tested
+ *                   against y's POWER flag) and pad trim (align.py:139-145) of the paths
+ *                   kw_dtw_batch produced, in place: pair p's selected points end up at the FRONT
+ *                   of its path region, selected_len_dev[p] of them.  region_off_dev[p] = point
+ *                   index of pair p's region; xoff/yoff_dev[p] = first frame of pair p in the
+ *                   concatenated feature matrices; tx/ty_dev: (padded) lengths.
+ * kw_joint_frames   gather + drop c0 + delta features over the aligned sequence + hstack
+ *                   (vocoder/abc/feature.py:170-194, converter/mcep.py:33, converter/delta.py:30,
+ *                   converter/dataset.py:68): out (total_rows, 2 * (3 or 1) * order), row offsets
+ *                   out_off_dev[n_pairs + 1] = prefix sums of selected_len; zero_flag_dev[row] = 1
+ *                   where the row's absolute sum is not above 1e-7 (remove_zeros_frames,
+ *                   converter/dataset.py:70: the caller drops those rows).
+ * ------------------------------------------------------------------------------------------ */
+int kw_dtw_features(int n_utts, const int64_t* off_dev, int64_t total_frames, int width,
+                    const double* mcep_dev, const uint8_t* voiced_dev,
+                    const double* threshold_dev, int power_mode, double power_weight,
+                    double vuv_weight, double* out_dev, void* stream);
+int kw_path_select(int n_pairs, const int64_t* region_off_dev, const int32_t* path_begin_dev,
+                   const int32_t* path_len_dev, const int32_t* tx_dev, const int32_t* ty_dev,
+                   const int64_t* xoff_dev, const int64_t* yoff_dev, const double* xfeat_dev,
+                   const double* yfeat_dev, int feat_dim, int strict, int check_power,
+                   int check_vuv, int trim, int pad_len, int32_t* path_dev,
+                   int32_t* selected_len_dev, void* stream);
+int kw_joint_frames(int n_pairs, const int64_t* out_off_dev, int64_t total_rows,
+                    const int64_t* region_off_dev, const int32_t* path_dev,
+                    const int64_t* xoff_dev, const int64_t* yoff_dev, const double* xmcep_dev,
+                    const double* ymcep_dev, int width, int use_delta, double* out_dev,
+                    uint8_t* zero_flag_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Hand-off to the MLSA differential filter: mel-cepstrum -> MLSA filter coefficients,
  * pysptk.mc2b(mc, alpha) as called at kwiiyatta/filter/mlsa.py:24-29 on the converted
  * (difference) mel-cepstra: b[M] = mc[M], b[m] = mc[m] - alpha b[m+1].  mc_dev and b_dev are

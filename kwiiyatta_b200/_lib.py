@@ -41,6 +41,10 @@ SIGNATURES = {
     'kw_convert_soft_workspace_bytes': (_sz, [_i64, _i, _i]),
     'kw_convert_soft_batch': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'kw_mc2b': (_i, [_i64, _i, _dbl, _i, _vp, _vp, _vp]),
+    'kw_dtw_features': (_i, [_i, _vp, _i64, _i, _vp, _vp, _vp, _i, _dbl, _dbl, _vp, _vp]),
+    'kw_path_select': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
+                            _i, _vp, _vp, _vp]),
+    'kw_joint_frames': (_i, [_i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'kw_convert_workspace_bytes': (_sz, [_i64, _i, _i, _i]),
     'kw_convert_batch': (_i, [_i, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz,
                               _vp]),

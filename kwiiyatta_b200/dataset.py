@@ -248,13 +248,60 @@ def delta_many(features):
     return [out[off[i]:off[i + 1]] for i in range(len(features))]
 
 
-def make_dataset_to_array(dataset, keys=None):
+def _device_chain(dataset):
+    """(delta or None, mcep, aligned) when ``dataset`` is the standard training chain
+    [DeltaFeatureDataset(] MelCepstrumDataset(AlignedDataset(...)) [)], else None."""
+    delta = dataset if type(dataset) is DeltaFeatureDataset else None
+    mcep = dataset.base if delta is not None else dataset
+    if type(mcep) is not MelCepstrumDataset or type(mcep.base) is not AlignedDataset:
+        return None
+    return delta, mcep, mcep.base
+
+
+def _assemble_on_device(chain, keys):
+    """The standard chain evaluated by kwiiyatta_b200.assemble on the device; None when the
+    request needs a per-item code path (mixed orders / sampling rates / frame periods, which the
+    host path resolves or reports exactly as the reference does)."""
+    from . import assemble
+    delta, mcep, aligned = chain
+    pairs, raws = _fetch(aligned.base, keys)
+    if not pairs or any(not isinstance(p, tuple) or len(p) != 2 for p in pairs):
+        return None
+    feats = [f for pair in pairs for f in pair]
+    order = mcep.order if mcep.order is not None else feats[0].mel_cepstrum_order
+    fs = mcep.fs if mcep.fs is not None else feats[0].fs
+    if any(f.mel_cepstrum_order != order or f.fs != fs for f in feats):
+        return None
+    periods = {r.frame_period for raw in raws for r in raw}
+    if delta is not None:
+        if len(periods) != 1 or delta.frame_period not in (None, next(iter(periods))):
+            return None
+    known = ('pad_silence', 'pad_len', 'vuv', 'power', 'strict', 'radius', 'vuv_weight',
+             'power_weight', 'power_pivot', 'power_threshold')
+    if any(k not in known for k in aligned.kwargs):
+        return None
+    x = assemble.joint_frames_device(pairs, use_delta=delta is not None, **aligned.kwargs)
+    mcep.order, mcep.fs = order, fs               # what the per-item path would have recorded
+    if delta is not None:
+        delta.frame_period = next(iter(periods))
+    return x
+
+
+def make_dataset_to_array(dataset, keys=None, device_resident=False):
     """(N, dim) training matrix: per key the horizontally stacked tuple without its zero frames,
     keys in the given (default: sorted) order (kwiiyatta/converter/dataset.py:61-77).  The whole
-    key list goes down the chain in one request."""
+    key list goes down the chain in one request.  ``device_resident``: for the standard training
+    chain return the matrix as a CUDA tensor assembled on the device
+    (kwiiyatta_b200.assemble), bit-identical to the host result."""
     if keys is None:
         keys = sorted(dataset.keys())
     keys = list(keys)
+    if device_resident and keys:
+        chain = _device_chain(dataset)
+        if chain is not None:
+            x = _assemble_on_device(chain, keys)
+            if x is not None:
+                return x
     if hasattr(dataset, 'get_many'):
         items = dataset.get_many(keys)
     else:
@@ -263,10 +310,16 @@ def make_dataset_to_array(dataset, keys=None):
     return np.concatenate(rows) if rows else None
 
 
-def joint_array_from_pairs(pairs, use_delta=True, pad_silence=True, pad_len=100, **align_kwargs):
+def joint_array_from_pairs(pairs, use_delta=True, pad_silence=True, pad_len=100,
+                           device_resident=False, **align_kwargs):
     """The training-array pipeline for a list of (source, target) features without the dataset
     objects: align_even (batched DTW) -> mcep without c0 (kwiiyatta/converter/mcep.py:33) ->
-    delta features (kwiiyatta/converter/delta.py:30) -> hstack -> remove zero frames."""
+    delta features (kwiiyatta/converter/delta.py:30) -> hstack -> remove zero frames.
+    ``device_resident``: the same array as a CUDA tensor, assembled on the device."""
+    if device_resident:
+        from . import assemble
+        return assemble.joint_frames_device(pairs, use_delta=use_delta, pad_silence=pad_silence,
+                                            pad_len=pad_len, **align_kwargs)
     aligned = _align.align_even_many(pairs, pad_silence=pad_silence, pad_len=pad_len,
                                      **align_kwargs)
     sides = [a.mel_cepstrum.data[:, 1:] for a, _ in aligned] + \

@@ -464,9 +464,14 @@ class FeatureConverter(abc.ABC):
     def _train(self, dataarray, **kwargs):
         raise NotImplementedError
 
+    # a back-end that takes the training matrix as a CUDA tensor gets it assembled on the device
+    accepts_device_array = False
+
     def train(self, dataset, keys, **kwargs):
         from . import dataset as ds
-        self._train(ds.make_dataset_to_array(dataset, keys), **kwargs)
+        self._train(ds.make_dataset_to_array(dataset, keys,
+                                             device_resident=self.accepts_device_array),
+                    **kwargs)
 
     @abc.abstractmethod
     def convert(self, feature, **kwargs):
@@ -475,6 +480,7 @@ class FeatureConverter(abc.ABC):
 
 class B200GMMFeatureConverter(FeatureConverter):
     """Drop-in for GMMFeatureConverter (kwiiyatta/converter/gmm.py:8-34)."""
+    accepts_device_array = True
 
     def __init__(self, components=64, max_iter=100, random_state=None, **kwargs):
         super().__init__()
