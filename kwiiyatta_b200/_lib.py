@@ -132,7 +132,34 @@ def device_guard(device_of):
 # Pinned staging buffers for the host -> device copy of a batch, kept between calls (pinning is
 # far more expensive than the copy).  slot -> (tensor, event of the last copy that read it)
 _STAGING = {}
-_GATHER_THREADS = 8
+_GATHER_THREADS = max(4, min(32, os.cpu_count() or 8))
+_POOL = None
+
+
+def copy_pool():
+    """Threads for host-side copies into / out of pinned memory (numpy releases the GIL)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(_GATHER_THREADS)
+    return _POOL
+
+
+def parallel_copy(jobs):
+    """``jobs``: list of (dst_view, src_array) pairs, copied by the pool; blocks until done."""
+    if not jobs:
+        return
+    total = sum(src.nbytes for _, src in jobs)
+    if total < (1 << 21) or len(jobs) == 1:
+        for dst, src in jobs:
+            dst[...] = src
+        return
+    step = max(1, (len(jobs) + 4 * _GATHER_THREADS - 1) // (4 * _GATHER_THREADS))
+
+    def run(lo):
+        for dst, src in jobs[lo:lo + step]:
+            dst[...] = src
+    list(copy_pool().map(run, range(0, len(jobs), step)))
 
 
 def gather_to_device(torch, arrays, dev, slot):
@@ -153,7 +180,7 @@ def gather_to_device(torch, arrays, dev, slot):
     host = view.numpy()
     off = np.concatenate(([0], np.cumsum(rows)))
     n = len(arrays)
-    step = max(1, (n + _GATHER_THREADS - 1) // _GATHER_THREADS)
+    step = max(1, (n + 4 * _GATHER_THREADS - 1) // (4 * _GATHER_THREADS))
 
     def copy(lo):
         for i in range(lo, min(n, lo + step)):
@@ -162,8 +189,7 @@ def gather_to_device(torch, arrays, dev, slot):
     if total * f * 8 < (1 << 22) or n == 1:
         copy(0) if n == 1 else [copy(lo) for lo in range(0, n, step)]
     else:
-        with ThreadPoolExecutor(_GATHER_THREADS) as ex:
-            list(ex.map(copy, range(0, n, step)))
+        list(copy_pool().map(copy, range(0, n, step)))
     out = view.to(dev, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))
@@ -198,6 +224,5 @@ def scatter_to_host(torch, tensor, offsets, slot):
         for lo in range(0, n, step):
             copy(lo)
     else:
-        with ThreadPoolExecutor(_GATHER_THREADS) as ex:
-            list(ex.map(copy, range(0, n, step)))
+        list(copy_pool().map(copy, range(0, n, step)))
     return out

@@ -84,8 +84,15 @@ class MLPG:
         _lib.check(rc, 'kw_convert_batch')
         return (out, mix) if return_mix else out
 
+    CHUNK_FRAMES = 65536       # frames per pipeline chunk (36 MB in, 12 MB out at Dh = 72)
+
     @_on_own_device
     def transform_many(self, features):
+        """Batched ``transform`` from host arrays to host arrays.  Large batches run as a
+        three-stage pipeline over chunks of utterances: while the kernels of chunk i run, chunk
+        i + 1 is gathered into pinned memory and copied up and the result of chunk i - 1 is
+        copied down and scattered to the output arrays (two pinned buffers per direction, a
+        copy-in and a copy-out stream beside the compute stream)."""
         torch = _lib.require_cuda()
         feats = [np.ascontiguousarray(f, dtype=np.float64) for f in features]
         for f in feats:
@@ -94,11 +101,96 @@ class MLPG:
         lens = np.array([len(f) for f in feats], dtype=np.int64)
         if lens.sum() == 0:
             return [np.zeros((0, self.static_dim)) for _ in feats]
-        off = np.concatenate(([0], np.cumsum(lens)))
-        src = _lib.gather_to_device(torch, feats, self._dev, 'mlpg_in')
-        off_dev = torch.from_numpy(off).to(self._dev, non_blocking=True)
-        out = self.transform_device(src, off_dev, len(feats), int(lens.max()))
-        return _lib.scatter_to_host(torch, out, off, 'mlpg_out')
+        if lens.sum() <= 2 * self.CHUNK_FRAMES:
+            off = np.concatenate(([0], np.cumsum(lens)))
+            src = _lib.gather_to_device(torch, feats, self._dev, 'mlpg_in')
+            off_dev = torch.from_numpy(off).to(self._dev, non_blocking=True)
+            out = self.transform_device(src, off_dev, len(feats), int(lens.max()))
+            return _lib.scatter_to_host(torch, out, off, 'mlpg_out')
+        return self._transform_pipelined(torch, feats, lens)
+
+    def _transform_pipelined(self, torch, feats, lens):
+        dev, dh, sd = self._dev, self.dim_half, self.static_dim
+        # chunks of whole utterances
+        chunks, lo, acc = [], 0, 0
+        for i, t in enumerate(lens):
+            acc += int(t)
+            if acc >= self.CHUNK_FRAMES or i == len(lens) - 1:
+                chunks.append((lo, i + 1))
+                lo, acc = i + 1, 0
+        cap = max(int(lens[a:b].sum()) for a, b in chunks)
+        key = ('mlpg_pipe', str(dev), dh, sd)
+        bufs = _lib._STAGING.get(key)
+        if bufs is None or bufs['cap'] < cap:
+            bufs = {'cap': cap,
+                    'hin': [torch.empty((cap, dh), dtype=torch.float64).pin_memory()
+                            for _ in range(2)],
+                    'hout': [torch.empty((cap, sd), dtype=torch.float64).pin_memory()
+                             for _ in range(2)],
+                    'din': [torch.empty((cap, dh), dtype=torch.float64, device=dev)
+                            for _ in range(2)],
+                    'dout': [torch.empty((cap, sd), dtype=torch.float64, device=dev)
+                             for _ in range(2)],
+                    'streams': (torch.cuda.Stream(dev), torch.cuda.Stream(dev))}
+            _lib._STAGING[key] = bufs
+        s_in, s_out = bufs['streams']
+        compute = torch.cuda.current_stream(dev)
+        outputs = [None] * len(feats)
+        ev_h2d, ev_comp, ev_d2h = {}, {}, {}
+        lib = _lib.lib()
+
+        def scatter(c):
+            a, b = chunks[c]
+            ev_d2h[c].synchronize()
+            host = bufs['hout'][c & 1].numpy()
+            off = np.concatenate(([0], np.cumsum(lens[a:b])))
+            jobs = []
+            for j in range(a, b):
+                outputs[j] = np.empty((int(lens[j]), sd))
+                jobs.append((outputs[j], host[off[j - a]:off[j - a + 1]]))
+            _lib.parallel_copy(jobs)
+
+        for c, (a, b) in enumerate(chunks):
+            n_c = int(lens[a:b].sum())
+            off = np.concatenate(([0], np.cumsum(lens[a:b])))
+            if c >= 2:
+                ev_h2d[c - 2].synchronize()          # pinned input buffer free again
+            host = bufs['hin'][c & 1].numpy()
+            _lib.parallel_copy([(host[off[j - a]:off[j - a + 1]], feats[j]) for j in range(a, b)])
+            with torch.cuda.stream(s_in):
+                if c >= 2:
+                    s_in.wait_event(ev_comp[c - 2])  # device input buffer consumed
+                bufs['din'][c & 1][:n_c].copy_(bufs['hin'][c & 1][:n_c], non_blocking=True)
+                off_dev = torch.from_numpy(off).to(dev, non_blocking=True)
+                ev_h2d[c] = torch.cuda.Event()
+                ev_h2d[c].record(s_in)
+            compute.wait_event(ev_h2d[c])
+            if c >= 2:
+                compute.wait_event(ev_d2h[c - 2])    # device output buffer copied down
+            src = bufs['din'][c & 1][:n_c]
+            out = bufs['dout'][c & 1][:n_c]
+            ws_bytes = lib.kw_convert_workspace_bytes(n_c, self.num_mixtures, dh, self.precision)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            rc = lib.kw_convert_batch(b - a, off_dev.data_ptr(), n_c, int(lens[a:b].max()),
+                                      src.data_ptr(), self.num_mixtures, dh,
+                                      self._prepared.data_ptr(), out.data_ptr(), None,
+                                      self.precision, ws.data_ptr(), ws_bytes,
+                                      compute.cuda_stream)
+            _lib.check(rc, 'kw_convert_batch')
+            off_dev.record_stream(compute)
+            ev_comp[c] = torch.cuda.Event()
+            ev_comp[c].record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[c])
+                if c >= 2:
+                    pass                              # hout[c & 1] was scattered before (below)
+                bufs['hout'][c & 1][:n_c].copy_(out, non_blocking=True)
+                ev_d2h[c] = torch.cuda.Event()
+                ev_d2h[c].record(s_out)
+            if c >= 1:
+                scatter(c - 1)                        # overlaps the kernels of chunk c
+        scatter(len(chunks) - 1)
+        return outputs
 
     @_on_own_device
     def transform_soft(self, src):

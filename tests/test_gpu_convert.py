@@ -146,3 +146,26 @@ def test_converter_persistence_round_trip(cuda, tmp_path):
             warnings.simplefilter('ignore')
             assert np.array_equal(conv.convert(mcep, **kwargs).data,
                                   again.convert(mcep, **kwargs).data)
+
+
+def test_pipelined_transform_many_equals_single_shot(cuda):
+    """The chunked, double-buffered host pipeline of transform_many (copy-in / kernels / copy-out
+    on three streams) returns what one launch over the whole batch returns."""
+    w, m, c = synth.make_joint_gmm(8, seed=11)
+    rng = np.random.default_rng(4)
+    base = _sources(4, 400)
+    src = [base[i % 4][:int(t)] + rng.normal(0, 0.01, (int(t), 72))
+           for i, t in enumerate(rng.integers(1, 400, 60))]
+    for precision in ('fp64', 'tc'):
+        paramgen = MLPG(_Model(w, m, c), precision=precision)
+        paramgen.CHUNK_FRAMES = 10 ** 9
+        single = paramgen.transform_many(src)
+        for chunk in (1500, 4000):
+            paramgen.CHUNK_FRAMES = chunk
+            piped = paramgen.transform_many(src)
+            assert len(piped) == len(single)
+            for a, b in zip(piped, single):
+                assert a.shape == b.shape and np.array_equal(a, b)
+        # twice in a row: the staging buffers and streams are reused
+        again = paramgen.transform_many(src)
+        assert all(np.array_equal(a, b) for a, b in zip(again, single))
