@@ -263,15 +263,24 @@ def run_b200(args):
     cells_total = sum_over_ranks(cells_local)
     nominal_total = sum_over_ranks(nominal_local)
     dtw_cells_per_s = cells_total * K / (dtw_ms / 1e3)
-    # end to end through the fastdtw-compatible API: host features in, host paths out
-    kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)     # warm-up (pins the staging)
+    # end to end through the batched host API: features in pinned host memory in, host paths out
+    x_pin, y_pin = torch.from_numpy(x_host).pin_memory(), torch.from_numpy(y_host).pin_memory()
+    kfd.fastdtw_batch_packed(x_pin, y_pin, tx, ty, radius=RADIUS, dist=2, device=dev)  # warm-up
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)
+    kfd.fastdtw_batch_packed(x_pin, y_pin, tx, ty, radius=RADIUS, dist=2, device=dev)
     torch.cuda.synchronize()
     dtw_e2e_s = time.perf_counter() - t0
     dtw_e2e = sum_over_ranks(cells_local) / max_over_ranks(dtw_e2e_s * 1e3) * 1e3
+    # ... and from a list of separate pageable arrays (fastdtw_batch: host copies included)
+    kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kfd.fastdtw_batch(feats, radius=RADIUS, dist=2, device=dev)
+    torch.cuda.synchronize()
+    dtw_e2e_lists = cells_local / (time.perf_counter() - t0)
+    del x_pin, y_pin
 
     # ---------------- joint frames for EM (align_even -> mcep -> delta -> hstack) ----------
     kw.set_pad_silence(lambda f, n: f)     # the synthetic features are already padded
@@ -431,14 +440,25 @@ def run_b200(args):
     conv_flops = (2.0 * N_MIX_CONVERT + 2.0) * conv_frames_total * 72 * 72
     src_host = src_dev.cpu().numpy()
     src_list = [src_host[i * UTT_FRAMES:(i + 1) * UTT_FRAMES] for i in range(n_utts)]
-    paramgen.transform_many(src_list[:max(1, n_utts // 8)])     # warm-up (pins the staging)
-    paramgen.transform_many(src_list)
+    # end to end: source frames in one pinned host block -> converted frames in a pinned block
+    src_pin = torch.from_numpy(src_host).pin_memory()
+    out_pin = torch.empty((n_utts * UTT_FRAMES, 24), dtype=torch.float64).pin_memory()
+    utt_lens = [UTT_FRAMES] * n_utts
+    paramgen.transform_packed(src_pin, utt_lens, out=out_pin)     # warm-up (buffers, streams)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    paramgen.transform_many(src_list)
+    paramgen.transform_packed(src_pin, utt_lens, out=out_pin)
     torch.cuda.synchronize()
     conv_e2e = conv_frames_total / (max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3)
+    # ... and from / to lists of separate pageable arrays (host copies included)
+    paramgen.transform_many(src_list)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    paramgen.transform_many(src_list)
+    torch.cuda.synchronize()
+    conv_e2e_lists = n_utts * UTT_FRAMES / (time.perf_counter() - t0)
+    del src_pin, out_pin
 
     clock_info = clocks.stop() if rank == 0 else None
 
@@ -553,7 +573,9 @@ def run_b200(args):
                              'model': 'SMs x 64 FP64 lanes x f_max / 72 FP64-pipe ops per cell'},
                 'e2e': {'value': dtw_e2e, 'unit': 'cells/s',
                         'h2d_bytes_per_step': int(x_host.nbytes + y_host.nbytes),
-                        'd2h_bytes_per_step': int(8 * (tx.sum() + ty.sum()) + 20 * n_pairs)},
+                        'd2h_bytes_per_step': int(8 * (tx.sum() + ty.sum()) + 20 * n_pairs),
+                        'api': 'fastdtw_batch_packed (pinned host blocks in, host paths out)',
+                        'from_lists_of_pageable_arrays': dtw_e2e_lists},
                 'cpu_baseline': cpu['dtw'] if cpu else None,
             },
             'convert': {
@@ -571,7 +593,9 @@ def run_b200(args):
                                       'boundary is only hbm_boundary_gbs, far from the HBM bound'},
                 'e2e': {'value': conv_e2e, 'unit': 'frames/s',
                         'h2d_bytes_per_step': int(n_utts * UTT_FRAMES * 72 * 8),
-                        'd2h_bytes_per_step': int(n_utts * UTT_FRAMES * 24 * 8)},
+                        'd2h_bytes_per_step': int(n_utts * UTT_FRAMES * 24 * 8),
+                        'api': 'MLPG.transform_packed (pinned host block in, pinned block out)',
+                        'from_lists_of_pageable_arrays': conv_e2e_lists},
                 'cpu_baseline': cpu['convert'] if cpu else None,
             },
         },

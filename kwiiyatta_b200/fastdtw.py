@@ -50,16 +50,12 @@ class DtwBatchResult:
         self.region_off = np.concatenate(([0], np.cumsum(region)))
 
     def to_host(self):
-        """list of (distance: float, path: (L, 2) int32 ndarray) plus total cells."""
-        cost = self.cost.cpu().numpy()
+        """list of (distance: float, path: (L, 2) int32 ndarray)."""
+        cost = self.cost.cpu().tolist()
         path = self.path.cpu().numpy()
-        begin = self.path_begin.cpu().numpy()
-        length = self.path_len.cpu().numpy()
-        out = []
-        for p in range(len(cost)):
-            s = int(self.region_off[p]) + int(begin[p])
-            out.append((float(cost[p]), path[s:s + int(length[p])]))
-        return out
+        first = (self.region_off[:-1] + self.path_begin.cpu().numpy()).tolist()
+        length = self.path_len.cpu().tolist()
+        return [(cost[p], path[first[p]:first[p] + length[p]]) for p in range(len(cost))]
 
 
 TIE_MODES = {'python': 0, 'cython': 1, 0: 0, 1: 1}
@@ -131,6 +127,64 @@ def fastdtw_batch(pairs, radius=1, dist=2, precision=0, device=None, tie_mode='p
     if with_margin:
         return res.to_host(), res.margin.cpu().numpy()
     return res.to_host()
+
+
+def fastdtw_batch_packed(x_host, y_host, tx, ty, radius=1, dist=2, precision=0,
+                         tie_mode='python', device=None, n_chunks=None):
+    """Batched FastDTW from two host tensors holding all x (sum tx, F) and all y (sum ty, F)
+    rows -- pinned memory for full speed.  The pairs are split into chunks that go through
+    copy-in / kernels / copy-out on separate streams, so the upload of one chunk overlaps the
+    kernels of the previous one.  Returns the list ``fastdtw_batch`` returns."""
+    torch = _lib.require_cuda()
+    dev = torch.device('cuda' if device is None else device)
+    tx = np.ascontiguousarray(tx, dtype=np.int32)
+    ty = np.ascontiguousarray(ty, dtype=np.int32)
+    n = len(tx)
+    if n == 0:
+        return []
+    if x_host.shape[1] != y_host.shape[1]:
+        raise ValueError('second dimension of x and y must be the same')
+    if n_chunks is None:
+        n_chunks = 2 if n >= 296 else 1          # keep >= one wave of CTAs (148 SMs) per chunk
+    xrow = np.concatenate(([0], np.cumsum(tx.astype(np.int64))))
+    yrow = np.concatenate(([0], np.cumsum(ty.astype(np.int64))))
+    bounds = [n * c // n_chunks for c in range(n_chunks + 1)]
+    results = []
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(n_chunks)] if n_chunks > 1 else [main]
+        start = torch.cuda.Event()
+        start.record(main)
+        parts = []
+        for c in range(n_chunks):
+            a, b = bounds[c], bounds[c + 1]
+            st = streams[c]
+            with torch.cuda.stream(st):
+                st.wait_event(start)
+                xd = x_host[int(xrow[a]):int(xrow[b])].to(dev, non_blocking=True)
+                yd = y_host[int(yrow[a]):int(yrow[b])].to(dev, non_blocking=True)
+                res = fastdtw_batch_device(xd, yd, tx[a:b], ty[a:b], radius, dist, precision,
+                                           tie_mode)
+                host = {k: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                        for k, t in (('cost', res.cost), ('path', res.path),
+                                     ('begin', res.path_begin), ('len', res.path_len))}
+                host['cost'].copy_(res.cost, non_blocking=True)
+                host['path'].copy_(res.path, non_blocking=True)
+                host['begin'].copy_(res.path_begin, non_blocking=True)
+                host['len'].copy_(res.path_len, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(st)
+            parts.append((res, host, done, (xd, yd)))
+        for res, host, done, _ in parts:
+            done.synchronize()
+            main.wait_event(done)
+            cost = host['cost'].tolist()
+            path = host['path'].numpy()
+            first = (res.region_off[:-1] + host['begin'].numpy()).tolist()
+            length = host['len'].tolist()
+            results.extend((cost[p], path[first[p]:first[p] + length[p]])
+                           for p in range(len(cost)))
+    return results
 
 
 def fastdtw(x, y, radius=1, dist=None):

@@ -88,45 +88,69 @@ class MLPG:
 
     @_on_own_device
     def transform_many(self, features):
-        """Batched ``transform`` from host arrays to host arrays.  Large batches run as a
-        three-stage pipeline over chunks of utterances: while the kernels of chunk i run, chunk
-        i + 1 is gathered into pinned memory and copied up and the result of chunk i - 1 is
-        copied down and scattered to the output arrays (two pinned buffers per direction, a
-        copy-in and a copy-out stream beside the compute stream)."""
+        """Batched ``transform`` from a list of host arrays to a list of host arrays: one
+        multi-threaded gather into pinned memory, ``transform_packed``, one scatter.  (With
+        separate pageable arrays on both sides the host copies bound this call; callers that
+        keep their frames in one pinned block use ``transform_packed`` directly.)"""
         torch = _lib.require_cuda()
         feats = [np.ascontiguousarray(f, dtype=np.float64) for f in features]
         for f in feats:
             if f.ndim != 2 or f.shape[1] != self.dim_half:
                 raise ValueError(f'expected (T, {self.dim_half}) features, got {f.shape}')
         lens = np.array([len(f) for f in feats], dtype=np.int64)
-        if lens.sum() == 0:
+        total = int(lens.sum())
+        if total == 0:
             return [np.zeros((0, self.static_dim)) for _ in feats]
-        if lens.sum() <= 2 * self.CHUNK_FRAMES:
-            off = np.concatenate(([0], np.cumsum(lens)))
-            src = _lib.gather_to_device(torch, feats, self._dev, 'mlpg_in')
-            off_dev = torch.from_numpy(off).to(self._dev, non_blocking=True)
-            out = self.transform_device(src, off_dev, len(feats), int(lens.max()))
-            return _lib.scatter_to_host(torch, out, off, 'mlpg_out')
-        return self._transform_pipelined(torch, feats, lens)
+        off = np.concatenate(([0], np.cumsum(lens)))
+        key = ('mlpg_many', str(self._dev))
+        bufs = _lib._STAGING.get(key)
+        if bufs is None or bufs[0].shape[0] < total or bufs[0].shape[1] != self.dim_half \
+                or bufs[1].shape[1] != self.static_dim:
+            bufs = (torch.empty((total, self.dim_half), dtype=torch.float64).pin_memory(),
+                    torch.empty((total, self.static_dim), dtype=torch.float64).pin_memory())
+            _lib._STAGING[key] = bufs
+        hin, hout = bufs[0][:total], bufs[1][:total]
+        host = hin.numpy()
+        _lib.parallel_copy([(host[off[i]:off[i + 1]], feats[i]) for i in range(len(feats))])
+        self.transform_packed(hin, lens, out=hout)
+        res = hout.numpy()
+        outputs = [np.empty((int(t), self.static_dim)) for t in lens]
+        _lib.parallel_copy([(outputs[i], res[off[i]:off[i + 1]]) for i in range(len(feats))])
+        return outputs
 
-    def _transform_pipelined(self, torch, feats, lens):
+    @_on_own_device
+    def transform_packed(self, src, lens, out=None):
+        """Conversion of utterances packed row-wise in ONE host tensor ``src`` (sum T, dim_half)
+        float64 -- pinned memory for full speed -- with lengths ``lens``; returns (and, when
+        given, fills) the host tensor ``out`` (sum T, static_dim).  Runs as a three-stage
+        pipeline over chunks of whole utterances: while the kernels of chunk i run, chunk i + 1
+        is copied up and the result of chunk i - 1 is copied down (a copy-in and a copy-out
+        stream beside the compute stream, two device buffers per direction); synchronised on
+        return."""
+        torch = _lib.require_cuda()
         dev, dh, sd = self._dev, self.dim_half, self.static_dim
-        # chunks of whole utterances
+        lens = np.asarray(lens, dtype=np.int64)
+        total = int(lens.sum())
+        if tuple(src.shape) != (total, dh) or src.dtype != torch.float64 or src.is_cuda:
+            raise ValueError(f'src must be a host float64 tensor of shape ({total}, {dh})')
+        if out is None:
+            out = torch.empty((total, sd), dtype=torch.float64).pin_memory()
+        elif tuple(out.shape) != (total, sd) or out.dtype != torch.float64 or out.is_cuda:
+            raise ValueError(f'out must be a host float64 tensor of shape ({total}, {sd})')
+        if total == 0:
+            return out
+        rows = np.concatenate(([0], np.cumsum(lens)))
         chunks, lo, acc = [], 0, 0
         for i, t in enumerate(lens):
             acc += int(t)
             if acc >= self.CHUNK_FRAMES or i == len(lens) - 1:
                 chunks.append((lo, i + 1))
                 lo, acc = i + 1, 0
-        cap = max(int(lens[a:b].sum()) for a, b in chunks)
+        cap = max(int(rows[b] - rows[a]) for a, b in chunks)
         key = ('mlpg_pipe', str(dev), dh, sd)
         bufs = _lib._STAGING.get(key)
         if bufs is None or bufs['cap'] < cap:
             bufs = {'cap': cap,
-                    'hin': [torch.empty((cap, dh), dtype=torch.float64).pin_memory()
-                            for _ in range(2)],
-                    'hout': [torch.empty((cap, sd), dtype=torch.float64).pin_memory()
-                             for _ in range(2)],
                     'din': [torch.empty((cap, dh), dtype=torch.float64, device=dev)
                             for _ in range(2)],
                     'dout': [torch.empty((cap, sd), dtype=torch.float64, device=dev)
@@ -135,62 +159,48 @@ class MLPG:
             _lib._STAGING[key] = bufs
         s_in, s_out = bufs['streams']
         compute = torch.cuda.current_stream(dev)
-        outputs = [None] * len(feats)
-        ev_h2d, ev_comp, ev_d2h = {}, {}, {}
+        start = torch.cuda.Event()
+        start.record(compute)
+        s_in.wait_event(start)            # buffers may still be in use by the previous call
+        s_out.wait_event(start)
+        ev_comp, ev_d2h = {}, {}
         lib = _lib.lib()
-
-        def scatter(c):
-            a, b = chunks[c]
-            ev_d2h[c].synchronize()
-            host = bufs['hout'][c & 1].numpy()
-            off = np.concatenate(([0], np.cumsum(lens[a:b])))
-            jobs = []
-            for j in range(a, b):
-                outputs[j] = np.empty((int(lens[j]), sd))
-                jobs.append((outputs[j], host[off[j - a]:off[j - a + 1]]))
-            _lib.parallel_copy(jobs)
-
+        keep = []
         for c, (a, b) in enumerate(chunks):
-            n_c = int(lens[a:b].sum())
-            off = np.concatenate(([0], np.cumsum(lens[a:b])))
-            if c >= 2:
-                ev_h2d[c - 2].synchronize()          # pinned input buffer free again
-            host = bufs['hin'][c & 1].numpy()
-            _lib.parallel_copy([(host[off[j - a]:off[j - a + 1]], feats[j]) for j in range(a, b)])
+            r0, r1 = int(rows[a]), int(rows[b])
+            n_c = r1 - r0
+            off = rows[a:b + 1] - r0
             with torch.cuda.stream(s_in):
                 if c >= 2:
-                    s_in.wait_event(ev_comp[c - 2])  # device input buffer consumed
-                bufs['din'][c & 1][:n_c].copy_(bufs['hin'][c & 1][:n_c], non_blocking=True)
+                    s_in.wait_event(ev_comp[c - 2])      # device input buffer consumed
+                bufs['din'][c & 1][:n_c].copy_(src[r0:r1], non_blocking=True)
                 off_dev = torch.from_numpy(off).to(dev, non_blocking=True)
-                ev_h2d[c] = torch.cuda.Event()
-                ev_h2d[c].record(s_in)
-            compute.wait_event(ev_h2d[c])
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            compute.wait_event(ev_in)
             if c >= 2:
-                compute.wait_event(ev_d2h[c - 2])    # device output buffer copied down
-            src = bufs['din'][c & 1][:n_c]
-            out = bufs['dout'][c & 1][:n_c]
+                compute.wait_event(ev_d2h[c - 2])        # device output buffer copied down
+            chunk_in, chunk_out = bufs['din'][c & 1][:n_c], bufs['dout'][c & 1][:n_c]
             ws_bytes = lib.kw_convert_workspace_bytes(n_c, self.num_mixtures, dh, self.precision)
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
             rc = lib.kw_convert_batch(b - a, off_dev.data_ptr(), n_c, int(lens[a:b].max()),
-                                      src.data_ptr(), self.num_mixtures, dh,
-                                      self._prepared.data_ptr(), out.data_ptr(), None,
+                                      chunk_in.data_ptr(), self.num_mixtures, dh,
+                                      self._prepared.data_ptr(), chunk_out.data_ptr(), None,
                                       self.precision, ws.data_ptr(), ws_bytes,
                                       compute.cuda_stream)
             _lib.check(rc, 'kw_convert_batch')
             off_dev.record_stream(compute)
+            keep.append(off)
             ev_comp[c] = torch.cuda.Event()
             ev_comp[c].record(compute)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_comp[c])
-                if c >= 2:
-                    pass                              # hout[c & 1] was scattered before (below)
-                bufs['hout'][c & 1][:n_c].copy_(out, non_blocking=True)
+                out[r0:r1].copy_(chunk_out, non_blocking=True)
                 ev_d2h[c] = torch.cuda.Event()
                 ev_d2h[c].record(s_out)
-            if c >= 1:
-                scatter(c - 1)                        # overlaps the kernels of chunk c
-        scatter(len(chunks) - 1)
-        return outputs
+        ev_d2h[len(chunks) - 1].synchronize()
+        compute.wait_event(ev_d2h[len(chunks) - 1])
+        return out
 
     @_on_own_device
     def transform_soft(self, src):

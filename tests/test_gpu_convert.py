@@ -148,24 +148,34 @@ def test_converter_persistence_round_trip(cuda, tmp_path):
                                   again.convert(mcep, **kwargs).data)
 
 
-def test_pipelined_transform_many_equals_single_shot(cuda):
-    """The chunked, double-buffered host pipeline of transform_many (copy-in / kernels / copy-out
-    on three streams) returns what one launch over the whole batch returns."""
+def test_pipelined_transform_packed_equals_single_shot(cuda):
+    """transform_packed (chunks of utterances through copy-in / kernels / copy-out on three
+    streams, from one pinned block to one pinned block) returns what one launch over the whole
+    batch returns, and transform_many is the same thing from and to lists."""
+    import torch
     w, m, c = synth.make_joint_gmm(8, seed=11)
     rng = np.random.default_rng(4)
     base = _sources(4, 400)
     src = [base[i % 4][:int(t)] + rng.normal(0, 0.01, (int(t), 72))
            for i, t in enumerate(rng.integers(1, 400, 60))]
+    lens = [len(s) for s in src]
+    off = np.concatenate(([0], np.cumsum(lens)))
+    packed = torch.from_numpy(np.concatenate(src)).pin_memory()
     for precision in ('fp64', 'tc'):
         paramgen = MLPG(_Model(w, m, c), precision=precision)
-        paramgen.CHUNK_FRAMES = 10 ** 9
-        single = paramgen.transform_many(src)
-        for chunk in (1500, 4000):
+        single = paramgen.transform_device(packed.cuda(), torch.from_numpy(off).cuda(), len(src),
+                                           max(lens)).cpu().numpy()
+        for chunk in (1500, 4000, 10 ** 9):
             paramgen.CHUNK_FRAMES = chunk
-            piped = paramgen.transform_many(src)
-            assert len(piped) == len(single)
-            for a, b in zip(piped, single):
-                assert a.shape == b.shape and np.array_equal(a, b)
-        # twice in a row: the staging buffers and streams are reused
-        again = paramgen.transform_many(src)
-        assert all(np.array_equal(a, b) for a, b in zip(again, single))
+            out = paramgen.transform_packed(packed, lens)
+            assert np.array_equal(out.numpy(), single)
+            many = paramgen.transform_many(src)
+            assert all(np.array_equal(many[i], single[off[i]:off[i + 1]])
+                       for i in range(len(src)))
+        # into a caller-provided pinned buffer, twice in a row (buffers and streams are reused)
+        buf = torch.empty((int(off[-1]), 24), dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            assert paramgen.transform_packed(packed, lens, out=buf) is buf
+            assert np.array_equal(buf.numpy(), single)
+    with pytest.raises(ValueError):
+        paramgen.transform_packed(packed[:, :10], lens)

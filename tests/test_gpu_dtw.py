@@ -262,3 +262,20 @@ def test_margin_variant_returns_the_same_paths(cuda):
         for (c1, p1), (c2, p2) in zip(plain, with_m):
             assert c1 == c2 and np.array_equal(p1, p2)
         assert (margins > 0).all()
+
+
+def test_packed_host_api_equals_the_list_api(cuda):
+    import torch
+    rng = np.random.default_rng(21)
+    pairs = [_rand_pair(rng, int(tx), int(ty), 6)
+             for tx, ty in rng.integers(20, 200, (301, 2))]
+    tx = [len(x) for x, _ in pairs]
+    ty = [len(y) for _, y in pairs]
+    xh = torch.from_numpy(np.concatenate([x for x, _ in pairs])).pin_memory()
+    yh = torch.from_numpy(np.concatenate([y for _, y in pairs])).pin_memory()
+    expected = kfd.fastdtw_batch(pairs, radius=3, dist=2)
+    for n_chunks in (None, 1, 3):
+        got = kfd.fastdtw_batch_packed(xh, yh, tx, ty, radius=3, dist=2, n_chunks=n_chunks)
+        assert len(got) == len(expected)
+        for (c1, p1), (c2, p2) in zip(got, expected):
+            assert c1 == c2 and np.array_equal(p1, p2)
