@@ -152,7 +152,20 @@ def fastdtw_batch_packed(x_host, y_host, tx, ty, radius=1, dist=2, precision=0,
     results = []
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
-        streams = [torch.cuda.Stream(dev) for _ in range(n_chunks)] if n_chunks > 1 else [main]
+        # streams and pinned result buffers live across calls: the caching allocator keeps one
+        # pool per stream, and pinning is far more expensive than the copies
+        key = ('dtw_packed', str(dev))
+        cache = _lib._STAGING.setdefault(key, {'streams': [], 'host': {}})
+        while len(cache['streams']) < n_chunks:
+            cache['streams'].append(torch.cuda.Stream(dev))
+        streams = cache['streams'][:n_chunks] if n_chunks > 1 else [main]
+
+        def pinned(slot, name, like):
+            buf = cache['host'].get((slot, name))
+            if buf is None or buf.numel() < like.numel() or buf.dtype != like.dtype:
+                buf = torch.empty(max(like.numel(), 1), dtype=like.dtype).pin_memory()
+                cache['host'][(slot, name)] = buf
+            return buf[:like.numel()].view(like.shape)
         start = torch.cuda.Event()
         start.record(main)
         parts = []
@@ -165,7 +178,7 @@ def fastdtw_batch_packed(x_host, y_host, tx, ty, radius=1, dist=2, precision=0,
                 yd = y_host[int(yrow[a]):int(yrow[b])].to(dev, non_blocking=True)
                 res = fastdtw_batch_device(xd, yd, tx[a:b], ty[a:b], radius, dist, precision,
                                            tie_mode)
-                host = {k: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host = {k: pinned(c, k, t)
                         for k, t in (('cost', res.cost), ('path', res.path),
                                      ('begin', res.path_begin), ('len', res.path_len))}
                 host['cost'].copy_(res.cost, non_blocking=True)
@@ -179,7 +192,7 @@ def fastdtw_batch_packed(x_host, y_host, tx, ty, radius=1, dist=2, precision=0,
             done.synchronize()
             main.wait_event(done)
             cost = host['cost'].tolist()
-            path = host['path'].numpy()
+            path = host['path'].numpy().copy()       # the pinned buffer is reused by the next call
             first = (res.region_off[:-1] + host['begin'].numpy()).tolist()
             length = host['len'].tolist()
             results.extend((cost[p], path[first[p]:first[p] + length[p]])

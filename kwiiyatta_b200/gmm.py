@@ -177,10 +177,9 @@ class GaussianMixture:
         _lib.check(rc, 'kw_gmm_mstep_accumulate')
 
     def _allreduce(self, torch):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            if dist.get_world_size(self.process_group) > 1:
-                dist.all_reduce(self._stats, group=self.process_group)
+        """The path's one exchange: sum of the statistics vector over the ranks."""
+        from . import dist as kdist
+        kdist.allreduce_stats(self._stats, self.process_group)
 
     def _finalize(self, torch, centres, weight_norm):
         k, d = centres.shape

@@ -26,7 +26,8 @@ def _worker(rank, world, port, x, resp0, precision, out):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world,
                             device_id=torch.device('cuda', rank))
-    lo, hi = (0, len(x) // 2) if rank == 0 else (len(x) // 2, len(x))
+    cut = int(len(x) * 0.37)                  # unequal shards
+    lo, hi = (0, cut) if rank == 0 else (cut, len(x))
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         gm = GaussianMixture(n_components=resp0.shape[1], max_iter=5, tol=0.0,
