@@ -198,6 +198,25 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, const uint
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t* r) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm2(uint32_t addr, uint32_t* r) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+// registers -> TMEM: this thread's lane, 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+          "r"(v[7])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 template <int R> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
 }
@@ -228,7 +247,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // hi, lo * 2^11 (E-step) and lo unscaled (M-step).
 __host__ __device__ inline int dpb_of(int DP) { return DP + 16; }
 __host__ __device__ inline size_t tile_elems(int DP) { return (size_t)TILE_M * dpb_of(DP); }
-constexpr int X_PARTS = 3;
+constexpr int X_PARTS = 5;   // hi, lo*2^11 (E-step), lo, and K-major hi / lo for the M-step
 // L_k is upper triangular, so B[j][d] = L[d][j] vanishes for j < d.  B is stored per 16-wide
 // k-step: block ks holds the row groups jg >= 2*ks only, each as two adjacent 8x8 core matrices
 // (LBO = 128 B between them, SBO = 256 B between row groups).  Offsets in halves.
@@ -341,6 +360,11 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
     __half* hi = xt + (size_t)tile * X_PARTS * tile_elems(DP);
     __half* lo_s = hi + tile_elems(DP);
     __half* lo_u = lo_s + tile_elems(DP);
+    // M-step operands, K-major (8 x 8 cores with the FRAMES contiguous) per 64-frame tile:
+    // element (feature c, frame r) of M-tile r / 64 at  (r/64) 64 DPB + ((c/8) 8 + (r%64)/8) 64
+    // + (c%8) 8 + r%8
+    __half* hi_k = lo_u + tile_elems(DP);
+    __half* lo_k = hi_k + tile_elems(DP);
     const int kg_n = DPB / 8;
     for (int e = threadIdx.x; e < TILE_M * DPB; e += blockDim.x) {
         const int r = e / DPB, c = e - r * DPB;
@@ -354,6 +378,10 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
         hi[o] = h;
         lo_s[o] = __double2half(res * LO_SCALE);
         lo_u[o] = __double2half(res);
+        const size_t ok = (size_t)(r >> 6) * 64 * DPB + ((size_t)(c >> 3) * 8 + ((r & 63) >> 3)) * 64 +
+                          (c & 7) * 8 + (r & 7);
+        hi_k[ok] = h;
+        lo_k[ok] = __double2half(res);
     }
 }
 
@@ -1522,6 +1550,520 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core M-step statistics, second generation: the generated operand lives in TENSOR MEMORY.
+//
+// The first-generation kernel above writes A = r (x' - mu') to shared memory and the MMAs read it
+// back from there; with the packed frames B, the bulk copies and the generators' own reads that is
+// 230 KB of shared-memory traffic per (tile, component) against 85 clk x 12 MMAs of tensor time,
+// and the shared-memory pipe is what bounds it (profiles/ncu_r1d_mstats_tc.txt: 49 % LSU
+// wavefronts + the MMA operand reads, tensor pipe 38 %).  Here
+//   * A goes from the generators' registers straight into TMEM (tcgen05.st) and the MMAs take it
+//     from there (A-from-TMEM form of tcgen05.mma): no A stores, no A operand reads;
+//   * for that a thread must own one FEATURE (TMEM lane) and hold it for consecutive frames (two
+//     per 32-bit column), so the packed frames it reads are K-major -- 8 x 8 cores with the frames
+//     contiguous (pack_x_kernel's hi_k / lo_k parts); one 16-byte load is 8 frames of the
+//     thread's feature, and B, the same tile, is a K-major operand;
+//   * the shared memory A no longer needs holds a third B stage.
+// Rows 128..143 of S (D = 144) are the transposes of columns the big MMA already produces, except
+// the 16 x 17 corner, which two mma.sync warps compute as before from a small shared-memory copy
+// of those 16 rows of A.  Work distribution, tile skipping, per-tile weight scale, flush per tile
+// and the partial layout are those of the first generation (the reduce / post kernels are shared).
+// ------------------------------------------------------------------------------------------
+constexpr int M2_NB = 3;           // B stages
+struct Mstep2Smem {
+    uint32_t b_stage, off_b, off_ac, off_rs, off_flags, off_bars, off_tmem, off_corner, total;
+};
+__host__ __device__ inline Mstep2Smem mstep2_smem(int DP) {
+    Mstep2Smem g;
+    const int DPB = dpb_of(DP);
+    g.b_stage = 2u * MT * DPB * 2;                 // hi + lo
+    uint32_t o = 0;
+    g.off_b = o;      o += M2_NB * g.b_stage;
+    g.off_ac = o;     o += 2u * 2 * 2048;          // corner rows of A: [A stage][hi, lo][2 KB]
+    g.off_rs = o;     o += M2_NB * MT * 4;
+    o = (o + 15u) & ~15u;
+    g.off_flags = o;  o += 96;   // item ring[4] | pinv[3] @16 | ginv[2] @32 | gflag[2] @48 | pent[3] @64
+    g.off_bars = o;   o += 24 * 8;
+    g.off_tmem = o;   o += 16;
+    g.off_corner = o; o += 2 * 12 * 32 * 4;
+    g.total = o;
+    return g;
+}
+enum { M2_B_FULL = 0, M2_B_EMPTY = 3, M2_A_FULL = 6, M2_A_EMPTY = 8, M2_TM_FULL = 10,
+       M2_TM_EMPTY = 12, M2_IT_FULL = 14, M2_IT_EMPTY = 18 };
+
+__global__ void __launch_bounds__(640, 1)
+mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
+                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
+                  const float* __restrict__ mu32, float* __restrict__ partial,
+                  double* __restrict__ npartial, int* __restrict__ item_counter,
+                  const unsigned char* __restrict__ tflags, int n_mt_pad) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const MstepGeom G = mstep_geom(DP);
+    const Mstep2Smem L = mstep2_smem(DP);
+    unsigned char* b_base = smem + L.off_b;
+    unsigned char* ac_base = smem + L.off_ac;
+    float* r_s = reinterpret_cast<float*>(smem + L.off_rs);
+    volatile int* item_ring = reinterpret_cast<volatile int*>(smem + L.off_flags);          // [4]
+    volatile float* pinv = reinterpret_cast<volatile float*>(smem + L.off_flags + 16);     // [3 B stages]
+    volatile float* ginv = reinterpret_cast<volatile float*>(smem + L.off_flags + 32);     // [2 TMEM stages]
+    volatile int* gflag = reinterpret_cast<volatile int*>(smem + L.off_flags + 48);        // [2 TMEM stages]
+    volatile int* pent = reinterpret_cast<volatile int*>(smem + L.off_flags + 64);         // [3 B stages]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int n_items = K * n_chunks;
+    const int DPB = G.DPB;
+    const uint32_t part_b = (uint32_t)MT * DPB * 2;      // bytes of one part of a B stage
+    const uint32_t acc_cols = (uint32_t)G.N1;            // accumulator stage s at column s * N1
+    const uint32_t a_col0 = 2u * acc_cols;               // A stage a: hi at a_col0 + 64 a, lo + 32
+    const bool corner = G.corner;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < M2_NB; ++i) {
+            mbar_init(bars + M2_B_FULL + i, 1);
+            mbar_init(bars + M2_B_EMPTY + i, 9 + (corner ? 2 : 0));
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + M2_A_FULL + i, 8);
+            mbar_init(bars + M2_A_EMPTY + i, 1 + (corner ? 2 : 0));
+            mbar_init(bars + M2_TM_FULL + i, 1);
+            mbar_init(bars + M2_TM_EMPTY + i, 8);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bars + M2_IT_FULL + i, 1);
+            mbar_init(bars + M2_IT_EMPTY + i, 17 + (corner ? 2 : 0));
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto next_item = [&](uint32_t idx) -> int {          // consumer side, whole warp
+        const uint32_t slot = idx & 3u;
+        mbar_wait(bars + M2_IT_FULL + slot, (idx >> 2) & 1u);
+        const int it = item_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + M2_IT_EMPTY + slot);
+        return it;
+    };
+    auto draw_item = [&](uint32_t idx) -> int {          // producer warp
+        int it = 0;
+        if (lane == 0) {
+            const uint32_t slot = idx & 3u;
+            mbar_wait(bars + M2_IT_EMPTY + slot, ((idx >> 2) & 1u) ^ 1u);
+            it = atomicAdd(item_counter, 1);
+            if (it >= n_items) it = -1;
+            item_ring[slot] = it;
+            mbar_arrive(bars + M2_IT_FULL + slot);
+        }
+        return __shfl_sync(0xffffffffu, it, 0);
+    };
+    auto item_tiles = [&](int item, int& k, int& t0, int& t1) {
+        const int chunk = item / K;
+        k = item - chunk * K;
+        t0 = chunk * tiles_per_chunk;
+        t1 = min(n_mtiles, t0 + tiles_per_chunk);
+    };
+
+    if (warp < 4) {
+      reg_dec<40>();
+      if (warp == 0) {
+        // ---------------- producer: K-major packed frames (hi, lo) + the tile's weights -------
+        uint32_t g = 0;
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = draw_item(it_idx);
+            if (item < 0) break;
+            int k, t0, t1;
+            item_tiles(item, k, t0, t1);
+            auto load2 = [&](int t, double& r0, double& r1) {
+                const long long n = (long long)t * MT + 2 * lane;
+                const double* rp = respT + (size_t)k * Npad + n;
+                r0 = (t >= 0 && n < N) ? rp[0] : 0.0;
+                r1 = (t >= 0 && n + 1 < N) ? rp[1] : 0.0;
+            };
+            const unsigned char* fk = tflags + (size_t)k * n_mt_pad;
+            double nacc = 0.0;
+            for (int tb = t0; tb < t1; tb += 32) {
+                const int tq = tb + lane;
+                unsigned mask = __ballot_sync(0xffffffffu, tq < t1 && fk[tq] != 0);
+                double a0 = 0.0, a1 = 0.0;
+                if (mask) load2(tb + __ffs(mask) - 1, a0, a1);
+                while (mask) {
+                    const int t = tb + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float f0 = (float)a0, f1 = (float)a1;
+                    nacc += a0 + a1;
+                    load2(mask ? tb + __ffs(mask) - 1 : -1, a0, a1);   // next non-empty tile
+                    float fm = fmaxf(f0, f1);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, o));
+                    int ex;
+                    (void)frexpf(fm, &ex);               // 2^-ex fm in [0.5, 1)
+                    const float up = ldexpf(1.f, -ex);
+                    const uint32_t s = g % M2_NB, u = g / M2_NB;
+                    mbar_wait(bars + M2_B_EMPTY + s, (u & 1u) ^ 1u);
+                    *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) =
+                        make_float2(f0 * up, f1 * up);
+                    __syncwarp();
+                    if (lane == 0) {
+                        pinv[s] = ldexpf(1.f, ex);
+                        pent[s] = t;
+                        mbar_expect_tx(bars + M2_B_FULL + s, 2 * part_b);
+                        const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                             3 * tile_elems(DP) + (size_t)(t & 1) * MT * DPB;
+                        unsigned char* dst = b_base + s * L.b_stage;
+                        bulk_g2s(dst, tile, part_b, bars + M2_B_FULL + s);
+                        bulk_g2s(dst + part_b, tile + tile_elems(DP), part_b,
+                                 bars + M2_B_FULL + s);
+                    }
+                    __syncwarp();
+                    ++g;
+                }
+            }
+            {   // END of the item
+                const uint32_t s = g % M2_NB, u = g / M2_NB;
+                mbar_wait(bars + M2_B_EMPTY + s, (u & 1u) ^ 1u);
+                if (lane == 0) {
+                    pent[s] = -1;
+                    mbar_arrive(bars + M2_B_FULL + s);
+                }
+                __syncwarp();
+                ++g;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
+            if (lane == 0) {
+                npartial[(size_t)item * 2] = nacc;
+                npartial[(size_t)item * 2 + 1] = 0.0;
+            }
+        }
+      } else if (warp == 1) {
+        // ---------------- MMA issuer: A from TMEM, B K-major from shared memory -----------------
+        const uint32_t idesc = make_idesc(128, G.N1);
+        // K-major, no swizzle: SBO = stride between 8-feature groups, LBO = between 8-frame groups
+        uint64_t d_b[M2_NB][2];
+#pragma unroll
+        for (int st = 0; st < M2_NB; ++st)
+#pragma unroll
+            for (int pt = 0; pt < 2; ++pt)
+                d_b[st][pt] = make_desc(smem_u32(b_base + st * L.b_stage + pt * part_b), 128, 1024);
+        const uint64_t step_b = 256 >> 4;           // one k-step = 16 frames = two 128-byte cores
+        uint32_t g = 0, f = 0;
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
+            for (;;) {
+                const uint32_t sb = g % M2_NB, ub = g / M2_NB;
+                const uint32_t sa = g & 1u, ua = g >> 1;
+                const uint32_t ts = f & 1u, tu = f >> 1;
+                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                const int tt = pent[sb];
+                const float tile_inv = pinv[sb];
+                mbar_wait(bars + M2_TM_EMPTY + ts, (tu & 1u) ^ 1u);
+                mbar_wait(bars + M2_A_FULL + sa, ua & 1u);
+                tc_fence_after();
+                ++g;
+                if (tt < 0) {
+                    // END: release the stages and close the item with an empty flush group
+                    if (lane == 0) {
+                        mbar_arrive(bars + M2_A_EMPTY + sa);
+                        mbar_arrive(bars + M2_B_EMPTY + sb);
+                        gflag[ts] = 2;
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    umma_commit(bars + M2_TM_FULL + ts);
+                    ++f;
+                    break;
+                }
+                const uint32_t acc = tmem_base + ts * acc_cols;
+                const uint32_t a_hi = tmem_base + a_col0 + sa * 64u, a_lo = a_hi + 32u;
+                const uint64_t b_hi = d_b[sb][0], b_lo = d_b[sb][1];
+                // cross passes first (2^-11 of the main term), so only the four A_hi B_hi MMAs
+                // truncate the accumulator at full magnitude
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ta = (pass == 1) ? a_lo : a_hi;
+                    uint64_t db = (pass == 0) ? b_lo : b_hi;
+#pragma unroll
+                    for (int ks = 0; ks < MT / 16; ++ks) {
+                        umma_f16_ts(acc, ta + 8u * ks, db, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+                        db += step_b;
+                    }
+                }
+                umma_commit(bars + M2_A_EMPTY + sa);
+                umma_commit(bars + M2_B_EMPTY + sb);
+                if (lane == 0) {
+                    gflag[ts] = 1;
+                    ginv[ts] = tile_inv;
+                }
+                __threadfence_block();
+                __syncwarp();
+                umma_commit(bars + M2_TM_FULL + ts);
+                ++f;
+            }
+        }
+      } else if (corner) {
+        // ---------------- corner warps 2, 3: features 128..143 x columns 128..151 -----------
+        // mma.sync m16n8k16 from the K-major tiles: A rows = the 16 corner features (their own
+        // small shared-memory copy, written by the generators), B rows = features 128..151 of the
+        // packed frames; every 8 x 8 core is an ldmatrix tile as it lies.
+        const int cw = warp - 2;
+        float* cacc = reinterpret_cast<float*>(smem + L.off_corner) + cw * 12 * 32;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
+        const uint32_t mi = (uint32_t)lane >> 3, rr = (uint32_t)lane & 7u;
+        // A fragment matrices: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15),
+        // (rows 8-15, k 8-15): feature group mi & 1, frame group 2 ks + (mi >> 1)
+        const uint32_t la = (((mi & 1u) * 8 + (mi >> 1)) * 8 + rr) * 16;
+        // B fragment matrices for column blocks nb, nb + 1: (nb, k 0-7), (nb, k 8-15),
+        // (nb + 1, k 0-7), (nb + 1, k 8-15): feature group 16 + nb + (mi >> 1), frame group + (mi & 1)
+        const uint32_t lb = (((16 + (mi >> 1)) * 8 + (mi & 1u)) * 8 + rr) * 16;
+        const uint32_t lb2 = ((18 * 8 + (mi & 1u)) * 8 + rr) * 16;      // column block 2 (x2)
+        const uint32_t a_s0 = smem_u32(ac_base), b_s0 = smem_u32(b_base);
+        float acc[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+        uint32_t g = 0;
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
+            for (;;) {
+                const uint32_t sb = g % M2_NB, ub = g / M2_NB;
+                const uint32_t sa = g & 1u, ua = g >> 1;
+                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                const int tt = pent[sb];
+                const float tile_inv = pinv[sb];
+                mbar_wait(bars + M2_A_FULL + sa, ua & 1u);
+                ++g;
+                if (tt >= 0) {
+                    const uint32_t ab = a_s0 + sa * 4096u + la, bb = b_s0 + sb * L.b_stage;
+#pragma unroll
+                    for (int kq = 0; kq < MT / 32; ++kq) {
+                        const uint32_t ks = (uint32_t)(cw * (MT / 32) + kq);
+                        uint32_t ah[4], al[4], bh[6], bl[4];
+                        ldsm4(ab + ks * 256u, ah);
+                        ldsm4(ab + 2048u + ks * 256u, al);
+                        ldsm4(bb + lb + ks * 256u, bh);
+                        ldsm2(bb + lb2 + ks * 256u, bh + 4);
+                        ldsm4(bb + part_b + lb + ks * 256u, bl);
+#pragma unroll
+                        for (int nb = 0; nb < 3; ++nb) {
+                            mma16816(acc + 4 * nb, al, bh + 2 * nb);
+                            // (the ones column of block 2 has no lo part)
+                            if (nb < 2) mma16816(acc + 4 * nb, ah, bl + 2 * nb);
+                            mma16816(acc + 4 * nb, ah, bh + 2 * nb);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bars + M2_A_EMPTY + sa);
+                    mbar_arrive(bars + M2_B_EMPTY + sb);
+                }
+                if (tt >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        cacc[i * 32 + lane] = fmaf(acc[i], tile_inv, cacc[i * 32 + lane]);
+                        acc[i] = 0.f;
+                    }
+                }
+                if (tt < 0) break;
+            }
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+            if (cw == 1) {
+                asm volatile("bar.sync 3, 64;" ::: "memory");    // warp 2 has read our sums
+#pragma unroll
+                for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
+                continue;
+            }
+            float* out = partial + (size_t)item * G.partial_len + (size_t)128 * G.N1;
+            const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (nb < 3) {
+                        v.x = cacc[(4 * nb + 2 * h) * 32 + lane] +
+                              cacc[(12 + 4 * nb + 2 * h) * 32 + lane];
+                        v.y = cacc[(4 * nb + 2 * h + 1) * 32 + lane] +
+                              cacc[(12 + 4 * nb + 2 * h + 1) * 32 + lane];
+                        cacc[(4 * nb + 2 * h) * 32 + lane] = 0.f;
+                        cacc[(4 * nb + 2 * h + 1) * 32 + lane] = 0.f;
+                    }
+                    *reinterpret_cast<float2*>(out + (size_t)(112 + gq + 8 * h) * G.N2 + nb * 8 +
+                                               2 * tq) = v;
+                }
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+        }
+      }
+    } else if (warp < 12) {
+        reg_dec<88>();
+        // ---------------- generators (warps 4..11): A = r (x' - mu') -> TMEM ------------------
+        // Thread = feature row i = 32 q + lane of its TMEM lane quarter q = warp % 4; warps 4..7
+        // take frame groups 0..3 (k-steps 0, 1), warps 8..11 frame groups 4..7 (k-steps 2, 3).
+        // Threads of warps 4..7 also convert one (corner feature, frame group) unit each.
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int i = 32 * q + lane;
+        const bool valid = i < DP;
+        const int gt = threadIdx.x - 128;            // 0..255
+        const int cf = gt & 15, cfg = (gt >> 4) & 7; // corner unit: feature 128 + cf, frame group cfg
+        const bool on_c = corner && gt < 128;
+        const uint32_t row_off = ((uint32_t)(i >> 3) * 8u) * 128u + (uint32_t)(i & 7) * 16u;
+        const uint32_t c_src = ((uint32_t)(16 + (cf >> 3)) * 8u + (uint32_t)cfg) * 128u + (uint32_t)(cf & 7) * 16u;
+        const uint32_t c_dst = ((uint32_t)(cf >> 3) * 8u + (uint32_t)cfg) * 128u + (uint32_t)(cf & 7) * 16u;
+        const uint32_t t_lane = tmem_base + (((uint32_t)q * 32u) << 16) + a_col0;
+        uint32_t g = 0;
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
+            int k, t0, t1;
+            item_tiles(item, k, t0, t1);
+            const float mu_i = valid ? mu32[(size_t)k * G.DA + i] : 0.f;
+            const float mu_c = on_c ? mu32[(size_t)k * G.DA + 128 + cf] : 0.f;
+            for (;;) {
+                const uint32_t sb = g % M2_NB, ub = g / M2_NB;
+                const uint32_t sa = g & 1u, ua = g >> 1;
+                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                const int tt = pent[sb];
+                mbar_wait(bars + M2_A_EMPTY + sa, (ua & 1u) ^ 1u);
+                tc_fence_after();
+                const unsigned char* bh = b_base + sb * L.b_stage;
+                const float* rt = r_s + sb * MT;
+                // 8 frames of one feature: z = r (x' - mu), split into fp16 hi / lo pairs
+                auto convert8 = [&](uint32_t off, int fg, float mu, bool live, uint32_t* zh,
+                                    uint32_t* zl) {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + off);
+                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + off);
+                    const float4 ra = *reinterpret_cast<const float4*>(rt + fg * 8);
+                    const float4 rb = *reinterpret_cast<const float4*>(rt + fg * 8 + 4);
+                    const float rr8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    const __half2* hp = reinterpret_cast<const __half2*>(&hv);
+                    const __half2* lp = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
+                        float z0 = rr8[2 * e] * ((xh.x + xl.x) - mu);
+                        float z1 = rr8[2 * e + 1] * ((xh.y + xl.y) - mu);
+                        if (!live) { z0 = 0.f; z1 = 0.f; }
+                        const __half2 zh2 = __floats2half2_rn(z0, z1);
+                        const float2 zf = __half22float2(zh2);
+                        const __half2 zl2 = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
+                        zh[e] = *reinterpret_cast<const uint32_t*>(&zh2);
+                        zl[e] = *reinterpret_cast<const uint32_t*>(&zl2);
+                    }
+                };
+                if (tt >= 0) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int ks = 2 * h + kk;
+                        uint32_t zh[8], zl[8];
+                        convert8(row_off + (uint32_t)(2 * ks) * 128u, 2 * ks, mu_i, valid, zh, zl);
+                        convert8(row_off + (uint32_t)(2 * ks + 1) * 128u, 2 * ks + 1, mu_i, valid,
+                                 zh + 4, zl + 4);
+                        tmem_st8(t_lane + sa * 64u + 8u * ks, zh);
+                        tmem_st8(t_lane + sa * 64u + 32u + 8u * ks, zl);
+                    }
+                    if (on_c) {
+                        uint32_t zh[4], zl[4];
+                        convert8(c_src, cfg, mu_c, true, zh, zl);
+                        unsigned char* dst = ac_base + sa * 4096u + c_dst;
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+                        *reinterpret_cast<uint4*>(dst + 2048u) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+                    }
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bars + M2_A_FULL + sa);
+                    mbar_arrive(bars + M2_B_EMPTY + sb);
+                }
+                ++g;
+                if (tt < 0) break;
+            }
+        }
+    } else {
+        reg_inc<128>();
+        // ---------------- epilogue (warps 12..19): TMEM -> fp32 registers -> partials -----------
+        const uint32_t quarter = (uint32_t)(warp & 3);
+        const int half = (warp - 12) >> 2;
+        const int row = (int)quarter * 32 + lane;
+        const int n16_1 = G.N1 / 16;
+        const int c1_begin = half == 0 ? 0 : (n16_1 + 1) / 2;
+        const int c1_end = half == 0 ? (n16_1 + 1) / 2 : n16_1;
+        float acc[5][16];
+        uint32_t f = 0;
+        for (uint32_t it_idx = 0;; ++it_idx) {
+            const int item = next_item(it_idx);
+            if (item < 0) break;
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
+            for (;;) {
+                const uint32_t ts = f & 1u, tu = f >> 1;
+                mbar_wait(bars + M2_TM_FULL + ts, tu & 1u);
+                tc_fence_after();
+                const int fl = gflag[ts];         // bit 0: the group holds data, bit 1: last group
+                const bool empty = (fl & 1) == 0;
+                const float inv = empty ? 0.f : ginv[ts];
+                const float2 inv2 = make_float2(inv, inv);
+                const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    if (!empty && c1_begin + c < c1_end) {
+                        uint32_t v[16];
+                        tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float2 t = __ffma2_rn(
+                                make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2,
+                                make_float2(acc[c][j], acc[c][j + 1]));
+                            acc[c][j] = t.x;
+                            acc[c][j + 1] = t.y;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + M2_TM_EMPTY + ts);
+                ++f;
+                if (fl & 2) break;
+            }
+            float* out = partial + (size_t)item * G.partial_len;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                if (c1_begin + c < c1_end) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = acc[c][j];
+                }
+            }
+            if (corner && row < 112) {
+                // second block of the partial: only its rows 112..127 carry data (corner warps);
+                // the rest is zero so that the shared reduce kernel sums defined values
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    out[(size_t)128 * G.N1 + (size_t)row * G.N2 + half * 16 + j] = 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // Fixed-order sum of the per-chunk partials: raw[k][e], e < partial_len, then n_k at [partial_len].
 __global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
                                         const float* __restrict__ partial,
@@ -1795,12 +2337,24 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
             N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags);
         KW_CUDA_CHECK(cudaGetLastError());
     }
-    static int swap_strides = -1;
+    static int swap_strides = -1, generation = 2;
     const int m_flush = 1;     // one tile per TMEM flush: the flush carries the tile's weight scale
     if (swap_strides < 0) {
         const char* e = getenv("KW_TC_MSWAP");
         swap_strides = e != nullptr ? atoi(e) : 0;
+        const char* g = getenv("KW_TC_MSTEP");     // 1 = first-generation kernel (A in smem)
+        if (g != nullptr && atoi(g) == 1) generation = 1;
     }
+    if (generation == 2) {
+        const tc::Mstep2Smem L2 = tc::mstep2_smem(DP);
+        KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc2_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)L2.total));
+        tc::mstats_tc2_kernel<<<grid, 640, L2.total, st>>>(
+            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
+            w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad);
+        KW_CUDA_CHECK(cudaGetLastError());
+    } else {
     static unsigned long long* prof_dev = nullptr;
     static int prof_on = -1;
     if (prof_on < 0) {
@@ -1823,6 +2377,7 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
                 h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
     }
     KW_CUDA_CHECK(cudaGetLastError());
+    }
     tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
         K, G.partial_len, w.m_chunks, w.mpartial, w.npartial, w.mraw);
     KW_CUDA_CHECK(cudaGetLastError());
