@@ -1598,7 +1598,9 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                   int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
                   const float* __restrict__ mu32, float* __restrict__ partial,
                   double* __restrict__ npartial, int* __restrict__ item_counter,
-                  const unsigned char* __restrict__ tflags, int n_mt_pad) {
+                  const unsigned char* __restrict__ tflags, int n_mt_pad, int dbg) {
+    // dbg (timing experiments only, 0 in production): 1 = no MMAs, 2 = no operand generation,
+    // 4 = no epilogue loads
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     const Mstep2Smem L = mstep2_smem(DP);
@@ -1787,6 +1789,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 const uint64_t b_hi = d_b[sb][0], b_lo = d_b[sb][1];
                 // cross passes first (2^-11 of the main term), so only the four A_hi B_hi MMAs
                 // truncate the accumulator at full magnitude
+                if (!(dbg & 1))
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t ta = (pass == 1) ? a_lo : a_hi;
@@ -1960,7 +1963,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                         zl[e] = *reinterpret_cast<const uint32_t*>(&zl2);
                     }
                 };
-                if (tt >= 0) {
+                if (tt >= 0 && !(dbg & 2)) {
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
                         const int ks = 2 * h + kk;
@@ -2020,7 +2023,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    if (!empty && c1_begin + c < c1_end) {
+                    if (!empty && c1_begin + c < c1_end && !(dbg & 4)) {
                         uint32_t v[16];
                         tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
                         tmem_ld_wait();
@@ -2352,7 +2355,7 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
                                            (int)L2.total));
         tc::mstats_tc2_kernel<<<grid, 640, L2.total, st>>>(
             N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad);
+            w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad, swap_strides);
         KW_CUDA_CHECK(cudaGetLastError());
     } else {
     static unsigned long long* prof_dev = nullptr;
