@@ -235,6 +235,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;  // descriptor version for sm_100
     return d;                // base offset 0, layout type 0 = no swizzle
 }
+// K-major tile with the 128-byte swizzle (rows of 128 bytes = 64 fp16 of K, 8-row groups 1024
+// bytes apart, tile base 1024-byte aligned); a k-step of 16 elements advances the start address
+// by 32 bytes inside the swizzle atom.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;                       // LBO: unused with a swizzled K-major layout
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows x 128 bytes
+    d |= (uint64_t)1 << 46;                       // descriptor version for sm_100
+    d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
+    return d;
+}
 // Instruction descriptor: kind::f16, A = B = fp16, D = fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -360,9 +372,10 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
     __half* hi = xt + (size_t)tile * X_PARTS * tile_elems(DP);
     __half* lo_s = hi + tile_elems(DP);
     __half* lo_u = lo_s + tile_elems(DP);
-    // M-step operands, K-major (8 x 8 cores with the FRAMES contiguous) per 64-frame tile:
-    // element (feature c, frame r) of M-tile r / 64 at  (r/64) 64 DPB + ((c/8) 8 + (r%64)/8) 64
-    // + (c%8) 8 + r%8
+    // M-step operands, K-major with the 128-byte swizzle: per 64-frame tile one 128-byte row per
+    // feature (64 frames), its 16-byte chunks (8 frames) XOR-ed with the row number mod 8:
+    // element (feature c, frame r) of M-tile r / 64 at  (r/64) 64 DPB + 64 c
+    // + 8 (((r%64)/8) ^ (c%8)) + r%8
     __half* hi_k = lo_u + tile_elems(DP);
     __half* lo_k = hi_k + tile_elems(DP);
     const int kg_n = DPB / 8;
@@ -378,8 +391,8 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
         hi[o] = h;
         lo_s[o] = __double2half(res * LO_SCALE);
         lo_u[o] = __double2half(res);
-        const size_t ok = (size_t)(r >> 6) * 64 * DPB + ((size_t)(c >> 3) * 8 + ((r & 63) >> 3)) * 64 +
-                          (c & 7) * 8 + (r & 7);
+        const size_t ok = (size_t)(r >> 6) * 64 * DPB + (size_t)c * 64 +
+                          (size_t)((((r & 63) >> 3) ^ (c & 7)) * 8) + (r & 7);
         hi_k[ok] = h;
         lo_k[ok] = __double2half(res);
     }
@@ -1561,9 +1574,10 @@ mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk,
 //   * A goes from the generators' registers straight into TMEM (tcgen05.st) and the MMAs take it
 //     from there (A-from-TMEM form of tcgen05.mma): no A stores, no A operand reads;
 //   * for that a thread must own one FEATURE (TMEM lane) and hold it for consecutive frames (two
-//     per 32-bit column), so the packed frames it reads are K-major -- 8 x 8 cores with the frames
-//     contiguous (pack_x_kernel's hi_k / lo_k parts); one 16-byte load is 8 frames of the
-//     thread's feature, and B, the same tile, is a K-major operand;
+//     per 32-bit column), so the packed frames it reads are K-major -- one 128-byte row of 64
+//     frames per feature, 128-byte swizzled (pack_x_kernel's hi_k / lo_k parts); one 16-byte load
+//     is 8 frames of the thread's feature, and B, the same tile, is a swizzled K-major operand
+//     (the no-swizzle layouts of the first generation cost the MMAs twice their floor);
 //   * the shared memory A no longer needs holds a third B stage.
 // Rows 128..143 of S (D = 144) are the transposes of columns the big MMA already produces, except
 // the 16 x 17 corner, which two mma.sync warps compute as before from a small shared-memory copy
@@ -1748,14 +1762,14 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
       } else if (warp == 1) {
         // ---------------- MMA issuer: A from TMEM, B K-major from shared memory -----------------
         const uint32_t idesc = make_idesc(128, G.N1);
-        // K-major, no swizzle: SBO = stride between 8-feature groups, LBO = between 8-frame groups
+        // K-major rows of 128 bytes with the 128-byte swizzle
         uint64_t d_b[M2_NB][2];
 #pragma unroll
         for (int st = 0; st < M2_NB; ++st)
 #pragma unroll
             for (int pt = 0; pt < 2; ++pt)
-                d_b[st][pt] = make_desc(smem_u32(b_base + st * L.b_stage + pt * part_b), 128, 1024);
-        const uint64_t step_b = 256 >> 4;           // one k-step = 16 frames = two 128-byte cores
+                d_b[st][pt] = make_desc_sw128(smem_u32(b_base + st * L.b_stage + pt * part_b));
+        const uint64_t step_b = 32 >> 4;            // one k-step = 16 frames = 32 bytes of a row
         uint32_t g = 0, f = 0;
         for (uint32_t it_idx = 0;; ++it_idx) {
             const int item = next_item(it_idx);
@@ -1794,6 +1808,9 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t ta = (pass == 1) ? a_lo : a_hi;
                     uint64_t db = (pass == 0) ? b_lo : b_hi;
+                    if ((pass == 0 && (dbg & 32)) || (pass == 1 && (dbg & 64)) ||
+                        (pass == 2 && (dbg & 128)))
+                        continue;
 #pragma unroll
                     for (int ks = 0; ks < MT / 16; ++ks) {
                         umma_f16_ts(acc, ta + 8u * ks, db, idesc, (pass > 0 || ks > 0) ? 1u : 0u);
@@ -1827,8 +1844,9 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
         const uint32_t la = (((mi & 1u) * 8 + (mi >> 1)) * 8 + rr) * 16;
         // B fragment matrices for column blocks nb, nb + 1: (nb, k 0-7), (nb, k 8-15),
         // (nb + 1, k 0-7), (nb + 1, k 8-15): feature group 16 + nb + (mi >> 1), frame group + (mi & 1)
-        const uint32_t lb = (((16 + (mi >> 1)) * 8 + (mi & 1u)) * 8 + rr) * 16;
-        const uint32_t lb2 = ((18 * 8 + (mi & 1u)) * 8 + rr) * 16;      // column block 2 (x2)
+        // (swizzled rows: feature j = 8 group + rr at j * 128, chunk (frame group ^ rr))
+        const uint32_t lb = ((16 + (mi >> 1)) * 8 + rr) * 128;
+        const uint32_t lb2 = (18 * 8 + rr) * 128;                       // column block 2 (x2)
         const uint32_t a_s0 = smem_u32(ac_base), b_s0 = smem_u32(b_base);
         float acc[12];
 #pragma unroll
@@ -1851,11 +1869,12 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                     for (int kq = 0; kq < MT / 32; ++kq) {
                         const uint32_t ks = (uint32_t)(cw * (MT / 32) + kq);
                         uint32_t ah[4], al[4], bh[6], bl[4];
+                        const uint32_t ch = (((2u * ks + (mi & 1u)) ^ rr) << 4);   // swizzled chunk
                         ldsm4(ab + ks * 256u, ah);
                         ldsm4(ab + 2048u + ks * 256u, al);
-                        ldsm4(bb + lb + ks * 256u, bh);
-                        ldsm2(bb + lb2 + ks * 256u, bh + 4);
-                        ldsm4(bb + part_b + lb + ks * 256u, bl);
+                        ldsm4(bb + lb + ch, bh);
+                        ldsm2(bb + lb2 + ch, bh + 4);
+                        ldsm4(bb + part_b + lb + ch, bl);
 #pragma unroll
                         for (int nb = 0; nb < 3; ++nb) {
                             mma16816(acc + 4 * nb, al, bh + 2 * nb);
@@ -1919,8 +1938,8 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
         const int gt = threadIdx.x - 128;            // 0..255
         const int cf = gt & 15, cfg = (gt >> 4) & 7; // corner unit: feature 128 + cf, frame group cfg
         const bool on_c = corner && gt < 128;
-        const uint32_t row_off = ((uint32_t)(i >> 3) * 8u) * 128u + (uint32_t)(i & 7) * 16u;
-        const uint32_t c_src = ((uint32_t)(16 + (cf >> 3)) * 8u + (uint32_t)cfg) * 128u + (uint32_t)(cf & 7) * 16u;
+        const uint32_t row_off = (uint32_t)i * 128u, row_x = (uint32_t)(i & 7);
+        const uint32_t c_src = (uint32_t)(128 + cf) * 128u + (((uint32_t)cfg ^ (uint32_t)(cf & 7)) << 4);
         const uint32_t c_dst = ((uint32_t)(cf >> 3) * 8u + (uint32_t)cfg) * 128u + (uint32_t)(cf & 7) * 16u;
         const uint32_t t_lane = tmem_base + (((uint32_t)q * 32u) << 16) + a_col0;
         uint32_t g = 0;
@@ -1961,6 +1980,12 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                         const __half2 zl2 = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
                         zh[e] = *reinterpret_cast<const uint32_t*>(&zh2);
                         zl[e] = *reinterpret_cast<const uint32_t*>(&zl2);
+                        if (dbg & 256) zl[e] = 0u;
+                        if (dbg & 512) {          // lo scaled by 2^11: no fp16 subnormals
+                            const __half2 zs = __floats2half2_rn((z0 - zf.x) * 2048.f,
+                                                                 (z1 - zf.y) * 2048.f);
+                            zl[e] = *reinterpret_cast<const uint32_t*>(&zs);
+                        }
                     }
                 };
                 if (tt >= 0 && !(dbg & 2)) {
@@ -1968,11 +1993,16 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                     for (int kk = 0; kk < 2; ++kk) {
                         const int ks = 2 * h + kk;
                         uint32_t zh[8], zl[8];
-                        convert8(row_off + (uint32_t)(2 * ks) * 128u, 2 * ks, mu_i, valid, zh, zl);
-                        convert8(row_off + (uint32_t)(2 * ks + 1) * 128u, 2 * ks + 1, mu_i, valid,
-                                 zh + 4, zl + 4);
-                        tmem_st8(t_lane + sa * 64u + 8u * ks, zh);
-                        tmem_st8(t_lane + sa * 64u + 32u + 8u * ks, zl);
+                        convert8(row_off + ((((uint32_t)(2 * ks)) ^ row_x) << 4), 2 * ks, mu_i, valid,
+                                 zh, zl);
+                        convert8(row_off + ((((uint32_t)(2 * ks + 1)) ^ row_x) << 4), 2 * ks + 1, mu_i,
+                                 valid, zh + 4, zl + 4);
+                        if (!(dbg & 16)) {
+                            tmem_st8(t_lane + sa * 64u + 8u * ks, zh);
+                            tmem_st8(t_lane + sa * 64u + 32u + 8u * ks, zl);
+                        } else if (zh[0] == 0x12345678u && zl[3] == 0x9abcdef0u) {
+                            pent[0] = 0;      // (keeps the conversion alive)
+                        }
                     }
                     if (on_c) {
                         uint32_t zh[4], zl[4];
@@ -1981,7 +2011,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                         *reinterpret_cast<uint4*>(dst) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
                         *reinterpret_cast<uint4*>(dst + 2048u) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
                     }
-                    tmem_st_wait();
+                    if (!(dbg & 8)) tmem_st_wait();
                 }
                 tc_fence_before();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
