@@ -5,7 +5,7 @@ Lloyd passes run on this library's own kernels: the assignment step is ``kw_gmm_
 with identity precisions and equal weights (argmin of the squared distance; tcgen05 contraction
 with fp64 re-check of near-ties when ``precision='tc'``), the centre update is the first-moment
 part of ``kw_gmm_mstep_accumulate`` on one-hot responsibilities, all-reduced across ranks.  Only
-the k-means++ seeding (K sequential D^2-weighted draws) uses stock torch ops.  The result is not
+the k-means++ seeding (K sequential D^2-weighted draws, all on the device) uses stock torch ops.  The result is not
 bit-compatible with any sklearn KMeans version (their seeding consumes the RNG differently
 across versions); parity tests inject ``resp_init`` instead."""
 import numpy as np
@@ -28,12 +28,16 @@ def _seed_centres(x, k, seed, group):
     if rank == 0:
         if n < k:
             raise ValueError(f'need at least {k} frames on rank 0 to seed k-means, got {n}')
-        centres[0] = x[int(rs.randint(n))]
+        # k-means++: every draw (D^2-weighted, by inverting the cumulative sum at a uniform
+        # number drawn on the host beforehand) stays on the device -- no read-back per centre
+        first = int(rs.randint(n))
+        uniform = torch.from_numpy(rs.random_sample(k)).to(x.device)
+        centres[0] = x[first]
         closest = _dist2(x, centres[0:1]).squeeze(1).clamp_min_(0.0)
         for j in range(1, k):
-            probs = (closest / closest.sum()).cpu().numpy()
-            idx = min(int(np.searchsorted(np.cumsum(probs), rs.random_sample())), n - 1)
-            centres[j] = x[idx]
+            cum = torch.cumsum(closest, dim=0)
+            idx = torch.searchsorted(cum, uniform[j] * cum[-1]).clamp_(max=n - 1)
+            centres[j] = x.index_select(0, idx.reshape(1))[0]
             closest = torch.minimum(closest,
                                     _dist2(x, centres[j:j + 1]).squeeze(1).clamp_min_(0.0))
     if multi:
@@ -42,8 +46,11 @@ def _seed_centres(x, k, seed, group):
     return centres
 
 
-def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30, precision=0):
-    """Hard labels (int64 CUDA tensor) of the device-resident frames ``x`` (N, D) float64."""
+def kmeans_labels(x, k, seed=None, group=None, n_lloyd=300, precision=0, tol=1e-4):
+    """Hard labels (int64 CUDA tensor) of the device-resident frames ``x`` (N, D) float64.
+    Lloyd passes stop as sklearn's KMeans does (max_iter = 300, tol = 1e-4): when no label
+    changes, or when the squared centre shift falls below ``tol`` times the mean per-feature
+    variance of the data."""
     import torch
     import torch.distributed as dist
     lib = _lib.lib()
@@ -66,6 +73,14 @@ def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30, precision=0):
                                       stream), 'kw_gmm_pack_frames')
     rows = torch.arange(n, device=x.device)
     prev = None
+    # tolerance on the squared centre shift, relative to the data's mean variance (all ranks)
+    mom = torch.stack((x.sum(dim=0), (x * x).sum(dim=0)))
+    cnt = torch.tensor([float(n)], **f64)
+    if multi:
+        dist.all_reduce(mom, group=group)
+        dist.all_reduce(cnt, group=group)
+    var_mean = (mom[1] / cnt - (mom[0] / cnt) ** 2).mean()
+    shift_tol = tol * var_mean
     for it in range(max(n_lloyd, 0) + 1):
         aux[:, :d] = centres
         _lib.check(lib.kw_gmm_hard_labels(n, x.data_ptr(), k, d, centres.data_ptr(),
@@ -93,7 +108,16 @@ def kmeans_labels(x, k, seed=None, group=None, n_lloyd=30, precision=0):
         blocks = stats[:k * sb].view(k, sb)
         counts = blocks[:, 0]
         nz = counts > 0
-        centres = centres.clone()
-        centres[nz] = centres[nz] + blocks[nz, 1:1 + d] / counts[nz][:, None]
-        centres = centres.contiguous()
+        moved = centres.clone()
+        moved[nz] = moved[nz] + blocks[nz, 1:1 + d] / counts[nz][:, None]
+        shift = ((moved - centres) ** 2).sum()
+        centres = moved.contiguous()
+        if n_lloyd > 0 and bool(shift <= shift_tol):
+            # converged: one more assignment with the final centres, as sklearn does
+            aux[:, :d] = centres
+            _lib.check(lib.kw_gmm_hard_labels(n, x.data_ptr(), k, d, centres.data_ptr(),
+                                              eye.data_ptr(), aux.data_ptr(), labels.data_ptr(),
+                                              precision, ws.data_ptr(), ws_bytes, stream),
+                       'kw_gmm_hard_labels')
+            break
     return labels.long()
