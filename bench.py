@@ -474,7 +474,7 @@ def run_b200(args):
 
     em_tflops = 2 * flops_half / (em_ms / K / 1e3) / 1e12
     tc = args.precision == 'tc'
-    names = ('estep_tc_kernel', 'mstats_tc_kernel') if tc else ('gmm_estep_kernel', 'gmm_mstats_kernel')
+    names = ('estep_tc_kernel', 'mstats_tc2_kernel') if tc else ('gmm_estep_kernel', 'gmm_mstats_kernel')
     dominant_ms, dominant = (estep_ms, names[0]) if estep_ms >= mstep_ms else (mstep_ms, names[1])
     dom_tflops = flops_half / (dominant_ms / 1e3) / 1e12
     peak = peaks['bf16_tflops_sustained']
@@ -519,14 +519,14 @@ def run_b200(args):
             'note': f'B200GMMFeatureConverter._train on a pinned host (N,144) array, '
                     f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model',
         },
-        'gpu_launches': (10 if tc else 6) * K,
+        'gpu_launches': (11 if tc else 6) * K,
         'roofline': {
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': dom_tflops / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel
-            # in the ncu --set full capture of this workload (profiles/ncu_r1d_mstats_tc.txt,
-            # profiles/ncu_r1c_estep_tc.txt); algorithmic: packed X 113 MB + resp 90 MB in
-            'traffic': ({'mstats_tc_kernel': 204.4e6 + 75.6e6, 'estep_tc_kernel': 116.5e6 + 54.3e6}
+            # in the ncu --set full capture of this workload (profiles/ncu_r2_mstats_tc2.txt,
+            # profiles/ncu_r2_estep_tc.txt); algorithmic: packed X 113 MB + resp 90 MB
+            'traffic': ({'mstats_tc2_kernel': 159.3e6 + 68.6e6, 'estep_tc_kernel': 116.5e6 + 55.4e6}
                         .get(dominant) if n_frames == 176323 else None),
             'traffic_unit': 'bytes per launch (ncu, 1 GPU)',
             'peak_source': f"{peaks['source']} bf16_tflops_sustained",
@@ -536,6 +536,13 @@ def run_b200(args):
             'frac_of_peak_over_passes': (dom_tflops / (peak / 3)) if tc else None,
             'estep_ms': estep_ms, 'mstep_accumulate_ms': mstep_ms,
             'em_iteration_tflops': em_tflops,
+            'other_contraction': {
+                'kernel': names[1] if dominant == names[0] else names[0],
+                'achieved': flops_half / (min(estep_ms, mstep_ms) / 1e3) / 1e12,
+                'frac': flops_half / (min(estep_ms, mstep_ms) / 1e3) / 1e12 / peak},
+            'power': 'the M-step statistics kernel runs at the 1 kW board power cap with dense '
+                     'data (tools/time_mstep.py: 984 W, sw_power_cap active); bf16_tflops_sustained '
+                     'is the cuBLAS rate under the same cap',
         },
         'cpu_baseline': cpu['em'] if cpu else None,
         'clocks': clock_info,

@@ -279,3 +279,18 @@ def test_packed_host_api_equals_the_list_api(cuda):
         assert len(got) == len(expected)
         for (c1, p1), (c2, p2) in zip(got, expected):
             assert c1 == c2 and np.array_equal(p1, p2)
+
+
+def test_configs3_pair_4096_unconstrained(cuda):
+    """configs[3]: one 4096 x 4096 pair of 26-dim features, unconstrained window (fastdtw.dtw):
+    path and cost bit-exact against the C oracle, and the path's decision margin."""
+    a, b = synth.make_pair(0, length=4096)
+    x, y = make_feature(a, a.fs), make_feature(b, b.fs)
+    assert x.shape == (4096, 26) and y.shape == (4096, 26)
+    (res,), margins = kfd.fastdtw_batch([(x, y)], radius=-1, dist=2, with_margin=True)
+    ecost, epath, em = dtw_c.fastdtw(x, y, radius=-1, dist=2, return_margin=True)
+    assert np.array_equal(res[1], epath) and res[0] == ecost
+    assert np.allclose(margins[0], em, rtol=0, atol=64 * np.spacing(ecost))
+    assert margins[0][0] > 1e4 * np.spacing(ecost)
+    cy = kfd.fastdtw_batch([(x, y)], radius=-1, dist=2, tie_mode='cython')[0]
+    assert np.array_equal(cy[1], epath)
