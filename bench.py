@@ -519,7 +519,7 @@ def run_b200(args):
             'note': f'B200GMMFeatureConverter._train on a pinned host (N,144) array, '
                     f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model',
         },
-        'gpu_launches': (11 if tc else 6) * K,
+        'gpu_launches': (10 if tc else 6) * K,
         'roofline': {
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': dom_tflops / peak,
