@@ -397,30 +397,6 @@ def run_b200(args):
     del gm, xj_dev
     torch.cuda.empty_cache()
 
-    # ---------------- configs[3]: long unconstrained DTW, 256 pairs of 4096 x 4096 ----------
-    long_stage = None
-    if args.long_pairs > 0:
-        lx, ly = [], []
-        for i in range(8):
-            a, b = synth.make_pair(i, length=LONG_FRAMES)
-            from kwiiyatta_b200.alignment import make_feature as _mf
-            lx.append(_mf(a, a.fs))
-            ly.append(_mf(b, b.fs))
-        n_long = args.long_pairs
-        ltx = np.full(n_long, LONG_FRAMES, dtype=np.int32)
-        lrng = np.random.default_rng(77 + rank)
-        lx_dev = torch.from_numpy(np.concatenate(
-            [lx[i % 8] + lrng.normal(0, 0.01, lx[0].shape) for i in range(n_long)])).to(dev)
-        ly_dev = torch.from_numpy(np.concatenate(
-            [ly[i % 8] + lrng.normal(0, 0.01, ly[0].shape) for i in range(n_long)])).to(dev)
-        long_ms = timed_loop(lambda: kfd.fastdtw_batch_device(lx_dev, ly_dev, ltx, ltx, -1, 2),
-                             flush=True)
-        long_cells = sum_over_ranks(float(n_long) * LONG_FRAMES * LONG_FRAMES)
-        long_stage = {'ms': long_ms / K, 'cells': long_cells,
-                      'value': long_cells * K / (long_ms / 1e3), 'pairs_per_gpu': n_long}
-        del lx_dev, ly_dev
-        torch.cuda.empty_cache()
-
     # ---------------- stage 3: conversion (configs[4]) -------------------------------------
     n_utts = args.utts
     w, m, c = synth.make_joint_gmm(N_MIX_CONVERT, seed=0)
@@ -459,6 +435,33 @@ def run_b200(args):
     torch.cuda.synchronize()
     conv_e2e_lists = n_utts * UTT_FRAMES / (time.perf_counter() - t0)
     del src_pin, out_pin
+
+    del src_dev, paramgen
+    torch.cuda.empty_cache()
+
+    # ---------------- configs[3]: long unconstrained DTW, 256 pairs of 4096 x 4096 ----------
+    long_stage = None
+    if args.long_pairs > 0:
+        lx, ly = [], []
+        for i in range(8):
+            a, b = synth.make_pair(i, length=LONG_FRAMES)
+            from kwiiyatta_b200.alignment import make_feature as _mf
+            lx.append(_mf(a, a.fs))
+            ly.append(_mf(b, b.fs))
+        n_long = args.long_pairs
+        ltx = np.full(n_long, LONG_FRAMES, dtype=np.int32)
+        lrng = np.random.default_rng(77 + rank)
+        lx_dev = torch.from_numpy(np.concatenate(
+            [lx[i % 8] + lrng.normal(0, 0.01, lx[0].shape) for i in range(n_long)])).to(dev)
+        ly_dev = torch.from_numpy(np.concatenate(
+            [ly[i % 8] + lrng.normal(0, 0.01, ly[0].shape) for i in range(n_long)])).to(dev)
+        long_ms = timed_loop(lambda: kfd.fastdtw_batch_device(lx_dev, ly_dev, ltx, ltx, -1, 2),
+                             flush=True)
+        long_cells = sum_over_ranks(float(n_long) * LONG_FRAMES * LONG_FRAMES)
+        long_stage = {'ms': long_ms / K, 'cells': long_cells,
+                      'value': long_cells * K / (long_ms / 1e3), 'pairs_per_gpu': n_long}
+        del lx_dev, ly_dev
+        torch.cuda.empty_cache()
 
     clock_info = clocks.stop() if rank == 0 else None
 

@@ -1,10 +1,10 @@
 """K-means initial labels for the EM (sklearn ``init_params='kmeans'``,
 sklearn/mixture/_base.py:119-128) -- SURVEY.md section 8f rank 1.
 
-Lloyd passes run on this library's own kernels: the assignment step is ``kw_gmm_hard_labels``
-with identity precisions and equal weights (argmin of the squared distance; tcgen05 contraction
-with fp64 re-check of near-ties when ``precision='tc'``), the centre update is the first-moment
-part of ``kw_gmm_mstep_accumulate`` on one-hot responsibilities, all-reduced across ranks.  Only
+The assignment step of every Lloyd pass is this library's ``kw_gmm_hard_labels`` with identity
+precisions and equal weights (argmin of the squared distance; tcgen05 contraction with fp64
+re-check of near-ties when ``precision='tc'``); the centre update is one (K x N)(N x D) product of
+the one-hot responsibilities with the frames, all-reduced across ranks.  Only
 the k-means++ seeding (K sequential D^2-weighted draws, all on the device) uses stock torch ops.  The result is not
 bit-compatible with any sklearn KMeans version (their seeding consumes the RNG differently
 across versions); parity tests inject ``resp_init`` instead."""
@@ -66,8 +66,6 @@ def kmeans_labels(x, k, seed=None, group=None, n_lloyd=300, precision=0, tol=1e-
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
     npad = lib.kw_gmm_resp_len(n, k) // k
     resp = torch.zeros((k, npad), **f64)
-    stats = torch.zeros(lib.kw_gmm_stats_len(k, d), **f64)
-    sb = 1 + d + d * d
     stream = _lib.stream_ptr(torch)
     _lib.check(lib.kw_gmm_pack_frames(n, x.data_ptr(), k, d, precision, ws.data_ptr(), ws_bytes,
                                       stream), 'kw_gmm_pack_frames')
@@ -97,19 +95,19 @@ def kmeans_labels(x, k, seed=None, group=None, n_lloyd=300, precision=0, tol=1e-
             if changed.item() == 0:
                 break
         prev = lab
+        # centre update = first moments of the one-hot responsibilities: a (K x N)(N x D) product
+        # (the full M-step statistics would also form K D^2 second moments nobody reads)
         resp.zero_()
         resp[lab, rows] = 1.0
-        _lib.check(lib.kw_gmm_mstep_accumulate(n, x.data_ptr(), k, d, resp.data_ptr(),
-                                               centres.data_ptr(), stats.data_ptr(), precision,
-                                               ws.data_ptr(), ws_bytes, stream),
-                   'kw_gmm_mstep_accumulate')
+        moments = torch.empty((k, d + 1), **f64)
+        moments[:, :d] = resp[:, :n] @ x
+        moments[:, d] = resp[:, :n].sum(dim=1)
         if multi:
-            dist.all_reduce(stats, group=group)
-        blocks = stats[:k * sb].view(k, sb)
-        counts = blocks[:, 0]
+            dist.all_reduce(moments, group=group)
+        counts = moments[:, d]
         nz = counts > 0
         moved = centres.clone()
-        moved[nz] = moved[nz] + blocks[nz, 1:1 + d] / counts[nz][:, None]
+        moved[nz] = moments[nz, :d] / counts[nz][:, None]
         shift = ((moved - centres) ** 2).sum()
         centres = moved.contiguous()
         if n_lloyd > 0 and bool(shift <= shift_tol):
