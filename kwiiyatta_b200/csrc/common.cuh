@@ -59,7 +59,7 @@ void launch_reduce_fixed(const double* in, long long n, double extra, double* ou
 // gmm_tc.cu
 size_t tc_workspace_bytes(long long N, int K, int D);
 int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st);
+                   size_t workspace_bytes, cudaStream_t st, bool mstep_parts = true);
 int mstats_tc(long long N, const double* X, int K, int D, const double* resp, const double* centres,
               double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,

@@ -518,7 +518,7 @@ extern "C" int kw_convert_batch(int n_utts, const int64_t* off_dev, int64_t tota
     int rc;
     if (precision == 1) {
         rc = pack_frames_tc(total, src_dev, K, Dh, static_cast<char*>(workspace_dev) + w.bytes,
-                            workspace_bytes - w.bytes, st);
+                            workspace_bytes - w.bytes, st, /*mstep_parts=*/false);
         if (rc != KW_OK) return rc;
     }
     if (precision == 1)

@@ -366,7 +366,8 @@ __device__ __forceinline__ void split_store(double v, __half* hi_dst, __half* lo
 
 // One CTA per 128-frame tile.
 __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restrict__ X,
-                              const double* __restrict__ xinfo, __half* __restrict__ xt) {
+                              const double* __restrict__ xinfo, __half* __restrict__ xt,
+                              int mstep_parts) {
     const long long tile = blockIdx.x;
     const int DPB = dpb_of(DP);
     __half* hi = xt + (size_t)tile * X_PARTS * tile_elems(DP);
@@ -390,6 +391,7 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
         const double res = v - (double)__half2float(h);
         hi[o] = h;
         lo_s[o] = __double2half(res * LO_SCALE);
+        if (!mstep_parts) continue;          // posterior only (conversion): E-step parts suffice
         lo_u[o] = __double2half(res);
         const size_t ok = (size_t)(r >> 6) * 64 * DPB + (size_t)c * 64 +
                           (size_t)((((r & 63) >> 3) ^ (c & 7)) * 8) + (r & 7);
@@ -2264,7 +2266,7 @@ static int tc_check(long long N, int K, int D, void* workspace, size_t workspace
 
 // Centre, scale, split and tile the frames once per (X, workspace).
 int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st) {
+                   size_t workspace_bytes, cudaStream_t st, bool mstep_parts) {
     TcWorkspace w;
     int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
     if (rc != KW_OK) return rc;
@@ -2276,7 +2278,8 @@ int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
     tc::colstats_final_kernel<<<(DP + 7) / 8, 256, 0, st>>>(N, D, DP, TC_STAT_CHUNKS, w.colpartial,
                                                             w.xinfo);
     KW_CUDA_CHECK(cudaGetLastError());
-    tc::pack_x_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(N, D, DP, X, w.xinfo, w.xt);
+    tc::pack_x_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(N, D, DP, X, w.xinfo, w.xt,
+                                                         mstep_parts ? 1 : 0);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
