@@ -129,8 +129,11 @@ def device_guard(device_of):
     return wrap
 
 
-# Pinned staging buffers for the host -> device copy of a batch, kept between calls (pinning is
-# far more expensive than the copy).  slot -> (tensor, event of the last copy that read it)
+# Pinned staging buffers (and the side streams of the packed host APIs) kept between calls: pinning
+# is far more expensive than the copy, and the caching allocator keeps one pool per stream.  This
+# is a per-process cache of the Python host layer (the C ABI itself keeps no state); calls that
+# share a slot must not run concurrently from several host threads.
+# slot -> (tensor, event of the last copy that read it) or a dict of buffers
 _STAGING = {}
 _GATHER_THREADS = max(4, min(32, os.cpu_count() or 8))
 _POOL = None

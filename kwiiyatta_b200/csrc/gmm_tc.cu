@@ -895,27 +895,22 @@ __global__ void refine_argmax_kernel(long long N, int D, const double* __restric
 //
 //   S_k[i][j] = sum_n z_ni x'_nj,   z_ni = r_nk (x'_ni - mu'_ki)        (i, j < DP; x'_{n,DP} = 1)
 //
-// A = z (generated per (tile, component) by CUDA cores, fp16 hi + unscaled lo), B = x' (the
-// packed frames, shared by all components), both MN-major (the contraction runs over frames).
-// Work item = (component, chunk of 64-frame tiles); the accumulator lives in TMEM for M_FLUSH
-// tiles, is then added (fp32, round-to-nearest) into registers of the epilogue warps and written
-// as float64 partials at the end of the item.  Rows >= 128 of S come from a second, narrow MMA on
-// a shifted row window (rows DP-128 .. DP-1 x columns 128 .. DP+15).
+// A = z (generated per (tile, component) by CUDA cores, fp16 hi + lo), B = x' (the packed frames,
+// shared by all components); the contraction runs over the frames of a 64-frame tile.  Work item
+// = (component, chunk of tiles); the accumulator (rows = features 0..127, columns = features and
+// the ones column) is flushed from TMEM after every tile into fp32 registers of the epilogue warps
+// (round to nearest, with the tile's weight scale undone) and written as fp32 partials at the end
+// of the item, summed in fp64 in a fixed order afterwards.  Rows 128..143 of S (D = 144) are the
+// transposes of columns the MMA already produces, except a 16 x 17 corner (second block of the
+// partial, rows 112..127).
 // ------------------------------------------------------------------------------------------
 constexpr int MT = 64;        // frames per M-step tile
 
-__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
-    return make_idesc(M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
-}
-
 struct MstepGeom {
-    int DP, DPB, DA;     // DA = feature rows of the A tile (>= 128)
-    int N1, N2;          // accumulator widths of the two MMAs (N2 = 0 when DP <= 128)
-    int a_win2;          // first feature group of MMA2's row window
-    uint32_t b_stage, a_stage;   // bytes per smem stage (hi + lo)
-    uint32_t off_b, off_a, off_rs, off_mu, off_flags, off_bars, off_tmem, off_corner, total;
-    int partial_len;     // doubles per work item
-    bool corner;         // DP == 144: the 16 x 17 block outside MMA1 goes to a mma.sync warp
+    int DP, DPB, DA;     // DA = rows of the per-component centre table (>= 128)
+    int N1, N2;          // widths of the two blocks of a partial (N2 = 0 when DP <= 128)
+    int partial_len;     // floats per work item
+    bool corner;         // DP == 144: the 16 x 17 block outside the MMA goes to mma.sync warps
 };
 __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     MstepGeom g;
@@ -924,28 +919,10 @@ __host__ __device__ inline MstepGeom mstep_geom(int DP) {
     g.DA = DP > 128 ? DP : 128;
     g.N1 = g.DPB;
     g.N2 = DP > 128 ? DP + 16 - 128 : 0;
-    g.a_win2 = (DP - 128) / 8;
-    g.b_stage = 2u * MT * g.DPB * 2;
-    g.a_stage = 2u * MT * g.DA * 2;
-    uint32_t o = 0;
-    g.off_b = o;    o += 2 * g.b_stage;
-    g.off_a = o;    o += 2 * g.a_stage;
-    g.off_rs = o;   o += 2 * MT * 4;
-    o = (o + 15u) & ~15u;
-    g.off_mu = o;   o += (uint32_t)g.DA * 4;
-    o = (o + 15u) & ~15u;
-    g.off_flags = o; o += 64;    // group_empty[2] at +32, pskip[2] at +48 (int)
-    g.off_bars = o; o += 24 * 8;
-    g.off_tmem = o; o += 16;
-    g.off_corner = o; o += 2 * 12 * 32 * 4;  // second-level sums of the two corner warps
-    g.total = o;
     g.partial_len = 128 * g.N1 + 128 * g.N2;
     g.corner = (DP == 144);
     return g;
 }
-
-enum { MB_B_FULL = 0, MB_B_EMPTY = 2, MB_A_FULL = 4, MB_A_EMPTY = 6, MB_TM_FULL = 8,
-       MB_TM_EMPTY = 10, MB_IT_FULL = 12, MB_IT_EMPTY = 16 };   // 4 item-ring slots each
 
 // mu'_k = fl32((mu_k - c) / sigma) for the generators, one CTA per component.
 __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restrict__ centres,
@@ -985,606 +962,28 @@ mstats_tc_flags_kernel(long long N, long long Npad, int n_mtiles, int n_mt_pad, 
     if ((lane & 7) == 0) flags[(size_t)k * n_mt_pad + tile] = (m > 1e-16f) ? 1 : 0;
 }
 
-template <bool PROF>
-__global__ void __launch_bounds__(640, 1)
-mstats_tc_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
-                 int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
-                 const float* __restrict__ mu32, float* __restrict__ partial,
-                 double* __restrict__ npartial, int swap_strides, int M_FLUSH,
-                 int* __restrict__ item_counter, const unsigned char* __restrict__ tflags,
-                 int n_mt_pad, unsigned long long* __restrict__ prof) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const MstepGeom G = mstep_geom(DP);
-    unsigned char* b_base = smem + G.off_b;
-    unsigned char* a_base = smem + G.off_a;
-    float* r_s = reinterpret_cast<float*>(smem + G.off_rs);
-    volatile int* gflag = reinterpret_cast<volatile int*>(smem + G.off_flags + 32);       // [2 TMEM stages]
-    volatile int* pent = reinterpret_cast<volatile int*>(smem + G.off_flags + 48);        // [2 stages] tile of the entry, -1 = end of item
-    // Per-tile power-of-two weight scale.  A = r (x' - mu') is fp16: with small responsibilities
-    // it drops into the subnormal range and loses its low part, so the producer scales the
-    // tile's weights to max r in [0.5, 1) and the flush multiplies the tile's sums back
-    // (pinv: by B stage, ginv: by TMEM stage; both exact powers of two).
-    volatile float* pinv = reinterpret_cast<volatile float*>(smem + G.off_flags + 16);    // [2 B stages]
-    volatile float* ginv = reinterpret_cast<volatile float*>(smem + G.off_flags + 24);    // [2 TMEM stages]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.off_bars);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G.off_tmem);
-    // warp index through a shuffle so the compiler knows the role branches are warp-uniform
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int n_items = K * n_chunks;
-    const uint32_t part_b = (uint32_t)MT * G.DPB * 2;   // bytes of one part of a B stage
-    const uint32_t part_a = (uint32_t)MT * G.DA * 2;
-    const uint32_t acc_cols = (uint32_t)(G.N1 + G.N2);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(bars + MB_B_FULL + i, 1);
-            // 8 generator warps + the MMA commit (+ the corner warps)
-            mbar_init(bars + MB_B_EMPTY + i, 9 + (G.corner ? 2 : 0));
-            mbar_init(bars + MB_A_FULL + i, 8);
-            mbar_init(bars + MB_A_EMPTY + i, 1 + (G.corner ? 2 : 0));
-            mbar_init(bars + MB_TM_FULL + i, 1);
-            mbar_init(bars + MB_TM_EMPTY + i, 8);
-        }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bars + MB_IT_FULL + i, 1);
-            // consumers of an item: MMA warp, corner warps, 8 generator and 8 epilogue warps
-            mbar_init(bars + MB_IT_EMPTY + i, 17 + (G.corner ? 2 : 0));
-        }
-        fence_barrier_init();
-    }
-    // zero the A stages once (feature rows >= DP stay zero)
-    for (uint32_t i = threadIdx.x; i < 2 * G.a_stage / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(a_base)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    // Work items (component, chunk of tiles) are handed out dynamically: the frames are kept
-    // sorted by dominant component, so items differ widely in how many of their tiles carry
-    // weight, and a static round-robin leaves the kernel waiting for the unlucky CTAs.  The
-    // producer warp draws the next item from a global counter and passes it to the other roles
-    // through a 4-slot ring (every role sees the same sequence; -1 ends it).
-    volatile int* item_ring = reinterpret_cast<volatile int*>(smem + G.off_flags);   // [4]
-    auto next_item = [&](uint32_t idx) -> int {          // consumer side, whole warp
-        const uint32_t slot = idx & 3u;
-        mbar_wait(bars + MB_IT_FULL + slot, (idx >> 2) & 1u);
-        const int it = item_ring[slot];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + MB_IT_EMPTY + slot);
-        return it;
-    };
-    auto draw_item = [&](uint32_t idx) -> int {          // producer warp
-        int it = 0;
-        if (lane == 0) {
-            const uint32_t slot = idx & 3u;
-            mbar_wait(bars + MB_IT_EMPTY + slot, ((idx >> 2) & 1u) ^ 1u);
-            it = atomicAdd(item_counter, 1);
-            if (it >= n_items) it = -1;
-            item_ring[slot] = it;
-            mbar_arrive(bars + MB_IT_FULL + slot);
-        }
-        return __shfl_sync(0xffffffffu, it, 0);
-    };
-    auto item_tiles = [&](int item, int& k, int& t0, int& t1) {
-        const int chunk = item / K;
-        k = item - chunk * K;
-        t0 = chunk * tiles_per_chunk;
-        t1 = min(n_mtiles, t0 + tiles_per_chunk);
-    };
-
-    // warpgroup 0: producer + MMA issuer (+2 idle warps), 1-2: generators, 3-4: epilogue (holds
-    // the second-level accumulators, so it takes the registers the others give up).  The sum
-    // after rebalancing must not exceed the launch allocation (640 x 96): setmaxnreg.inc only
-    // draws from what the CTA's own warps released:  128*40 + 256*88 + 256*128 = 60416 <= 61440.
-    if (warp < 4) {
-      reg_dec<40>();
-      if (warp == 0) {
-        // ---------------- producer: packed frames (hi, unscaled lo) ----------------
-        // mstats_tc_flags_kernel marked the tiles that carry weight for each component; the
-        // warp looks 32 of them up at a time.  A tile whose responsibilities are all <= 1e-16
-        // contributes nothing representable and never enters the pipeline; for the others the
-        // producer loads the weights (two frames per lane, one entry ahead) and also
-        // publishes the weights (fp32, as the MMAs will see them) with the stage, so the
-        // generators read nothing from global memory.  Every item ends with an END entry
-        // (pent = -1) that lets the other roles close the item.
-        {
-            uint32_t g = 0;
-            for (uint32_t it_idx = 0;; ++it_idx) {
-                const int item = draw_item(it_idx);
-                if (item < 0) break;
-                int k, t0, t1;
-                item_tiles(item, k, t0, t1);
-                auto load2 = [&](int t, double& r0, double& r1) {
-                    const long long n = (long long)t * MT + 2 * lane;
-                    const double* rp = respT + (size_t)k * Npad + n;
-                    r0 = (t >= 0 && n < N) ? rp[0] : 0.0;
-                    r1 = (t >= 0 && n + 1 < N) ? rp[1] : 0.0;
-                };
-                const unsigned char* fk = tflags + (size_t)k * n_mt_pad;
-                double nacc = 0.0;
-                for (int tb = t0; tb < t1; tb += 32) {
-                    // 32 tiles per look-up: which of them carry weight at all
-                    const int tq = tb + lane;
-                    unsigned mask = __ballot_sync(0xffffffffu, tq < t1 && fk[tq] != 0);
-                    double a0 = 0.0, a1 = 0.0;
-                    if (mask) load2(tb + __ffs(mask) - 1, a0, a1);
-                    while (mask) {
-                        const int t = tb + __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float f0 = (float)a0, f1 = (float)a1;
-                        const double a0w = a0, a1w = a1;                    // n_k sums the doubles
-                        load2(mask ? tb + __ffs(mask) - 1 : -1, a0, a1);   // next non-empty tile
-                        nacc += a0w + a1w;
-                        float fm = fmaxf(f0, f1);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-                            fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, o));
-                        // fm > 1e-16 (the tile is flagged non-empty): 2^-ex fm in [0.5, 1)
-                        int ex;
-                        (void)frexpf(fm, &ex);
-                        const float up = ldexpf(1.f, -ex);
-                        const uint32_t s = g & 1u, u = g >> 1;
-                        mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                        *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) =
-                            make_float2(f0 * up, f1 * up);
-                        __syncwarp();
-                        if (lane == 0) {
-                            pinv[s] = ldexpf(1.f, ex);
-                            pent[s] = t;
-                            mbar_expect_tx(bars + MB_B_FULL + s, 2 * part_b);
-                            const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
-                                                 (size_t)(t & 1) * MT * G.DPB;
-                            unsigned char* dst = b_base + s * G.b_stage;
-                            bulk_g2s(dst, tile, part_b, bars + MB_B_FULL + s);
-                            bulk_g2s(dst + part_b, tile + 2 * tile_elems(DP), part_b,
-                                     bars + MB_B_FULL + s);
-                        }
-                        __syncwarp();
-                        ++g;
-                    }
-                }
-                {   // END of the item
-                    const uint32_t s = g & 1u, u = g >> 1;
-                    mbar_wait(bars + MB_B_EMPTY + s, (u & 1u) ^ 1u);
-                    if (lane == 0) {
-                        pent[s] = -1;
-                        mbar_arrive(bars + MB_B_FULL + s);
-                    }
-                    __syncwarp();
-                    ++g;
-                }
-                // n_k of this item
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
-                if (lane == 0) {
-                    npartial[(size_t)item * 2] = nacc;
-                    npartial[(size_t)item * 2 + 1] = 0.0;
-                }
-            }
-        }
-      } else if (warp == 1) {
-        // ---------------- MMA issuer (whole warp converged, one elected lane issues) --------
-        {
-            const uint32_t idesc1 = make_idesc_mn(128, G.N1);
-            const uint32_t idesc2 = make_idesc_mn(128, G.N2 > 0 ? G.N2 : 16);
-            // MN-major, no swizzle: SBO = stride between 8-element groups along M/N (features),
-            // LBO = stride between 8-frame groups along K.  Base descriptors per stage and part;
-            // per MMA only an offset is added to the address field.
-            const uint32_t sbo = 128, lbo_a = (uint32_t)(G.DA / 8) * 128,
-                           lbo_b = (uint32_t)(G.DPB / 8) * 128;
-            uint64_t d_a[2][2], d_b[2][2];      // [stage][0 = hi, 1 = lo]
-#pragma unroll
-            for (int st = 0; st < 2; ++st)
-#pragma unroll
-                for (int pt = 0; pt < 2; ++pt) {
-                    d_a[st][pt] = make_desc(smem_u32(a_base + st * G.a_stage + pt * part_a), lbo_a, sbo);
-                    d_b[st][pt] = make_desc(smem_u32(b_base + st * G.b_stage + pt * part_b), lbo_b, sbo);
-                }
-            const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
-            const uint64_t win_a = (uint64_t)(G.a_win2 * 128) >> 4, win_b = (16 * 128) >> 4;
-            const bool has2 = G.N2 > 0 && !G.corner;
-            (void)swap_strides;
-            long long p_tm = 0, p_a = 0, p_b = 0, p_issue = 0;
-            const long long p_start = tick<PROF>();
-            uint32_t g = 0, f = 0;
-            for (uint32_t it_idx = 0;; ++it_idx) {
-                const int item = next_item(it_idx);
-                if (item < 0) break;
-                int cnt = 0;                      // tiles accumulated since the last flush
-                for (;;) {
-                    const uint32_t s = g & 1u, u = g >> 1;
-                    const uint32_t ts = f & 1u, tu = f >> 1;
-                    const long long c0 = tick<PROF>();
-                    mbar_wait(bars + MB_B_FULL + s, u & 1u);
-                    const int tt = pent[s];
-                    const float tile_inv = pinv[s];
-                    const long long c1 = tick<PROF>();
-                    if (cnt == 0) mbar_wait(bars + MB_TM_EMPTY + ts, (tu & 1u) ^ 1u);
-                    const long long c2 = tick<PROF>();
-                    mbar_wait(bars + MB_A_FULL + s, u & 1u);
-                    const long long c3 = tick<PROF>();
-                    p_b += c1 - c0; p_tm += c2 - c1; p_a += c3 - c2;
-                    tc_fence_after();
-                    ++g;
-                    if (tt < 0) {
-                        // END: release the stage and close the item's last flush group
-                        if (lane == 0) {
-                            mbar_arrive(bars + MB_A_EMPTY + s);
-                            mbar_arrive(bars + MB_B_EMPTY + s);
-                            gflag[ts] = (cnt > 0 ? 1 : 0) | 2;
-                        }
-                        __threadfence_block();
-                        __syncwarp();
-                        umma_commit(bars + MB_TM_FULL + ts);
-                        ++f;
-                        break;
-                    }
-                    const uint32_t acc1 = tmem_base + ts * acc_cols;
-                    const uint32_t acc2 = acc1 + (uint32_t)G.N1;
-                    const uint64_t a_hi_d = s ? d_a[1][0] : d_a[0][0], a_lo_d = s ? d_a[1][1] : d_a[0][1];
-                    const uint64_t b_hi_d = s ? d_b[1][0] : d_b[0][0], b_lo_d = s ? d_b[1][1] : d_b[0][1];
-                    if (swap_strides != 1) {      // (1 = timing experiment: no MMAs)
-                    // The accumulator truncates (round toward zero) on every MMA, a loss in
-                    // proportion to what it already holds: the two small cross passes
-                    // (A_hi B_lo, A_lo B_hi; 2^-11 of the main term) go first, so with one tile per
-                    // flush only the four A_hi B_hi MMAs truncate at full magnitude.
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        uint64_t da = (pass == 1) ? a_lo_d : a_hi_d;     // A lo in pass 1
-                        uint64_t db = (pass == 0) ? b_lo_d : b_hi_d;     // B lo in pass 0
-#pragma unroll
-                        for (int ks = 0; ks < MT / 16; ++ks) {
-                            const uint32_t accum = (pass > 0 || ks > 0) ? 1u : (cnt > 0 ? 1u : 0u);
-                            umma_f16(acc1, da, db, idesc1, accum);
-                            if (has2) umma_f16(acc2, da + win_a, db + win_b, idesc2, accum);
-                            da += step_a;
-                            db += step_b;
-                        }
-                    }
-                    }
-                    umma_commit(bars + MB_A_EMPTY + s);
-                    umma_commit(bars + MB_B_EMPTY + s);
-                    ++cnt;
-                    if (cnt == M_FLUSH) {      // M_FLUSH is 1: the flush undoes this tile's scale
-                        if (lane == 0) {
-                            gflag[ts] = 1;
-                            ginv[ts] = tile_inv;
-                        }
-                        __threadfence_block();
-                        __syncwarp();
-                        umma_commit(bars + MB_TM_FULL + ts);
-                        ++f;
-                        cnt = 0;
-                    }
-                    p_issue += tick<PROF>() - c3;
-                }
-            }
-            if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
-                prof[0] = (unsigned long long)(tick<PROF>() - p_start);
-                prof[1] = (unsigned long long)p_tm;
-                prof[2] = (unsigned long long)p_a;
-                prof[3] = (unsigned long long)p_b;
-                prof[4] = (unsigned long long)p_issue;
-                prof[5] = g;
-            }
-        }
-      } else if (G.corner) {
-        // ---------------- corner warps 2, 3: features 128..143 x columns 128..151 -----------
-        // MMA1 covers feature rows 0..127; what is left of the symmetric block is 16 rows x 17
-        // columns, far too small for a tcgen05 instruction (its dispatch alone costs as much
-        // as an N = 160 one).  Two warps (each takes half of a tile's frames) compute it with
-        // m16n8k16 mma.sync straight from the operand tiles the tcgen05 MMAs use: A (MN-major,
-        // hi / lo) and the packed frames B; the 8 x 8 core matrices are ldmatrix.trans tiles
-        // as they lie.
-        const int cw = warp - 2;
-        float* cacc = reinterpret_cast<float*>(smem + G.off_corner) + cw * 12 * 32;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
-        const int kgA = G.DA / 8, kgB = G.DPB / 8;
-        const uint32_t mi = (uint32_t)lane >> 3, rr = (uint32_t)lane & 7u;
-        // per-lane row addresses inside a stage for k-step 0 (frame groups 0, 1)
-        const uint32_t la = (((mi >> 1) * kgA + 16 + (mi & 1u)) * 8 + rr) * 16;
-        const uint32_t lb = (((mi & 1u) * kgB + 16 + (mi >> 1)) * 8 + rr) * 16;
-        const uint32_t lb2 = (((mi & 1u) * kgB + 18) * 8 + rr) * 16;
-        const uint32_t ka = 2u * kgA * 128, kb = 2u * kgB * 128;     // bytes per k-step
-        const uint32_t a_s0 = smem_u32(a_base), b_s0 = smem_u32(b_base);
-        float acc[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-        uint32_t g = 0;
-        long long c_wait = 0, c_work = 0;
-        for (uint32_t it_idx = 0;; ++it_idx) {
-            const int item = next_item(it_idx);
-            if (item < 0) break;
-            int cnt = 0;
-            for (;;) {
-                const uint32_t s = g & 1u, u = g >> 1;
-                const long long c0 = tick<PROF>();
-                mbar_wait(bars + MB_B_FULL + s, u & 1u);
-                const int tt = pent[s];
-                const float tile_inv = pinv[s];
-                mbar_wait(bars + MB_A_FULL + s, u & 1u);
-                const long long c1 = tick<PROF>();
-                c_wait += c1 - c0;
-                ++g;
-                if (tt >= 0 && swap_strides != 1) {
-                    const uint32_t ab = a_s0 + s * G.a_stage + la, bb = b_s0 + s * G.b_stage;
-#pragma unroll
-                    for (int kq = 0; kq < MT / 32; ++kq) {
-                        const int ks = cw * (MT / 32) + kq;
-                        uint32_t ah[4], al[4], bh[6], bl[4];
-                        ldsm4_t(ab + ks * ka, ah);
-                        ldsm4_t(ab + part_a + ks * ka, al);
-                        ldsm4_t(bb + lb + ks * kb, bh);
-                        ldsm2_t(bb + lb2 + ks * kb, bh + 4);
-                        ldsm4_t(bb + part_b + lb + ks * kb, bl);
-#pragma unroll
-                        for (int nb = 0; nb < 3; ++nb) {
-                            mma16816(acc + 4 * nb, al, bh + 2 * nb);
-                            // (the ones column of block 2 has no lo part)
-                            if (nb < 2) mma16816(acc + 4 * nb, ah, bl + 2 * nb);
-                            mma16816(acc + 4 * nb, ah, bh + 2 * nb);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bars + MB_A_EMPTY + s);
-                    mbar_arrive(bars + MB_B_EMPTY + s);
-                }
-                if (tt >= 0) ++cnt;
-                if (cnt == M_FLUSH || (tt < 0 && cnt > 0)) {
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) {
-                        cacc[i * 32 + lane] = fmaf(acc[i], tile_inv, cacc[i * 32 + lane]);
-                        acc[i] = 0.f;
-                    }
-                    cnt = 0;
-                }
-                c_work += tick<PROF>() - c1;
-                if (tt < 0) break;
-            }
-            // rows 112..127 of the second accumulator block of this item's partial: warp 2 adds
-            // warp 3's half and writes
-            asm volatile("bar.sync 3, 64;" ::: "memory");
-            if (cw == 1) {
-                asm volatile("bar.sync 3, 64;" ::: "memory");    // warp 2 has read our sums
-#pragma unroll
-                for (int i = 0; i < 12; ++i) cacc[i * 32 + lane] = 0.f;
-                continue;
-            }
-            float* out = partial + (size_t)item * G.partial_len + (size_t)128 * G.N1;
-            const int gq = lane >> 2, tq = lane & 3;
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float2 v = make_float2(0.f, 0.f);
-                    if (nb < 3) {
-                        v.x = cacc[(4 * nb + 2 * h) * 32 + lane] +
-                              cacc[(12 + 4 * nb + 2 * h) * 32 + lane];
-                        v.y = cacc[(4 * nb + 2 * h + 1) * 32 + lane] +
-                              cacc[(12 + 4 * nb + 2 * h + 1) * 32 + lane];
-                        cacc[(4 * nb + 2 * h) * 32 + lane] = 0.f;
-                        cacc[(4 * nb + 2 * h + 1) * 32 + lane] = 0.f;
-                    }
-                    *reinterpret_cast<float2*>(out + (size_t)(112 + gq + 8 * h) * G.N2 + nb * 8 +
-                                               2 * tq) = v;
-                }
-            asm volatile("bar.sync 3, 64;" ::: "memory");
-        }
-        if (prof != nullptr && blockIdx.x == 0 && lane == 0 && cw == 0) {
-            prof[6] = (unsigned long long)c_wait;
-            prof[7] = (unsigned long long)c_work;
-        }
-      }
-    } else if (warp < 12) {
-        reg_dec<88>();
-        // ---------------- generators (warps 4..11): A = r (x' - mu') split into hi / lo ---------
-        const int gt = threadIdx.x - 128;    // 0..255
-        const int kgA = G.DA / 8, kgB = G.DPB / 8, kgD = DP / 8;
-        // Chunk = 16 bytes = 8 features of one frame.  A thread keeps the SAME feature group for
-        // all its chunks, so mu' of that group lives in registers:
-        //   main: feature group gt/16 (0..15), frame-in-group gt&7, frame groups 4*((gt>>3)&1)+q;
-        //   extra (feature groups 16, 17 when DP > 128): threads < 128 take one more chunk.
-        const int fr = gt & 7;
-        const int featg_a = gt >> 4, fg_a0 = ((gt >> 3) & 1) * 4;
-        const bool on_a = featg_a < kgD;
-        const int featg_b = 16 + (gt >> 6), fg_b = (gt >> 3) & 7;
-        const bool on_b = gt < 128 && featg_b < kgD;
-        uint32_t a_bo[4], a_ao[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            a_bo[q] = ((uint32_t)((fg_a0 + q) * kgB + featg_a) * 8 + fr) * 16;
-            a_ao[q] = ((uint32_t)((fg_a0 + q) * kgA + featg_a) * 8 + fr) * 16;
-        }
-        const uint32_t b_bo = ((uint32_t)(fg_b * kgB + featg_b) * 8 + fr) * 16;
-        const uint32_t b_ao = ((uint32_t)(fg_b * kgA + featg_b) * 8 + fr) * 16;
-        uint32_t g = 0;
-        long long g_b = 0, g_a = 0, g_gen = 0, g_pub = 0, g_bar = 0;
-        const long long g_start = tick<PROF>();
-        for (uint32_t it_idx = 0;; ++it_idx) {
-            const int item = next_item(it_idx);
-            if (item < 0) break;
-            int k, t0, t1;
-            item_tiles(item, k, t0, t1);
-            float mu_a[8], mu_b[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                mu_a[e] = on_a ? mu32[(size_t)k * G.DA + featg_a * 8 + e] : 0.f;
-                mu_b[e] = on_b ? mu32[(size_t)k * G.DA + featg_b * 8 + e] : 0.f;
-            }
-            for (;;) {
-                const uint32_t s = g & 1u, u = g >> 1;
-                const long long c0 = tick<PROF>();
-                mbar_wait(bars + MB_B_FULL + s, u & 1u);
-                const int tt = pent[s];           // tile of this entry, -1 = end of the item
-                const long long c1 = tick<PROF>();
-                mbar_wait(bars + MB_A_EMPTY + s, (u & 1u) ^ 1u);
-                const long long c2 = tick<PROF>();
-                g_b += c1 - c0; g_a += c2 - c1;
-                const unsigned char* bh = b_base + s * G.b_stage;
-                unsigned char* ah = a_base + s * G.a_stage;
-                const float* rt = r_s + s * MT;   // published by the producer with the stage
-                auto convert = [&](uint32_t bo, uint32_t ao, float r, const float* mu8) {
-                    const uint4 hv = *reinterpret_cast<const uint4*>(bh + bo);
-                    const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + bo);
-                    const __half2* hp = reinterpret_cast<const __half2*>(&hv);
-                    const __half2* lp = reinterpret_cast<const __half2*>(&lv);
-                    uint4 oh, ol;
-                    __half2* ohp = reinterpret_cast<__half2*>(&oh);
-                    __half2* olp = reinterpret_cast<__half2*>(&ol);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
-                        const float z0 = r * ((xh.x + xl.x) - mu8[2 * e]);
-                        const float z1 = r * ((xh.y + xl.y) - mu8[2 * e + 1]);
-                        const __half2 zh = __floats2half2_rn(z0, z1);
-                        const float2 zf = __half22float2(zh);
-                        ohp[e] = zh;
-                        olp[e] = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
-                    }
-                    *reinterpret_cast<uint4*>(ah + ao) = oh;
-                    *reinterpret_cast<uint4*>(ah + part_a + ao) = ol;
-                };
-                if (tt >= 0 && swap_strides != 2) {   // (2 = timing experiment: no generation)
-                    if (on_a) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            convert(a_bo[q], a_ao[q], rt[(fg_a0 + q) * 8 + fr], mu_a);
-                    }
-                    if (on_b) convert(b_bo, b_ao, rt[fg_b * 8 + fr], mu_b);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bars + MB_A_FULL + s);
-                    mbar_arrive(bars + MB_B_EMPTY + s);
-                }
-                g_gen += tick<PROF>() - c2;
-                ++g;
-                if (tt < 0) break;
-            }
-        }
-        if (prof != nullptr && blockIdx.x == 0 && gt == 64) {
-            prof[8] = (unsigned long long)(tick<PROF>() - g_start);
-            prof[9] = (unsigned long long)g_b;
-            prof[10] = (unsigned long long)g_a;
-            prof[11] = (unsigned long long)g_gen;
-            prof[12] = (unsigned long long)g_pub;
-            prof[13] = (unsigned long long)g_bar;
-        }
-    } else {
-        reg_inc<128>();
-        // ---------------- epilogue (warps 12..19): TMEM -> fp32 registers -> fp64 partials -----
-        const uint32_t quarter = (uint32_t)(warp & 3);
-        const int half = (warp - 12) >> 2;
-        const int row = (int)quarter * 32 + lane;
-        const int n16_1 = G.N1 / 16, n16_2 = G.N2 / 16;
-        const int c1_begin = half == 0 ? 0 : (n16_1 + 1) / 2;
-        const int c1_end = half == 0 ? (n16_1 + 1) / 2 : n16_1;
-        const int c2_begin = half == 0 ? 0 : (n16_2 + 1) / 2;
-        const int c2_end = half == 0 ? (n16_2 + 1) / 2 : n16_2;
-        float acc[6][16];
-        uint32_t f = 0;
-        for (uint32_t it_idx = 0;; ++it_idx) {
-            const int item = next_item(it_idx);
-            if (item < 0) break;
-            int k, t0, t1;
-            item_tiles(item, k, t0, t1);
-#pragma unroll
-            for (int c = 0; c < 6; ++c)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
-            for (;;) {
-                const uint32_t ts = f & 1u, tu = f >> 1;
-                mbar_wait(bars + MB_TM_FULL + ts, tu & 1u);
-                tc_fence_after();
-                const int fl = gflag[ts];         // bit 0: the group holds data, bit 1: last group
-                const bool empty = (fl & 1) == 0;
-                const float inv = empty ? 0.f : ginv[ts];
-                const float2 inv2 = make_float2(inv, inv);
-                const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + ts * acc_cols;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    if (!empty && c1_begin + c < c1_end) {
-                        uint32_t v[16];
-                        tmem_ld16(tbase + (uint32_t)(c1_begin + c) * 16, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float2 t = __ffma2_rn(
-                                make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2,
-                                make_float2(acc[c][j], acc[c][j + 1]));
-                            acc[c][j] = t.x;
-                            acc[c][j + 1] = t.y;
-                        }
-                    }
-                }
-                if (!empty && c2_begin < c2_end && !G.corner) {
-                    uint32_t v[16];
-                    tmem_ld16(tbase + (uint32_t)G.N1 + (uint32_t)c2_begin * 16, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float2 t = __ffma2_rn(
-                            make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2,
-                            make_float2(acc[5][j], acc[5][j + 1]));
-                        acc[5][j] = t.x;
-                        acc[5][j + 1] = t.y;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + MB_TM_EMPTY + ts);
-                ++f;
-                if (fl & 2) break;
-            }
-            float* out = partial + (size_t)item * G.partial_len;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                if (c1_begin + c < c1_end) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        out[(size_t)row * G.N1 + (c1_begin + c) * 16 + j] = acc[c][j];
-                }
-            }
-            if (c2_begin < c2_end && !(G.corner && row >= 112)) {   // corner rows: the corner warp
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    out[(size_t)128 * G.N1 + (size_t)row * G.N2 + c2_begin * 16 + j] = acc[5][j];
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
 // ------------------------------------------------------------------------------------------
-// Tensor-core M-step statistics, second generation: the generated operand lives in TENSOR MEMORY.
+// The M-step kernel: the generated operand lives in TENSOR MEMORY.
 //
-// The first-generation kernel above writes A = r (x' - mu') to shared memory and the MMAs read it
-// back from there; with the packed frames B, the bulk copies and the generators' own reads that is
-// 230 KB of shared-memory traffic per (tile, component) against 85 clk x 12 MMAs of tensor time,
-// and the shared-memory pipe is what bounds it (profiles/ncu_r1d_mstats_tc.txt: 49 % LSU
-// wavefronts + the MMA operand reads, tensor pipe 38 %).  Here
+// Round 1's kernel (git history: mstats_tc_kernel) wrote A = r (x' - mu') to shared memory and the
+// MMAs read it back from there; with the packed frames B, the bulk copies and the generators' own
+// reads that was 230 KB of shared-memory traffic per (tile, component) against 85 clk x 12 MMAs of
+// tensor time, and the shared-memory pipe bounded it (profiles/ncu_r1d_mstats_tc.txt: 49 % LSU
+// wavefronts + the MMA operand reads, tensor pipe 38 %; dense case 1.83 ms, now 1.40 ms).  Here
 //   * A goes from the generators' registers straight into TMEM (tcgen05.st) and the MMAs take it
 //     from there (A-from-TMEM form of tcgen05.mma): no A stores, no A operand reads;
 //   * for that a thread must own one FEATURE (TMEM lane) and hold it for consecutive frames (two
 //     per 32-bit column), so the packed frames it reads are K-major -- one 128-byte row of 64
 //     frames per feature, 128-byte swizzled (pack_x_kernel's hi_k / lo_k parts); one 16-byte load
 //     is 8 frames of the thread's feature, and B, the same tile, is a swizzled K-major operand
-//     (the no-swizzle layouts of the first generation cost the MMAs twice their floor);
 //   * the shared memory A no longer needs holds a third B stage.
 // Rows 128..143 of S (D = 144) are the transposes of columns the big MMA already produces, except
 // the 16 x 17 corner, which two mma.sync warps compute as before from a small shared-memory copy
-// of those 16 rows of A.  Work distribution, tile skipping, per-tile weight scale, flush per tile
-// and the partial layout are those of the first generation (the reduce / post kernels are shared).
+// of those 16 rows of A.  Tiles without weight for the component never enter the pipeline
+// (mstats_tc_flags_kernel + the producer's ballot over 32 tiles); work items are drawn from a
+// global counter and handed to the other roles through a 4-slot ring, because frames sorted by
+// dominant component make them very uneven.  With dense data the kernel runs into the board's
+// power cap (tools/time_mstep.py): the dbg bits exist to take such measurements.
 // ------------------------------------------------------------------------------------------
 constexpr int M2_NB = 3;           // B stages
 struct Mstep2Smem {
@@ -2307,12 +1706,6 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     uint32_t cols = 32;
     while (cols < 2u * G * DP + DP + 16) cols <<= 1;  // two accumulator stages + the frame tile (hi+ones, lo)
     const int grid = (int)std::min<long long>(n_tiles, sms);
-    static unsigned long long* prof_dev = nullptr;
-    static int prof_on = -1;
-    if (prof_on < 0) {
-        prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
-        if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
-    }
     auto launch = [&](auto kern, unsigned long long* pd) -> int {
         KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)L.total));
@@ -2320,21 +1713,28 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
                                          resp, mode, mix, w.cand, 0.05, pd);
         return KW_OK;
     };
-    if (prof_on)
-        rc = (G == 2) ? launch(tc::estep_tc_kernel<true, 2>, prof_dev)
-                      : launch(tc::estep_tc_kernel<true, 1>, prof_dev);
-    else
-        rc = (G == 2) ? launch(tc::estep_tc_kernel<false, 2>, nullptr)
-                      : launch(tc::estep_tc_kernel<false, 1>, nullptr);
+#ifdef KW_TC_PROFILE_BUILD
+    // role profile (cycle counters of CTA 0): a separate instantiation, reading the clock
+    // serialises the issuing warp.  Build with -DKW_TC_PROFILE_BUILD to get it.
+    unsigned long long* prof_dev = nullptr;
+    cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
+    rc = (G == 2) ? launch(tc::estep_tc_kernel<true, 2>, prof_dev)
+                  : launch(tc::estep_tc_kernel<true, 1>, prof_dev);
     if (rc != KW_OK) return rc;
-    if (prof_on) {
+    {
         unsigned long long h[16];
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(prof_dev);
         fprintf(stderr, "[estep_tc cta0] mma: total %llu wait_tmem %llu wait_blo(+a) %llu wait_bhi %llu "
                         "issue %llu | epi(part0): total %llu barriers %llu wait_tmfull %llu work %llu | "
                         "epi(part3): barriers %llu wait %llu work %llu\n",
                 h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[13], h[14], h[15]);
     }
+#else
+    rc = (G == 2) ? launch(tc::estep_tc_kernel<false, 2>, nullptr)
+                  : launch(tc::estep_tc_kernel<false, 1>, nullptr);
+    if (rc != KW_OK) return rc;
+#endif
     KW_CUDA_CHECK(cudaGetLastError());
     if (mode == 1) {
         tc::refine_argmax_kernel<<<sms * 4, 256, 0, st>>>(N, D, X, pc, aux, mix, w.cand);
@@ -2359,10 +1759,6 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
     const tc::MstepGeom G = tc::mstep_geom(DP);
     tc::pack_centres_kernel<<<K, 160, 0, st>>>(K, D, G.DA, centres, w.xinfo, DP, w.mu32);
     KW_CUDA_CHECK(cudaGetLastError());
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
-    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
     KW_CUDA_CHECK(cudaMemsetAsync(w.item_counter, 0, sizeof(int), st));
@@ -2373,47 +1769,17 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
             N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags);
         KW_CUDA_CHECK(cudaGetLastError());
     }
-    static int swap_strides = -1, generation = 2;
-    const int m_flush = 1;     // one tile per TMEM flush: the flush carries the tile's weight scale
-    if (swap_strides < 0) {
-        const char* e = getenv("KW_TC_MSWAP");
-        swap_strides = e != nullptr ? atoi(e) : 0;
-        const char* g = getenv("KW_TC_MSTEP");     // 1 = first-generation kernel (A in smem)
-        if (g != nullptr && atoi(g) == 1) generation = 1;
-    }
-    if (generation == 2) {
-        const tc::Mstep2Smem L2 = tc::mstep2_smem(DP);
-        KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc2_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)L2.total));
-        tc::mstats_tc2_kernel<<<grid, 640, L2.total, st>>>(
-            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad, swap_strides);
-        KW_CUDA_CHECK(cudaGetLastError());
-    } else {
-    static unsigned long long* prof_dev = nullptr;
-    static int prof_on = -1;
-    if (prof_on < 0) {
-        prof_on = getenv("KW_TC_PROFILE") != nullptr ? 1 : 0;
-        if (prof_on) cudaMalloc(&prof_dev, 16 * sizeof(unsigned long long));
-    }
-    if (prof_on)
-        tc::mstats_tc_kernel<true><<<grid, 640, G.total, st>>>(
-            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, w.tflags, n_mt_pad, prof_dev);
-    else
-        tc::mstats_tc_kernel<false><<<grid, 640, G.total, st>>>(
-            N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-            w.mpartial, w.npartial, swap_strides, m_flush, w.item_counter, w.tflags, n_mt_pad, nullptr);
-    if (prof_on) {
-        unsigned long long h[16];
-        cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[mstats_tc cta0] mma: total %llu wait_tmem %llu wait_a %llu wait_b %llu "
-                        "issue %llu tiles %llu | corner: wait %llu work %llu | gen: total %llu wait_b %llu wait_a %llu work %llu publish %llu barrier %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
-    }
+    // timing experiments only (tools/time_mstep.py): bits that switch parts of the kernel off
+    const char* dbg_env = getenv("KW_TC_MSWAP");
+    const int dbg = dbg_env != nullptr ? atoi(dbg_env) : 0;
+    const tc::Mstep2Smem L2 = tc::mstep2_smem(DP);
+    KW_CUDA_CHECK(cudaFuncSetAttribute(tc::mstats_tc2_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)L2.total));
+    tc::mstats_tc2_kernel<<<grid, 640, L2.total, st>>>(
+        N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
+        w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad, dbg);
     KW_CUDA_CHECK(cudaGetLastError());
-    }
     tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
         K, G.partial_len, w.m_chunks, w.mpartial, w.npartial, w.mraw);
     KW_CUDA_CHECK(cudaGetLastError());
