@@ -20,12 +20,29 @@ def shard_indices(sizes, world_size):
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
 
 
-def allreduce_stats(stats, group=None):
+def allreduce_stats(stats, group=None, n_components=None, dim=None):
     """In-place sum of a statistics vector over the ranks of ``group`` (no-op when
-    torch.distributed is not initialised or the world has one rank)."""
+    torch.distributed is not initialised or the world has one rank).  For a CUDA vector with its
+    layout given (``n_components``, ``dim``) only the exchange form travels -- n_k, first moments
+    and the upper triangle of the symmetric second moments, half the bytes
+    (kw_gmm_stats_pack / kw_gmm_stats_unpack)."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return stats
+    if n_components is None or dim is None or not stats.is_cuda:
         dist.all_reduce(stats, group=group)
+        return stats
+    import torch
+    from . import _lib
+    lib = _lib.lib()
+    packed = torch.empty(lib.kw_gmm_stats_packed_len(n_components, dim), dtype=torch.float64,
+                         device=stats.device)
+    stream = torch.cuda.current_stream(stats.device).cuda_stream
+    _lib.check(lib.kw_gmm_stats_pack(n_components, dim, stats.data_ptr(), packed.data_ptr(),
+                                     stream), 'kw_gmm_stats_pack')
+    dist.all_reduce(packed, group=group)
+    _lib.check(lib.kw_gmm_stats_unpack(n_components, dim, packed.data_ptr(), stats.data_ptr(),
+                                       stream), 'kw_gmm_stats_unpack')
     return stats
 
 

@@ -179,7 +179,8 @@ class GaussianMixture:
     def _allreduce(self, torch):
         """The path's one exchange: sum of the statistics vector over the ranks."""
         from . import dist as kdist
-        kdist.allreduce_stats(self._stats, self.process_group)
+        k, d = self._means[self._cur].shape
+        kdist.allreduce_stats(self._stats, self.process_group, n_components=k, dim=d)
 
     def _finalize(self, torch, centres, weight_norm):
         k, d = centres.shape
