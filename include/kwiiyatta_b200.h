@@ -137,9 +137,11 @@ int kw_gmm_hard_labels(int64_t n_frames, const double* x_dev, int n_components, 
                        int32_t* labels_dev, int precision,
                        void* workspace_dev, size_t workspace_bytes, void* stream);
 
-/* M-step sufficient statistics around centres_dev (K, D) from resp_dev.  Frames with
- * r_nk <= 1e-16 are skipped (their total weight is below the rounding of n_k), so the cost
- * follows the sparsity of the posterior; the summation order is fixed (bitwise reproducible). */
+/* M-step sufficient statistics around centres_dev (K, D) from resp_dev.  Weight that cannot
+ * matter is skipped, so the cost follows the sparsity of the posterior: precision 0 drops frames
+ * with r_nk <= 1e-16 (below the rounding of n_k); precision 1 drops, per component, the 64-frame
+ * tiles in which every r_nk <= 1e-8 (orders below the rounding of its split-fp16 contraction).
+ * The summation order is fixed (bitwise reproducible). */
 int kw_gmm_mstep_accumulate(int64_t n_frames, const double* x_dev, int n_components, int dim,
                             const double* resp_dev, const double* centres_dev,
                             double* stats_dev, int precision,

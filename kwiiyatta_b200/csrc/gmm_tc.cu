@@ -936,12 +936,20 @@ __global__ void pack_centres_kernel(int K, int D, int DA, const double* __restri
     }
 }
 
-// flags[k][tile] = 1 when some frame of the 64-frame tile has weight > 1e-16 for component k
-// (as fp32, the form the MMAs see).  One warp per (component, 4 tiles): 8 lanes per tile, 8
-// consecutive frames per lane.
+// Per (component, 64-frame tile): everything the M-step kernel needs to know about the weights,
+// prepared in parallel over the whole GPU so that its single producer warp only issues copies:
+//   flags[k][tile]  1 when some frame of the tile has weight > floor (as fp32, the form the MMAs
+//                   see); only such tiles enter the kernel's pipeline
+//   wts[k][tile]    WSTRIDE floats: the 64 weights scaled by a power of two into [0.5, 1) at the
+//                   tile's maximum, then the inverse scale (one bulk copy puts them in shared memory)
+//   tsum[k][tile]   the tile's weight (double; 0 when not flagged): n_k is their fixed-order sum
+// One warp per (component, 4 tiles): 8 lanes per tile, 8 consecutive frames per lane.
+constexpr int WSTRIDE = MT + 4;
 __global__ void __launch_bounds__(256)
-mstats_tc_flags_kernel(long long N, long long Npad, int n_mtiles, int n_mt_pad, int K,
-                       const double* __restrict__ respT, unsigned char* __restrict__ flags) {
+mstats_tc_prep_kernel(long long N, long long Npad, int n_mtiles, int n_mt_pad, int K,
+                      const double* __restrict__ respT, unsigned char* __restrict__ flags,
+                      float* __restrict__ wts, double* __restrict__ tsum, float floor,
+                      int tiles_per_chunk, int* __restrict__ item_count) {
     const int lane = threadIdx.x & 31;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int gpk = n_mt_pad / 4;
@@ -949,17 +957,98 @@ mstats_tc_flags_kernel(long long N, long long Npad, int n_mtiles, int n_mt_pad, 
     if (k >= K) return;
     const int tile = (int)(w - (long long)k * gpk) * 4 + (lane >> 3);
     const long long n0 = (long long)tile * MT + (lane & 7) * 8;
-    float m = 0.f;
+    double r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = 0.0;
     if (tile < n_mtiles) {
         const double* rp = respT + (size_t)k * Npad + n0;
+        if (n0 + 8 <= N) {
+            const double2* rp2 = reinterpret_cast<const double2*>(rp);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (n0 + e < N) m = fmaxf(m, (float)rp[e]);
+            for (int e = 0; e < 4; ++e) {
+                const double2 v = rp2[e];
+                r[2 * e] = v.x;
+                r[2 * e + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (n0 + e < N) r[e] = rp[e];
+        }
     }
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    if ((lane & 7) == 0) flags[(size_t)k * n_mt_pad + tile] = (m > 1e-16f) ? 1 : 0;
+    float f[8];
+    float m = 0.f;
+    double sum = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        f[e] = (float)r[e];
+        m = fmaxf(m, f[e]);
+        sum += r[e];
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    const bool on = m > floor;
+    // 2^-ex m in [0.5, 1): power-of-two scale from the exponent bits
+    const uint32_t eb = __float_as_uint(m) >> 23;
+    const bool normal = eb >= 1u && eb <= 252u;
+    const float up = normal ? __uint_as_float((253u - eb) << 23) : 1.f;
+    const float inv = normal ? __uint_as_float((eb + 1u) << 23) : 1.f;
+    const size_t slot = (size_t)k * n_mt_pad + tile;
+    if (on) {
+        float4* dst = reinterpret_cast<float4*>(wts + slot * WSTRIDE + (lane & 7) * 8);
+        dst[0] = make_float4(f[0] * up, f[1] * up, f[2] * up, f[3] * up);
+        dst[1] = make_float4(f[4] * up, f[5] * up, f[6] * up, f[7] * up);
+    }
+    if ((lane & 7) == 0) {
+        flags[slot] = on ? 1 : 0;
+        tsum[slot] = on ? sum : 0.0;
+        if (on) atomicAdd(item_count + (tile / tiles_per_chunk) * K + k, 1);   // item = chunk K + k
+        if (on) *reinterpret_cast<float4*>(wts + slot * WSTRIDE + MT) = make_float4(inv, 0.f, 0.f, 0.f);
+    }
+}
+
+// Work items (component, chunk of tiles) in the order the persistent CTAs draw them: most tiles
+// first.  Frames sorted by dominant component make the items very uneven (0 .. all tiles carry
+// weight); drawn in index order the last ones decided the kernel's tail (+12 % on the bench
+// workload by list-scheduling the measured counts, tools/time_mstep_real.py).  Counting sort in one
+// block; ties in arbitrary order -- the order changes who computes an item, never a result.
+__global__ void __launch_bounds__(1024)
+mstats_tc_order_kernel(int n_items, const int* __restrict__ item_count, int* __restrict__ order) {
+    __shared__ int hist[1024], base[1024];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_items; i += 1024) atomicAdd(hist + min(item_count[i], 1023), 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 1023; b >= 0; --b) {
+            base[b] = run;
+            run += hist[b];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_items; i += 1024)
+        order[atomicAdd(base + min(item_count[i], 1023), 1)] = i;
+}
+
+// n_k = fixed-order sum of the tiles' weights; raw[k][partial_len].
+__global__ void __launch_bounds__(256)
+mstats_tc_nk_kernel(int n_mt_pad, int partial_len, const double* __restrict__ tsum,
+                    double* __restrict__ raw) {
+    __shared__ double sh[256];
+    const int k = blockIdx.x;
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n_mt_pad; i += 256) t += tsum[(size_t)k * n_mt_pad + i];
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) raw[(size_t)k * (partial_len + 1) + partial_len] = sh[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -996,9 +1085,9 @@ __host__ __device__ inline Mstep2Smem mstep2_smem(int DP) {
     uint32_t o = 0;
     g.off_b = o;      o += M2_NB * g.b_stage;
     g.off_ac = o;     o += 2u * 2 * 2048;          // corner rows of A: [A stage][hi, lo][2 KB]
-    g.off_rs = o;     o += M2_NB * MT * 4;
+    g.off_rs = o;     o += M2_NB * WSTRIDE * 4;     // per B stage: 64 scaled weights + inverse scale
     o = (o + 15u) & ~15u;
-    g.off_flags = o;  o += 96;   // item ring[4] | pinv[3] @16 | ginv[2] @32 | gflag[2] @48 | pent[3] @64
+    g.off_flags = o;  o += 96;   // item ring[4] | ginv[2] @32 | gflag[2] @48 | pent[3] @64
     g.off_bars = o;   o += 24 * 8;
     g.off_tmem = o;   o += 16;
     g.off_corner = o; o += 2 * 12 * 32 * 4;
@@ -1008,14 +1097,17 @@ __host__ __device__ inline Mstep2Smem mstep2_smem(int DP) {
 enum { M2_B_FULL = 0, M2_B_EMPTY = 3, M2_A_FULL = 6, M2_A_EMPTY = 8, M2_TM_FULL = 10,
        M2_TM_EMPTY = 12, M2_IT_FULL = 14, M2_IT_EMPTY = 18 };
 
+__device__ unsigned long long m2_prof[40];    // KW_TC_MSWAP & 16384: per-role wait clocks of CTA 0
+
 __global__ void __launch_bounds__(640, 1)
 mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk, int n_chunks,
-                  int K, int DP, const __half* __restrict__ xt, const double* __restrict__ respT,
+                  int K, int DP, const __half* __restrict__ xt, const float* __restrict__ wts,
                   const float* __restrict__ mu32, float* __restrict__ partial,
-                  double* __restrict__ npartial, int* __restrict__ item_counter,
+                  int* __restrict__ item_counter, const int* __restrict__ item_order,
                   const unsigned char* __restrict__ tflags, int n_mt_pad, int dbg) {
     // dbg (timing experiments only, 0 in production): 1 = no MMAs, 2 = no operand generation,
-    // 4 = no epilogue loads
+    // 4 = no epilogue loads, 1024 = no bulk copies, 2048 = no corner MMAs, 16384 = CTA 0 reports
+    // the clocks each role spends in its barrier waits
     extern __shared__ __align__(128) unsigned char smem[];
     const MstepGeom G = mstep_geom(DP);
     const Mstep2Smem L = mstep2_smem(DP);
@@ -1023,7 +1115,6 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
     unsigned char* ac_base = smem + L.off_ac;
     float* r_s = reinterpret_cast<float*>(smem + L.off_rs);
     volatile int* item_ring = reinterpret_cast<volatile int*>(smem + L.off_flags);          // [4]
-    volatile float* pinv = reinterpret_cast<volatile float*>(smem + L.off_flags + 16);     // [3 B stages]
     volatile float* ginv = reinterpret_cast<volatile float*>(smem + L.off_flags + 32);     // [2 TMEM stages]
     volatile int* gflag = reinterpret_cast<volatile int*>(smem + L.off_flags + 48);        // [2 TMEM stages]
     volatile int* pent = reinterpret_cast<volatile int*>(smem + L.off_flags + 64);         // [3 B stages]
@@ -1074,7 +1165,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
             const uint32_t slot = idx & 3u;
             mbar_wait(bars + M2_IT_EMPTY + slot, ((idx >> 2) & 1u) ^ 1u);
             it = atomicAdd(item_counter, 1);
-            if (it >= n_items) it = -1;
+            it = it < n_items ? item_order[it] : -1;
             item_ring[slot] = it;
             mbar_arrive(bars + M2_IT_FULL + slot);
         }
@@ -1087,8 +1178,31 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
         t1 = min(n_mtiles, t0 + tiles_per_chunk);
     };
 
+    // dbg & 16384: CTA 0 adds up the clocks each role spends in its barrier waits (m2_prof)
+    const bool prof_on = (dbg & 16384) != 0 && blockIdx.x == 0;
+    long long pw[4] = {0, 0, 0, 0};
+    const long long p_begin = prof_on ? clock64() : 0;
+    long long p_tiles = 0;
+    auto twait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if (!prof_on) {
+            mbar_wait(bar, parity);
+            return;
+        }
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t0;
+    };
+    auto report = [&](int role) {
+        if (prof_on && lane == 0) {
+            unsigned long long* o = m2_prof + role * 8;
+            o[0] = (unsigned long long)(clock64() - p_begin);
+            o[1] = (unsigned long long)p_tiles;
+            for (int i = 0; i < 4; ++i) o[2 + i] = (unsigned long long)pw[i];
+        }
+    };
+
     if (warp < 4) {
-      reg_dec<40>();
+      reg_dec<48>();
       if (warp == 0) {
         // ---------------- producer: K-major packed frames (hi, lo) + the tile's weights -------
         uint32_t g = 0;
@@ -1097,47 +1211,38 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
             if (item < 0) break;
             int k, t0, t1;
             item_tiles(item, k, t0, t1);
-            auto load2 = [&](int t, double& r0, double& r1) {
-                const long long n = (long long)t * MT + 2 * lane;
-                const double* rp = respT + (size_t)k * Npad + n;
-                r0 = (t >= 0 && n < N) ? rp[0] : 0.0;
-                r1 = (t >= 0 && n + 1 < N) ? rp[1] : 0.0;
-            };
             const unsigned char* fk = tflags + (size_t)k * n_mt_pad;
-            double nacc = 0.0;
+            const float* wk = wts + (size_t)k * n_mt_pad * WSTRIDE;
+            // The item's tiles that carry weight, in order.  This warp is one serial instruction
+            // stream per tile, and at ~200 instructions per tile (weights through registers, tile
+            // maximum, scale) it was the slowest role of the kernel on real posteriors
+            // (tools/time_mstep_real.py, KW_TC_MSWAP=16384: busy 83 % of the time, the MMA warp
+            // waiting).  All of that now happens beforehand in mstats_tc_prep_kernel; here a tile
+            // is three bulk copies: packed frames hi, lo and the prepared weights.
             for (int tb = t0; tb < t1; tb += 32) {
                 const int tq = tb + lane;
                 unsigned mask = __ballot_sync(0xffffffffu, tq < t1 && fk[tq] != 0);
-                double a0 = 0.0, a1 = 0.0;
-                if (mask) load2(tb + __ffs(mask) - 1, a0, a1);
                 while (mask) {
                     const int t = tb + __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const float f0 = (float)a0, f1 = (float)a1;
-                    nacc += a0 + a1;
-                    load2(mask ? tb + __ffs(mask) - 1 : -1, a0, a1);   // next non-empty tile
-                    float fm = fmaxf(f0, f1);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-                        fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, o));
-                    int ex;
-                    (void)frexpf(fm, &ex);               // 2^-ex fm in [0.5, 1)
-                    const float up = ldexpf(1.f, -ex);
                     const uint32_t s = g % M2_NB, u = g / M2_NB;
-                    mbar_wait(bars + M2_B_EMPTY + s, (u & 1u) ^ 1u);
-                    *reinterpret_cast<float2*>(r_s + s * MT + 2 * lane) =
-                        make_float2(f0 * up, f1 * up);
-                    __syncwarp();
+                    twait(bars + M2_B_EMPTY + s, (u & 1u) ^ 1u, pw[0]);
+                    ++p_tiles;
                     if (lane == 0) {
-                        pinv[s] = ldexpf(1.f, ex);
                         pent[s] = t;
-                        mbar_expect_tx(bars + M2_B_FULL + s, 2 * part_b);
-                        const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
-                                             3 * tile_elems(DP) + (size_t)(t & 1) * MT * DPB;
-                        unsigned char* dst = b_base + s * L.b_stage;
-                        bulk_g2s(dst, tile, part_b, bars + M2_B_FULL + s);
-                        bulk_g2s(dst + part_b, tile + tile_elems(DP), part_b,
-                                 bars + M2_B_FULL + s);
+                        if (dbg & 1024) {                 // no bulk copies
+                            mbar_arrive(bars + M2_B_FULL + s);
+                        } else {
+                            mbar_expect_tx(bars + M2_B_FULL + s, 2 * part_b + WSTRIDE * 4);
+                            const __half* tile = xt + (size_t)(t >> 1) * X_PARTS * tile_elems(DP) +
+                                                 3 * tile_elems(DP) + (size_t)(t & 1) * MT * DPB;
+                            unsigned char* dst = b_base + s * L.b_stage;
+                            bulk_g2s(dst, tile, part_b, bars + M2_B_FULL + s);
+                            bulk_g2s(dst + part_b, tile + tile_elems(DP), part_b,
+                                     bars + M2_B_FULL + s);
+                            bulk_g2s(r_s + s * WSTRIDE, wk + (size_t)t * WSTRIDE, WSTRIDE * 4,
+                                     bars + M2_B_FULL + s);
+                        }
                     }
                     __syncwarp();
                     ++g;
@@ -1153,13 +1258,8 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 __syncwarp();
                 ++g;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
-            if (lane == 0) {
-                npartial[(size_t)item * 2] = nacc;
-                npartial[(size_t)item * 2 + 1] = 0.0;
-            }
         }
+        report(0);
       } else if (warp == 1) {
         // ---------------- MMA issuer: A from TMEM, B K-major from shared memory -----------------
         const uint32_t idesc = make_idesc(128, G.N1);
@@ -1179,11 +1279,12 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 const uint32_t sb = g % M2_NB, ub = g / M2_NB;
                 const uint32_t sa = g & 1u, ua = g >> 1;
                 const uint32_t ts = f & 1u, tu = f >> 1;
-                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                twait(bars + M2_B_FULL + sb, ub & 1u, pw[0]);
                 const int tt = pent[sb];
-                const float tile_inv = pinv[sb];
-                mbar_wait(bars + M2_TM_EMPTY + ts, (tu & 1u) ^ 1u);
-                mbar_wait(bars + M2_A_FULL + sa, ua & 1u);
+                const float tile_inv = r_s[sb * WSTRIDE + MT];
+                twait(bars + M2_TM_EMPTY + ts, (tu & 1u) ^ 1u, pw[1]);
+                twait(bars + M2_A_FULL + sa, ua & 1u, pw[2]);
+                ++p_tiles;
                 tc_fence_after();
                 ++g;
                 if (tt < 0) {
@@ -1230,6 +1331,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 ++f;
             }
         }
+        report(1);
       } else if (corner) {
         // ---------------- corner warps 2, 3: features 128..143 x columns 128..151 -----------
         // mma.sync m16n8k16 from the K-major tiles: A rows = the 16 corner features (their own
@@ -1259,12 +1361,13 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
             for (;;) {
                 const uint32_t sb = g % M2_NB, ub = g / M2_NB;
                 const uint32_t sa = g & 1u, ua = g >> 1;
-                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                twait(bars + M2_B_FULL + sb, ub & 1u, pw[0]);
                 const int tt = pent[sb];
-                const float tile_inv = pinv[sb];
-                mbar_wait(bars + M2_A_FULL + sa, ua & 1u);
+                const float tile_inv = r_s[sb * WSTRIDE + MT];
+                twait(bars + M2_A_FULL + sa, ua & 1u, pw[1]);
+                ++p_tiles;
                 ++g;
-                if (tt >= 0) {
+                if (tt >= 0 && !(dbg & 2048)) {
                     const uint32_t ab = a_s0 + sa * 4096u + la, bb = b_s0 + sb * L.b_stage;
 #pragma unroll
                     for (int kq = 0; kq < MT / 32; ++kq) {
@@ -1326,6 +1429,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 }
             asm volatile("bar.sync 3, 64;" ::: "memory");
         }
+        if (warp == 2) report(2);
       }
     } else if (warp < 12) {
         reg_dec<88>();
@@ -1354,12 +1458,13 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
             for (;;) {
                 const uint32_t sb = g % M2_NB, ub = g / M2_NB;
                 const uint32_t sa = g & 1u, ua = g >> 1;
-                mbar_wait(bars + M2_B_FULL + sb, ub & 1u);
+                twait(bars + M2_B_FULL + sb, ub & 1u, pw[0]);
                 const int tt = pent[sb];
-                mbar_wait(bars + M2_A_EMPTY + sa, (ua & 1u) ^ 1u);
+                twait(bars + M2_A_EMPTY + sa, (ua & 1u) ^ 1u, pw[1]);
+                ++p_tiles;
                 tc_fence_after();
                 const unsigned char* bh = b_base + sb * L.b_stage;
-                const float* rt = r_s + sb * MT;
+                const float* rt = r_s + sb * WSTRIDE;
                 // 8 frames of one feature: z = r (x' - mu), split into fp16 hi / lo pairs
                 auto convert8 = [&](uint32_t off, int fg, float mu, bool live, uint32_t* zh,
                                     uint32_t* zl) {
@@ -1425,6 +1530,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 if (tt < 0) break;
             }
         }
+        if (warp == 4) report(3);
     } else {
         reg_inc<128>();
         // ---------------- epilogue (warps 12..19): TMEM -> fp32 registers -> partials -----------
@@ -1445,7 +1551,8 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
             for (;;) {
                 const uint32_t ts = f & 1u, tu = f >> 1;
-                mbar_wait(bars + M2_TM_FULL + ts, tu & 1u);
+                twait(bars + M2_TM_FULL + ts, tu & 1u, pw[0]);
+                ++p_tiles;
                 tc_fence_after();
                 const int fl = gflag[ts];         // bit 0: the group holds data, bit 1: last group
                 const bool empty = (fl & 1) == 0;
@@ -1491,6 +1598,7 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                     out[(size_t)128 * G.N1 + (size_t)row * G.N2 + half * 16 + j] = 0.f;
             }
         }
+        if (warp == 12) report(4);
     }
     tc_fence_before();
     __syncthreads();
@@ -1498,10 +1606,10 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// Fixed-order sum of the per-chunk partials: raw[k][e], e < partial_len, then n_k at [partial_len].
+// Fixed-order sum of the per-chunk partials: raw[k][e], e < partial_len (n_k, at [partial_len],
+// comes from mstats_tc_nk_kernel).
 __global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
                                         const float* __restrict__ partial,
-                                        const double* __restrict__ npartial,
                                         double* __restrict__ raw) {
     const int k = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1509,11 +1617,6 @@ __global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
         double t = 0.0;
         for (int c = 0; c < n_chunks; ++c)
             t += (double)partial[((size_t)c * K + k) * partial_len + e];
-        raw[(size_t)k * (partial_len + 1) + e] = t;
-    } else if (e == partial_len) {
-        double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c)
-            t += npartial[((size_t)c * K + k) * 2] + npartial[((size_t)c * K + k) * 2 + 1];
         raw[(size_t)k * (partial_len + 1) + e] = t;
     }
 }
@@ -1573,6 +1676,14 @@ __global__ void mstats_tc_post_kernel(int K, int D, int DP, const double* __rest
 
 constexpr int TC_STAT_CHUNKS = 1184;
 
+// A 64-frame tile enters the tensor-core M-step for a component only if one of its weights
+// exceeds this.  What is left out is bounded by floor x (frames in such tiles) per component; on
+// the bench workload 28 % of the (component, tile) pairs with any weight above 1e-16 lie below
+// 1e-8 and together hold 3.5e-5 frames of weight over all 64 components (n_k ~ 2750 each) -- the
+// statistics move by 1.6e-13 of their largest entry, six orders below the rounding of the
+// split-fp16 contraction itself (tools/time_mstep_real.py).  The FP64 path keeps 1e-16 per frame.
+constexpr float TC_TILE_FLOOR = 1e-8f;
+
 struct TcWorkspace {
     double* colpartial;
     double* xinfo;
@@ -1584,7 +1695,10 @@ struct TcWorkspace {
     int32_t* cand;
     float* mu32;
     float* mpartial;
-    double* npartial;
+    int* item_count;       // tiles with weight per M-step work item
+    int* item_order;       // work items, most tiles first
+    float* wts;            // per (component, tile): scaled weights + inverse scale (M-step)
+    double* tsum;          // per (component, tile): weight of the tile
     int* item_counter;
     unsigned char* tflags;
     double* mraw;
@@ -1638,8 +1752,11 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.cand = c.take<int32_t>((size_t)N);
     w.mu32 = c.take<float>((size_t)K * G.DA);
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
-    w.npartial = c.take<double>(2 * (size_t)w.m_chunks * K);
+    w.wts = c.take<float>((size_t)K * (size_t)((w.n_mtiles + 3) / 4 * 4) * tc::WSTRIDE);
+    w.tsum = c.take<double>((size_t)K * (size_t)((w.n_mtiles + 3) / 4 * 4));
     w.item_counter = c.take<int>(4);
+    w.item_count = c.take<int>((size_t)K * w.m_chunks);
+    w.item_order = c.take<int>((size_t)K * w.m_chunks);
     w.tflags = c.take<unsigned char>((size_t)K * (size_t)((w.n_mtiles + 3) / 4 * 4));
     w.mraw = c.take<double>((size_t)K * (G.partial_len + 1));
     w.bytes = align_up(c.used, 256);
@@ -1762,11 +1879,17 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
     KW_CUDA_CHECK(cudaMemsetAsync(w.item_counter, 0, sizeof(int), st));
+    KW_CUDA_CHECK(cudaMemsetAsync(w.item_count, 0, sizeof(int) * (size_t)items, st));
     const int n_mt_pad = (w.n_mtiles + 3) / 4 * 4;
+    const char* floor_env = getenv("KW_TC_TILE_FLOOR");      // experiments only
+    const float tile_floor = floor_env != nullptr ? (float)atof(floor_env) : TC_TILE_FLOOR;
     {
         const long long warps = (long long)K * (n_mt_pad / 4);
-        tc::mstats_tc_flags_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-            N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags);
+        tc::mstats_tc_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+            N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags, w.wts, w.tsum, tile_floor,
+            w.tiles_per_chunk, w.item_count);
+        KW_CUDA_CHECK(cudaGetLastError());
+        tc::mstats_tc_order_kernel<<<1, 1024, 0, st>>>(items, w.item_count, w.item_order);
         KW_CUDA_CHECK(cudaGetLastError());
     }
     // timing experiments only (tools/time_mstep.py): bits that switch parts of the kernel off
@@ -1777,11 +1900,24 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)L2.total));
     tc::mstats_tc2_kernel<<<grid, 640, L2.total, st>>>(
-        N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, resp, w.mu32,
-        w.mpartial, w.npartial, w.item_counter, w.tflags, n_mt_pad, dbg);
+        N, resp_pad(N), w.n_mtiles, w.tiles_per_chunk, w.m_chunks, K, DP, w.xt, w.wts, w.mu32,
+        w.mpartial, w.item_counter, w.item_order, w.tflags, n_mt_pad, dbg);
     KW_CUDA_CHECK(cudaGetLastError());
+    if (dbg & 16384) {
+        unsigned long long h[40];
+        KW_CUDA_CHECK(cudaStreamSynchronize(st));
+        KW_CUDA_CHECK(cudaMemcpyFromSymbol(h, tc::m2_prof, sizeof(h)));
+        const char* role[5] = {"producer  [B_EMPTY]", "mma       [B_FULL, TM_EMPTY, A_FULL]",
+                               "corner    [B_FULL, A_FULL]", "generator [B_FULL, A_EMPTY]",
+                               "epilogue  [TM_FULL]"};
+        for (int r = 0; r < 5; ++r)
+            fprintf(stderr, "[mstats_tc2 cta0] %-38s total %9llu clk, %5llu tiles, waits %9llu %9llu %9llu\n",
+                    role[r], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
+    }
     tc::mstats_tc_reduce_kernel<<<dim3((G.partial_len + 256) / 256, K), 256, 0, st>>>(
-        K, G.partial_len, w.m_chunks, w.mpartial, w.npartial, w.mraw);
+        K, G.partial_len, w.m_chunks, w.mpartial, w.mraw);
+    KW_CUDA_CHECK(cudaGetLastError());
+    tc::mstats_tc_nk_kernel<<<K, 256, 0, st>>>(n_mt_pad, G.partial_len, w.tsum, w.mraw);
     KW_CUDA_CHECK(cudaGetLastError());
     tc::mstats_tc_post_kernel<<<dim3(K, 8), 256, 0, st>>>(K, D, DP, w.mraw, w.xinfo, w.mu32,
                                                           centres, stats, 1.0 + 0.65 / 8388608.0);
