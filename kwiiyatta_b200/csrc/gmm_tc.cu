@@ -410,25 +410,46 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
 // A g1, ...), so one MMA of N = G (DP - 16 ks) computes the k-step for all of them and output
 // j of component c lands in accumulator column 8 G (j / 8) + 8 c + j % 8 whatever the k-step.
 // grid = G * ceil(K / G); components >= K are zero blocks.
-__global__ void pack_l_kernel(int K, int D, int DP, int G, const double* __restrict__ means,
-                              const double* __restrict__ prec_chol, const double* __restrict__ aux,
-                              const double* __restrict__ xinfo, __half* __restrict__ bt,
-                              double* __restrict__ cst) {
-    extern __shared__ double bpv[];      // DP: b'_j
+// grid (components, PACK_L_SLICES): every slice derives the component's scale (b' and the largest
+// entry: one column per thread, loads eight rows at a time), then stores its share of the
+// elements, threads running along a row of L so the reads coalesce.  (One CTA per component with
+// one load in flight per thread took 78 us of pure memory latency on 64 SMs.)
+constexpr int PACK_L_SLICES = 4;
+__global__ void __launch_bounds__(256)
+pack_l_kernel(int K, int D, int DP, int G, const double* __restrict__ means,
+              const double* __restrict__ prec_chol, const double* __restrict__ aux,
+              const double* __restrict__ xinfo, __half* __restrict__ bt,
+              double* __restrict__ cst) {
+    extern __shared__ double bpv[];      // DP: b'_j, then DP: column scales s_d, DP: mu_d - x0_d
     __shared__ double red[256];
+    double* sd = bpv + DP;
+    double* md = sd + DP;
     const int k = blockIdx.x;
     const int item = k / G, ci = k - item * G;
     const bool real = k < K;
     const double* L = prec_chol + (size_t)(real ? k : 0) * D * D;
     const double* mu = means + (size_t)(real ? k : 0) * D;
+    for (int d = threadIdx.x; d < DP; d += blockDim.x) {
+        sd[d] = d < D ? xinfo[DP + d] : 0.0;
+        md[d] = d < D ? mu[d] - xinfo[d] : 0.0;
+    }
+    __syncthreads();
     double amax = 0.0;
     for (int j = threadIdx.x; j < DP; j += blockDim.x) {
         double bp = 0.0;
         if (j < D && real) {
-            for (int d = 0; d <= j; ++d) {
-                const double l = L[(size_t)d * D + j];
-                amax = fmax(amax, fabs(l * xinfo[DP + d]));
-                bp = fma(mu[d] - xinfo[d], l, bp);
+            for (int d0 = 0; d0 <= j; d0 += 8) {
+                double l[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) l[q] = L[(size_t)min(d0 + q, j) * D + j];   // (clamped: unconditional loads)
+                asm volatile("" ::: "memory");      // keep the eight loads together, ahead of their uses
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (d0 + q <= j) {
+                        amax = fmax(amax, fabs(l[q] * sd[d0 + q]));
+                        bp = fma(md[d0 + q], l[q], bp);
+                    }
+                }
             }
         }
         bpv[j] = bp;
@@ -448,30 +469,47 @@ __global__ void pack_l_kernel(int K, int D, int DP, int G, const double* __restr
         scale = ldexp(1.0, e);
     }
     const double inv = 1.0 / scale;
-    if (threadIdx.x == 0 && real) {
+    if (threadIdx.x == 0 && real && blockIdx.y == 0) {
         cst[3 * k] = aux[(size_t)k * (D + 2) + D];
         cst[3 * k + 1] = aux[(size_t)k * (D + 2) + D + 1];
         cst[3 * k + 2] = scale * scale;
     }
     __half* hi = bt + (size_t)item * 2 * G * bmat_elems(DP);
     __half* lo = hi + (size_t)G * bmat_elems(DP);
-    for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
-        const int j = e / DP, d = e - j * DP;
-        const int ks = d >> 4, jg = j >> 3;
-        if (jg < 2 * ks) continue;             // structurally zero block: not stored
-        double v = 0.0;
-        if (real && j < D && d <= j) v = L[(size_t)d * D + j] * xinfo[DP + d] * inv;
-        const size_t o = (size_t)G * btri_off(DP, ks) +
-                         ((size_t)(G * (jg - 2 * ks) + ci) * 2 + ((d >> 3) & 1)) * 64 +
-                         (j & 7) * 8 + (d & 7);
-        split_store(v, hi + o, lo + o);
+    // element (d, j) = L[d][j] s_d / scale, rows d of this slice, j fastest across the threads
+    const int rows = (DP + PACK_L_SLICES - 1) / PACK_L_SLICES;
+    const int d_lo = blockIdx.y * rows, d_hi = min(DP, d_lo + rows);
+    for (int e0 = d_lo * DP; e0 < d_hi * DP; e0 += 4 * blockDim.x) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + q * blockDim.x + threadIdx.x;
+            const int d = e / DP, j = e - d * DP;
+            v[q] = (e < d_hi * DP && real && j < D && d <= j) ? L[(size_t)d * D + j] : 0.0;
+        }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + q * blockDim.x + threadIdx.x;
+            if (e >= d_hi * DP) continue;
+            const int d = e / DP, j = e - d * DP;
+            const int ks = d >> 4, jg = j >> 3;
+            if (jg < 2 * ks) continue;             // structurally zero block: not stored
+            const size_t o = (size_t)G * btri_off(DP, ks) +
+                             ((size_t)(G * (jg - 2 * ks) + ci) * 2 + ((d >> 3) & 1)) * 64 +
+                             (j & 7) * 8 + (d & 7);
+            split_store(v[q] * sd[d] * inv, hi + o, lo + o);
+        }
     }
-    for (int e = threadIdx.x; e < DP * 16; e += blockDim.x) {
-        const int j = e >> 4, dd = e & 15, jg = j >> 3;
-        const double v = (dd == 0 && real) ? -bpv[j] * inv : 0.0;
-        const size_t o = (size_t)G * bbias_off(DP) +
-                         ((size_t)(G * jg + ci) * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 + (dd & 7);
-        split_store(v, hi + o, lo + o);
+    if (blockIdx.y == 0) {
+        for (int e = threadIdx.x; e < DP * 16; e += blockDim.x) {
+            const int j = e >> 4, dd = e & 15, jg = j >> 3;
+            const double v = (dd == 0 && real) ? -bpv[j] * inv : 0.0;
+            const size_t o = (size_t)G * bbias_off(DP) +
+                             ((size_t)(G * jg + ci) * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 +
+                             (dd & 7);
+            split_store(v, hi + o, lo + o);
+        }
     }
 }
 
@@ -818,31 +856,50 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// Responsibilities from the weighted log-probabilities (component-major), one thread per frame;
-// mode 1: hard argmax (first maximum) instead.
-__global__ void lse_kernel(long long N, long long Npad, int K, double* __restrict__ respT,
-                           double* __restrict__ lse_partial, int mode, int32_t* __restrict__ mix) {
+// Responsibilities from the weighted log-probabilities (component-major), one thread per frame:
+// the frame's log-likelihood from one pass (running maximum and rescaled sum; terms more than 46
+// below the maximum cannot change a double-precision sum and skip their exp), then
+// r = exp(wlp - lse) in place.  A thread walks K values a whole row pitch apart, so the loads are
+// issued eight at a time -- with one in flight per thread the kernel was bound by memory latency
+// (81 us for 90 MB), not by bandwidth.
+__global__ void __launch_bounds__(128)
+lse_kernel(long long N, long long Npad, int K, double* __restrict__ respT,
+           double* __restrict__ lse_partial) {
     __shared__ double sh[128];
     const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
     double lse = 0.0;
     if (n < N) {
         double* col = respT + n;
-        double mx = -CUDART_INF;
-        int arg = 0;
-        for (int k = 0; k < K; ++k) {
-            const double v = col[(size_t)k * Npad];
-            if (v > mx) { mx = v; arg = k; }
+        double mx = -CUDART_INF, sum = 0.0;
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (k0 + j < K) ? col[(size_t)(k0 + j) * Npad] : -CUDART_INF;
+            asm volatile("" ::: "memory");          // eight loads in flight before the first use
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double dlt = v[j] - mx;
+                if (dlt > 0.0) {
+                    sum = (dlt < 46.0 ? sum * exp(-dlt) : 0.0) + 1.0;
+                    mx = v[j];
+                } else if (dlt > -46.0) {
+                    sum += exp(dlt);
+                }
+            }
         }
-        if (mode == 1) {
-            mix[n] = arg;
-        } else {
-            double s = 0.0;
-            for (int k = 0; k < K; ++k) s += exp(col[(size_t)k * Npad] - mx);
-            lse = log(s) + mx;
-            for (int k = 0; k < K; ++k) col[(size_t)k * Npad] = exp(col[(size_t)k * Npad] - lse);
+        lse = log(sum) + mx;
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (k0 + j < K) ? col[(size_t)(k0 + j) * Npad] : 0.0;
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (k0 + j < K) col[(size_t)(k0 + j) * Npad] = exp(v[j] - lse);
         }
     }
-    if (mode == 1) return;
     sh[threadIdx.x] = lse;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1022,12 +1079,29 @@ mstats_tc_order_kernel(int n_items, const int* __restrict__ item_count, int* __r
     __syncthreads();
     for (int i = threadIdx.x; i < n_items; i += 1024) atomicAdd(hist + min(item_count[i], 1023), 1);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int b = 1023; b >= 0; --b) {
-            base[b] = run;
-            run += hist[b];
+    {   // base[b] = number of items in bins above b: exclusive scan over descending bins
+        __shared__ int wsum[32];
+        const int b = 1023 - (int)threadIdx.x, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+        const int h = hist[b];
+        int inc = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
+        if (lane == 31) wsum[wi] = inc;
+        __syncthreads();
+        if (wi == 0) {
+            int t = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            wsum[lane] = t;
+        }
+        __syncthreads();
+        base[b] = inc - h + (wi > 0 ? wsum[wi - 1] : 0);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_items; i += 1024)
@@ -1815,7 +1889,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     // two components per MMA when both accumulators fit N <= 256 and TMEM (DP <= 96)
     const int G = (DP <= 96 && K >= 2) ? 2 : 1;
     const int KI = (K + G - 1) / G;
-    tc::pack_l_kernel<<<KI * G, 256, sizeof(double) * DP, st>>>(K, D, DP, G, means, pc, aux,
+    tc::pack_l_kernel<<<dim3(KI * G, tc::PACK_L_SLICES), 256, 3 * sizeof(double) * DP, st>>>(K, D, DP, G, means, pc, aux,
                                                                 w.xinfo, w.bt, w.cst);
     KW_CUDA_CHECK(cudaGetLastError());
     const int sms = device_sms();
@@ -1859,7 +1933,7 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
         return KW_OK;
     }
     const unsigned lgrid = (unsigned)((N + 127) / 128);
-    tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial, mode, mix);
+    tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial);
     KW_CUDA_CHECK(cudaGetLastError());
     launch_reduce_fixed(w.lse_partial, (long long)lgrid, (double)N, lse_out, st);
     KW_CUDA_CHECK(cudaGetLastError());
