@@ -1542,6 +1542,11 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                 // 8 frames of one feature: z = r (x' - mu), split into fp16 hi / lo pairs
                 auto convert8 = [&](uint32_t off, int fg, float mu, bool live, uint32_t* zh,
                                     uint32_t* zl) {
+                    if (!live) {               // feature rows past DP (small D only)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) zh[e] = zl[e] = 0u;
+                        return;
+                    }
                     const uint4 hv = *reinterpret_cast<const uint4*>(bh + off);
                     const uint4 lv = *reinterpret_cast<const uint4*>(bh + part_b + off);
                     const float4 ra = *reinterpret_cast<const float4*>(rt + fg * 8);
@@ -1552,20 +1557,13 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
-                        float z0 = rr8[2 * e] * ((xh.x + xl.x) - mu);
-                        float z1 = rr8[2 * e + 1] * ((xh.y + xl.y) - mu);
-                        if (!live) { z0 = 0.f; z1 = 0.f; }
+                        const float z0 = rr8[2 * e] * ((xh.x + xl.x) - mu);
+                        const float z1 = rr8[2 * e + 1] * ((xh.y + xl.y) - mu);
                         const __half2 zh2 = __floats2half2_rn(z0, z1);
                         const float2 zf = __half22float2(zh2);
                         const __half2 zl2 = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
                         zh[e] = *reinterpret_cast<const uint32_t*>(&zh2);
                         zl[e] = *reinterpret_cast<const uint32_t*>(&zl2);
-                        if (dbg & 256) zl[e] = 0u;
-                        if (dbg & 512) {          // lo scaled by 2^11: no fp16 subnormals
-                            const __half2 zs = __floats2half2_rn((z0 - zf.x) * 2048.f,
-                                                                 (z1 - zf.y) * 2048.f);
-                            zl[e] = *reinterpret_cast<const uint32_t*>(&zs);
-                        }
                     }
                 };
                 if (tt >= 0 && !(dbg & 2)) {
