@@ -1510,16 +1510,20 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
         // ---------------- generators (warps 4..11): A = r (x' - mu') -> TMEM ------------------
         // Thread = feature row i = 32 q + lane of its TMEM lane quarter q = warp % 4; warps 4..7
         // take frame groups 0..3 (k-steps 0, 1), warps 8..11 frame groups 4..7 (k-steps 2, 3).
-        // Threads of warps 4..7 also convert one (corner feature, frame group) unit each.
+        // Every thread also converts half a (corner feature, frame group) unit (D > 128).
         const int q = warp & 3, h = (warp - 4) >> 2;
         const int i = 32 * q + lane;
         const bool valid = i < DP;
         const int gt = threadIdx.x - 128;            // 0..255
-        const int cf = gt & 15, cfg = (gt >> 4) & 7; // corner unit: feature 128 + cf, frame group cfg
-        const bool on_c = corner && gt < 128;
+        // corner unit = (feature 128 + cf, frame group cfg), half a unit (4 frames) per thread so
+        // that all eight warps carry the same load
+        const int cf = (gt >> 1) & 15, cfg = (gt >> 5) & 7, chalf = gt & 1;
+        const bool on_c = corner;
         const uint32_t row_off = (uint32_t)i * 128u, row_x = (uint32_t)(i & 7);
-        const uint32_t c_src = (uint32_t)(128 + cf) * 128u + (((uint32_t)cfg ^ (uint32_t)(cf & 7)) << 4);
-        const uint32_t c_dst = ((uint32_t)(cf >> 3) * 8u + (uint32_t)cfg) * 128u + (uint32_t)(cf & 7) * 16u;
+        const uint32_t c_src = (uint32_t)(128 + cf) * 128u +
+                               (((uint32_t)cfg ^ (uint32_t)(cf & 7)) << 4) + 8u * (uint32_t)chalf;
+        const uint32_t c_dst = ((uint32_t)(cf >> 3) * 8u + (uint32_t)cfg) * 128u +
+                               (uint32_t)(cf & 7) * 16u + 8u * (uint32_t)chalf;
         const uint32_t t_lane = tmem_base + (((uint32_t)q * 32u) << 16) + a_col0;
         uint32_t g = 0;
         for (uint32_t it_idx = 0;; ++it_idx) {
@@ -1583,11 +1587,28 @@ mstats_tc2_kernel(long long N, long long Npad, int n_mtiles, int tiles_per_chunk
                         }
                     }
                     if (on_c) {
-                        uint32_t zh[4], zl[4];
-                        convert8(c_src, cfg, mu_c, true, zh, zl);
+                        // 4 frames of a corner feature
+                        const uint2 hv = *reinterpret_cast<const uint2*>(bh + c_src);
+                        const uint2 lv = *reinterpret_cast<const uint2*>(bh + part_b + c_src);
+                        const float4 ra = *reinterpret_cast<const float4*>(rt + cfg * 8 + chalf * 4);
+                        const float rr4[4] = {ra.x, ra.y, ra.z, ra.w};
+                        const __half2* hp = reinterpret_cast<const __half2*>(&hv);
+                        const __half2* lp = reinterpret_cast<const __half2*>(&lv);
+                        uint32_t zh[2], zl[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float2 xh = __half22float2(hp[e]), xl = __half22float2(lp[e]);
+                            const float z0 = rr4[2 * e] * ((xh.x + xl.x) - mu_c);
+                            const float z1 = rr4[2 * e + 1] * ((xh.y + xl.y) - mu_c);
+                            const __half2 zh2 = __floats2half2_rn(z0, z1);
+                            const float2 zf = __half22float2(zh2);
+                            const __half2 zl2 = __floats2half2_rn(z0 - zf.x, z1 - zf.y);
+                            zh[e] = *reinterpret_cast<const uint32_t*>(&zh2);
+                            zl[e] = *reinterpret_cast<const uint32_t*>(&zl2);
+                        }
                         unsigned char* dst = ac_base + sa * 4096u + c_dst;
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
-                        *reinterpret_cast<uint4*>(dst + 2048u) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(zh[0], zh[1]);
+                        *reinterpret_cast<uint2*>(dst + 2048u) = make_uint2(zl[0], zl[1]);
                     }
                     if (!(dbg & 8)) tmem_st_wait();
                 }
