@@ -527,14 +527,14 @@ def run_b200(args):
             'note': f'B200GMMFeatureConverter._train on a pinned host (N,144) array, '
                     f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model',
         },
-        'gpu_launches': (10 if tc else 6) * K,
+        'gpu_launches': (12 if tc else 6) * K,
         'roofline': {
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': dom_tflops / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel
-            # in the ncu --set full capture of this workload (profiles/ncu_r2_mstats_tc2.txt,
-            # profiles/ncu_r2_estep_tc.txt); algorithmic: packed X 113 MB + resp 90 MB
-            'traffic': ({'mstats_tc2_kernel': 159.3e6 + 68.6e6, 'estep_tc_kernel': 116.5e6 + 55.4e6}
+            # in the ncu --set full capture of this workload (profiles/ncu_r2c_mstats_tc2.txt,
+            # profiles/ncu_r2c_estep_tc.txt); algorithmic: packed X 113 MB + prepared weights
+            'traffic': ({'mstats_tc2_kernel': 295.2e6 + 60.9e6, 'estep_tc_kernel': 116.5e6 + 55.3e6}
                         .get(dominant) if n_frames == 176323 else None),
             'traffic_unit': 'bytes per launch (ncu, 1 GPU)',
             'peak_source': f"{peaks['source']} bf16_tflops_sustained",

@@ -159,7 +159,8 @@ int kw_gmm_mstep_finalize(int n_components, int dim, double reg_covar, int weigh
 /* Exchange form of the statistics for the all-reduce between ranks: the second-moment blocks are
  * symmetric, so [n_k, first moments, upper triangle] per component plus the two tail scalars carry
  * everything -- K (1 + D + D (D + 1) / 2) + 2 doubles, about half of kw_gmm_stats_len.  Pack, sum
- * the packed vectors over the ranks, unpack (the lower triangle is mirrored). */
+ * the packed vectors over the ranks, unpack (the lower triangle is mirrored).  Optional: worth it
+ * where the link bandwidth bounds the all-reduce; over NVLink the full vector is as fast. */
 size_t kw_gmm_stats_packed_len(int n_components, int dim);
 int kw_gmm_stats_pack(int n_components, int dim, const double* stats_dev, double* packed_dev,
                       void* stream);

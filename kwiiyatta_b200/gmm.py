@@ -176,11 +176,16 @@ class GaussianMixture:
             _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_mstep_accumulate')
 
+    # all-reduce the triangle-packed statistics instead of the full vector (see
+    # dist.allreduce_stats: slower over NVLink, for bandwidth-limited links)
+    exchange_form = False
+
     def _allreduce(self, torch):
         """The path's one exchange: sum of the statistics vector over the ranks."""
         from . import dist as kdist
         k, d = self._means[self._cur].shape
-        kdist.allreduce_stats(self._stats, self.process_group, n_components=k, dim=d)
+        kdist.allreduce_stats(self._stats, self.process_group, n_components=k, dim=d,
+                              exchange_form=self.exchange_form)
 
     def _finalize(self, torch, centres, weight_norm):
         k, d = centres.shape

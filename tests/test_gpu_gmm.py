@@ -173,3 +173,40 @@ def test_statistics_exchange_form_round_trip(cuda):
         _lib.check(lib.kw_gmm_stats_unpack(k, d, packed.data_ptr(), back.data_ptr(), stream),
                    'unpack')
         assert np.array_equal(back.cpu().numpy(), stats)
+
+
+def test_tensor_core_mstep_tile_floor(cuda):
+    """The tensor-core M-step leaves out, per component, the 64-frame tiles in which every
+    responsibility is <= 1e-8 (include/kwiiyatta_b200.h, kw_gmm_mstep_accumulate).  What that
+    drops is bounded by floor x frames: the statistics stay within the split-fp16 budget of the
+    FP64 kernel's, and a component that only has such weights gets exactly zero."""
+    import torch
+    import kwiiyatta_b200 as kw
+    rng = np.random.default_rng(11)
+    n, d, k = 64 * 300 + 17, 40, 4
+    x = rng.standard_normal((n, d))
+    resp = np.zeros((n, k))
+    resp[:, 0] = rng.uniform(0.2, 0.9, n)
+    resp[:, 1] = 1.0 - resp[:, 0]
+    resp[: 64 * 100, 1] = 5e-9                   # whole tiles below the floor: dropped
+    resp[64 * 100: 64 * 200: 64, 1] = 3e-3       # tiles with one frame above it: kept whole
+    resp[64 * 100 + 1: 64 * 200: 64, 1] = 5e-9
+    resp[:, 2] = 4e-9                            # never above the floor
+    resp[:, 3] = 1e-30
+    stats = {}
+    for prec in ('tc', 'fp64'):
+        gm = kw.GaussianMixture(n_components=k, max_iter=1, tol=0.0, resp_init=resp.copy(),
+                                precision=prec, reorder_every=0)
+        xd = gm.initialize(x)
+        centres = torch.zeros((k, d), dtype=torch.float64, device=xd.device)
+        gm._resp[:, :n].copy_(torch.from_numpy(resp.T.copy()).to(xd.device))
+        gm._stats.zero_()
+        gm._accumulate(torch, xd, centres)
+        stats[prec] = gm._stats[:-2].view(k, 1 + d + d * d).cpu().numpy()
+    tc, ref = stats['tc'], stats['fp64']
+    assert np.all(tc[2:] == 0.0)                                 # only sub-floor weights
+    dropped = 5e-9 * 64 * 100
+    assert 0.0 <= ref[1, 0] - tc[1, 0] <= dropped * (1 + 1e-6) + 1e-7 * ref[1, 0]
+    assert abs(tc[0, 0] - ref[0, 0]) <= 1e-7 * ref[0, 0]
+    scale = np.abs(ref[:2]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(tc[:2] - ref[:2]) <= 2e-6 * scale)

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, x, resp0, precision, out):
+def _worker(rank, world, port, x, resp0, precision, out, exchange_form=False):
     import torch
     import torch.distributed as dist
     from kwiiyatta_b200.gmm import GaussianMixture
@@ -32,14 +32,17 @@ def _worker(rank, world, port, x, resp0, precision, out):
         warnings.simplefilter('ignore')
         gm = GaussianMixture(n_components=resp0.shape[1], max_iter=5, tol=0.0,
                              resp_init=resp0[lo:hi], precision=precision,
-                             device=torch.device('cuda', rank)).fit(x[lo:hi])
+                             device=torch.device('cuda', rank))
+        gm.exchange_form = exchange_form
+        gm.fit(x[lo:hi])
     out.put((rank, gm.weights_, gm.means_, gm.covariances_, gm.lower_bounds_))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('precision', ['fp64', 'tc'])
-def test_two_rank_fit_equals_single(cuda, precision):
+@pytest.mark.parametrize('precision,exchange_form', [('fp64', False), ('tc', False),
+                                                     ('fp64', True)])
+def test_two_rank_fit_equals_single(cuda, precision, exchange_form):
     if cuda.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -56,7 +59,7 @@ def test_two_rank_fit_equals_single(cuda, precision):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, x, resp0, precision, q))
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, x, resp0, precision, q, exchange_form))
              for r in range(2)]
     for p in procs:
         p.start()
