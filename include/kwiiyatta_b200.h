@@ -123,11 +123,22 @@ int kw_gmm_pack_frames(int64_t n_frames, const double* x_dev, int n_components, 
                        int precision, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* E-step: resp_dev (kw_gmm_resp_len doubles, component-major) responsibilities, sum of log p(x) accumulated into
- * stats[K*(1+D+D*D)] and n_frames into the next slot. */
+ * stats[K*(1+D+D*D)] and n_frames into the next slot.
+ * resp_form: 0 = resp_dev receives the responsibilities r_nk.  1 (precision 1 only; ignored with
+ * precision 0) = the form an EM iteration wants: resp_dev keeps the weighted log-probabilities
+ * log(w_k N(x_n | k)), and what the tensor-core M-step consumes (per component and 64-frame tile:
+ * has-weight flag, fp32 weights, tile weight) goes straight to the workspace -- the K x N matrix
+ * of responsibilities is never written or re-read.  Follow with kw_gmm_mstep_accumulate(precision 1,
+ * resp_form 1) on the same workspace, or turn resp_dev into responsibilities in place with
+ * kw_gmm_normalize_resp. */
 int kw_gmm_estep(int64_t n_frames, const double* x_dev, int n_components, int dim,
                  const double* means_dev, const double* prec_chol_dev, const double* aux_dev,
-                 double* resp_dev, double* stats_dev, int precision,
+                 double* resp_dev, double* stats_dev, int precision, int resp_form,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* resp_dev as left by kw_gmm_estep(precision 1, resp_form 1) -> responsibilities, in place. */
+int kw_gmm_normalize_resp(int64_t n_frames, int n_components, int dim, double* resp_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Hard assignment argmax_k of the weighted log-probability (sklearn predict; with identity
  * precisions and equal weights this is the k-means assignment step).  labels_dev[n_frames] int32.
@@ -141,10 +152,13 @@ int kw_gmm_hard_labels(int64_t n_frames, const double* x_dev, int n_components, 
  * matter is skipped, so the cost follows the sparsity of the posterior: precision 0 drops frames
  * with r_nk <= 1e-16 (below the rounding of n_k); precision 1 drops, per component, the 64-frame
  * tiles in which every r_nk <= 1e-8 (orders below the rounding of its split-fp16 contraction).
- * The summation order is fixed (bitwise reproducible). */
+ * The summation order is fixed (bitwise reproducible).
+ * resp_form: 0 = resp_dev holds responsibilities; 1 = use what kw_gmm_estep(precision 1,
+ * resp_form 1) left in this workspace, resp_dev is not read (precision 1 only,
+ * KW_ERR_UNSUPPORTED with precision 0). */
 int kw_gmm_mstep_accumulate(int64_t n_frames, const double* x_dev, int n_components, int dim,
                             const double* resp_dev, const double* centres_dev,
-                            double* stats_dev, int precision,
+                            double* stats_dev, int precision, int resp_form,
                             void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Parameters from (all-reduced) statistics.  weight_norm: 0 -> n_k / sum_k n_k (M-step),

@@ -30,9 +30,10 @@ SIGNATURES = {
     'kw_gmm_resp_len': (_sz, [_i64, _i]),
     'kw_gmm_workspace_bytes': (_sz, [_i64, _i, _i, _i]),
     'kw_gmm_pack_frames': (_i, [_i64, _vp, _i, _i, _i, _vp, _sz, _vp]),
-    'kw_gmm_estep': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    'kw_gmm_estep': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    'kw_gmm_normalize_resp': (_i, [_i64, _i, _i, _vp, _vp, _sz, _vp]),
     'kw_gmm_hard_labels': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
-    'kw_gmm_mstep_accumulate': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    'kw_gmm_mstep_accumulate': (_i, [_i64, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     'kw_gmm_stats_packed_len': (_sz, [_i, _i]),
     'kw_gmm_stats_pack': (_i, [_i, _i, _vp, _vp, _vp]),
     'kw_gmm_stats_unpack': (_i, [_i, _i, _vp, _vp, _vp]),

@@ -61,10 +61,13 @@ size_t tc_workspace_bytes(long long N, int K, int D);
 int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
                    size_t workspace_bytes, cudaStream_t st, bool mstep_parts = true);
 int mstats_tc(long long N, const double* X, int K, int D, const double* resp, const double* centres,
-              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st);
+              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st,
+              int resp_form = 0);
+int normalize_resp_tc(long long N, int K, int D, double* resp, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st);
 int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
              const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
-             void* workspace, size_t workspace_bytes, cudaStream_t st);
+             void* workspace, size_t workspace_bytes, cudaStream_t st, int resp_form = 0);
 int mstats_fp64(long long N, const double* X, int K, int D, const double* resp,
                 const double* centres, double* partial, double* stats, double resp_floor,
                 cudaStream_t st);

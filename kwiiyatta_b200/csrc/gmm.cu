@@ -772,11 +772,12 @@ extern "C" size_t kw_gmm_workspace_bytes(int64_t n_frames, int K, int D, int pre
 
 extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const double* means_dev,
                             const double* prec_chol_dev, const double* aux_dev, double* resp_dev,
-                            double* stats_dev, int precision, void* workspace_dev,
-                            size_t workspace_bytes, void* stream) {
+                            double* stats_dev, int precision, int resp_form,
+                            void* workspace_dev, size_t workspace_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_estep: N, K, D must be positive");
     KW_REQUIRE(precision == 0 || precision == 1, "GMM precision must be 0 (fp64) or 1 (tensor)");
+    KW_REQUIRE(resp_form == 0 || resp_form == 1, "resp_form must be 0 or 1");
     GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
     if (w.bytes > workspace_bytes) {
         set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
@@ -786,7 +787,7 @@ extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const 
     if (precision == 1) {
         return estep_tc(N, x_dev, K, D, means_dev, prec_chol_dev, aux_dev, resp_dev, tail, 0,
                         nullptr, static_cast<char*>(workspace_dev) + w.bytes,
-                        workspace_bytes - w.bytes, st);
+                        workspace_bytes - w.bytes, st, resp_form);
     }
     int rc = estep_fp64(N, x_dev, K, D, prec_chol_dev, aux_dev, resp_dev, w.lse_partial, 0,
                         nullptr, st);
@@ -795,6 +796,19 @@ extern "C" int kw_gmm_estep(int64_t N, const double* x_dev, int K, int D, const 
     launch_reduce_fixed(w.lse_partial, nblk, (double)N, tail, st);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
+}
+
+extern "C" int kw_gmm_normalize_resp(int64_t N, int K, int D, double* resp_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_normalize_resp: N, K, D must be positive");
+    GmmWorkspace w = carve_gmm(N, K, D, workspace_dev);
+    if (w.bytes > workspace_bytes) {
+        set_error("GMM workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return KW_ERR_WORKSPACE;
+    }
+    return normalize_resp_tc(N, K, D, resp_dev, static_cast<char*>(workspace_dev) + w.bytes,
+                             workspace_bytes - w.bytes, st);
 }
 
 extern "C" int kw_gmm_hard_labels(int64_t N, const double* x_dev, int K, int D,
@@ -818,11 +832,17 @@ extern "C" int kw_gmm_hard_labels(int64_t N, const double* x_dev, int K, int D,
 
 extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, int D,
                                        const double* resp_dev, const double* centres_dev,
-                                       double* stats_dev, int precision, void* workspace_dev,
-                                       size_t workspace_bytes, void* stream) {
+                                       double* stats_dev, int precision, int resp_form,
+                                       void* workspace_dev, size_t workspace_bytes,
+                                       void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KW_REQUIRE(N > 0 && K > 0 && D > 0, "kw_gmm_mstep_accumulate: N, K, D must be positive");
     KW_REQUIRE(precision == 0 || precision == 1, "GMM precision must be 0 (fp64) or 1 (tensor)");
+    KW_REQUIRE(resp_form == 0 || resp_form == 1, "resp_form must be 0 or 1");
+    if (resp_form == 1 && precision == 0) {
+        set_error("the FP64 M-step takes responsibilities: call kw_gmm_normalize_resp first");
+        return KW_ERR_UNSUPPORTED;
+    }
     if (D + 1 > 1024) {
         set_error("dim %d too large", D);
         return KW_ERR_UNSUPPORTED;
@@ -835,7 +855,7 @@ extern "C" int kw_gmm_mstep_accumulate(int64_t N, const double* x_dev, int K, in
     if (precision == 1)
         return mstats_tc(N, x_dev, K, D, resp_dev, centres_dev, stats_dev,
                          static_cast<char*>(workspace_dev) + w.bytes, workspace_bytes - w.bytes,
-                         st);
+                         st, resp_form);
     return mstats_fp64(N, x_dev, K, D, resp_dev, centres_dev, w.partial, stats_dev, RESP_FLOOR, st);
 }
 

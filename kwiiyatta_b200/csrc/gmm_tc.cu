@@ -1125,6 +1125,116 @@ mstats_tc_nk_kernel(int n_mt_pad, int partial_len, const double* __restrict__ ts
     if (threadIdx.x == 0) raw[(size_t)k * (partial_len + 1) + partial_len] = sh[0];
 }
 
+// E-step tail for an EM iteration (kw_gmm_estep resp_form 1): from the weighted log-probabilities
+// straight to what mstats_tc2_kernel consumes -- the outputs of mstats_tc_prep_kernel -- without
+// writing the responsibilities at all.  respT keeps the log-probabilities
+// (kw_gmm_normalize_resp turns them into r).
+//
+// A block owns FB frames (FB / 64 M-step tiles) and stages their K x FB log-probabilities in
+// shared memory with one sweep of independent loads; everything after that is on chip:
+//   1. two threads per frame: maximum over the components;
+//   2. e = exp(wlp - max) once per element (skipped below exp(-46) of the maximum, where a term
+//      cannot change a double-precision sum), kept in place, and their sum -> log-likelihood;
+//   3. a warp per (tile, share of the components), two frames per lane: r = e / sum, then flag,
+//      scaled fp32 weights, inverse scale, tile weight, items' tile counts.
+// lse_kernel + mstats_tc_prep_kernel were bound by the FP64 pipe (two exp per element) and two
+// more passes over the matrix; this is one exp for the few components near the maximum and one
+// read of the matrix.
+template <int FB>
+__global__ void __launch_bounds__(2 * FB)
+lse_prep_kernel(long long N, long long Npad, int K, const double* __restrict__ wlpT,
+                double* __restrict__ lse_partial, int n_mt_pad, unsigned char* __restrict__ flags,
+                float* __restrict__ wts, double* __restrict__ tsum, float floor,
+                int tiles_per_chunk, int* __restrict__ item_count) {
+    extern __shared__ double tile_s[];                 // [K][FB]
+    __shared__ double mx_s[2][FB], sum_s[2][FB], lse_s[FB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = threadIdx.x % FB, part = threadIdx.x / FB;     // part 0 / 1: halves of K
+    const long long n = (long long)blockIdx.x * FB + fr;
+    const int kh = (K + 1) >> 1, k_lo = part * kh, k_hi = min(K, k_lo + kh);
+    // global -> shared with cp.async: every load of the block in flight at once, no registers
+    // (the compiler would not keep more than five register loads outstanding here)
+    if (n < N) {
+        const double* col = wlpT + n;
+        for (int k = k_lo; k < k_hi; ++k) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile_s + (size_t)k * FB + fr);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst),
+                         "l"(col + (size_t)k * Npad)
+                         : "memory");
+        }
+    } else {
+        for (int k = k_lo; k < k_hi; ++k) tile_s[(size_t)k * FB + fr] = -CUDART_INF;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    double mx = -CUDART_INF;
+#pragma unroll 8
+    for (int k = k_lo; k < k_hi; ++k) mx = fmax(mx, tile_s[(size_t)k * FB + fr]);
+    mx_s[part][fr] = mx;
+    __syncthreads();
+    mx = fmax(mx_s[0][fr], mx_s[1][fr]);
+    double sum = 0.0;
+#pragma unroll 4
+    for (int k = k_lo; k < k_hi; ++k) {
+        const double dlt = tile_s[(size_t)k * FB + fr] - mx;
+        const double e = dlt > -46.0 ? exp(dlt) : 0.0;
+        tile_s[(size_t)k * FB + fr] = e;
+        sum += e;
+    }
+    sum_s[part][fr] = sum;
+    __syncthreads();
+    if (part == 0) {
+        const double t = sum_s[0][fr] + sum_s[1][fr];
+        lse_s[fr] = n < N ? log(t) + mx : 0.0;
+        sum_s[0][fr] = n < N ? 1.0 / t : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < FB; ++i) t += lse_s[i];
+        lse_partial[blockIdx.x] = t;
+    }
+    constexpr int TPB = FB / MT;                       // tiles per block
+    constexpr int SHARE = (2 * FB / 32) / TPB;         // warps per tile
+    const int tl = warp % TPB, ws = warp / TPB;
+    const int tile = TPB * blockIdx.x + tl;
+    const long long n0 = (long long)tile * MT + 2 * lane;
+    const bool h0 = n0 < N, h1 = n0 + 1 < N;
+    const double i0 = sum_s[0][tl * MT + 2 * lane], i1 = sum_s[0][tl * MT + 2 * lane + 1];
+    const int chunk = tile / tiles_per_chunk;
+#pragma unroll 2
+    for (int k = ws; k < K; k += SHARE) {
+        const double2 e = *reinterpret_cast<const double2*>(tile_s + (size_t)k * FB + tl * MT +
+                                                            2 * lane);
+        const double r0 = h0 ? e.x * i0 : 0.0, r1 = h1 ? e.y * i1 : 0.0;
+        const float f0 = (float)r0, f1 = (float)r1;
+        const uint32_t mb = __reduce_max_sync(0xffffffffu,
+                                              max(__float_as_uint(f0), __float_as_uint(f1)));
+        const bool on = __uint_as_float(mb) > floor;
+        const size_t slot = (size_t)k * n_mt_pad + tile;
+        if (on) {
+            double s2 = r0 + r1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            const uint32_t eb = mb >> 23;
+            const bool normal = eb >= 1u && eb <= 252u;
+            const float up = normal ? __uint_as_float((253u - eb) << 23) : 1.f;
+            *reinterpret_cast<float2*>(wts + slot * WSTRIDE + 2 * lane) =
+                make_float2(f0 * up, f1 * up);
+            if (lane == 0) {
+                const float inv = normal ? __uint_as_float((eb + 1u) << 23) : 1.f;
+                *reinterpret_cast<float4*>(wts + slot * WSTRIDE + MT) =
+                    make_float4(inv, 0.f, 0.f, 0.f);
+                flags[slot] = 1;
+                tsum[slot] = s2;
+                atomicAdd(item_count + chunk * K + k, 1);
+            }
+        } else if (lane == 0) {
+            flags[slot] = 0;
+            tsum[slot] = 0.0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // The M-step kernel: the generated operand lives in TENSOR MEMORY.
 //
@@ -1776,6 +1886,11 @@ constexpr int TC_STAT_CHUNKS = 1184;
 // statistics move by 1.6e-13 of their largest entry, six orders below the rounding of the
 // split-fp16 contraction itself (tools/time_mstep_real.py).  The FP64 path keeps 1e-16 per frame.
 constexpr float TC_TILE_FLOOR = 1e-8f;
+constexpr int TC_RESP_FORM1_MAX_K = 384;     // K x 64 frames of doubles in shared memory
+static float tile_floor_tc() {
+    const char* floor_env = getenv("KW_TC_TILE_FLOOR");      // experiments only
+    return floor_env != nullptr ? (float)atof(floor_env) : TC_TILE_FLOOR;
+}
 
 struct TcWorkspace {
     double* colpartial;
@@ -1841,7 +1956,7 @@ static TcWorkspace carve_tc(long long N, int K, int D, void* base) {
     w.bt = c.take<__half>((size_t)(K + 1) * 2 * tc::bmat_elems(DP));   // (+1: odd K padded to a pair)
     w.sc = c.take<float>((size_t)K * 3 * DP);
     w.cst = c.take<double>(3 * (size_t)K);
-    w.lse_partial = c.take<double>((size_t)n_tiles + 1);
+    w.lse_partial = c.take<double>(2 * (size_t)n_tiles + 2);
     w.cand = c.take<int32_t>((size_t)N);
     w.mu32 = c.take<float>((size_t)K * G.DA);
     w.mpartial = c.take<float>((size_t)w.m_chunks * K * G.partial_len);
@@ -1898,7 +2013,7 @@ int pack_frames_tc(long long N, const double* X, int K, int D, void* workspace,
 // lse_out[1];  mode 1: hard labels into mix (FP64 re-check of near ties).
 int estep_tc(long long N, const double* X, int K, int D, const double* means, const double* pc,
              const double* aux, double* resp, double* lse_out, int mode, int32_t* mix,
-             void* workspace, size_t workspace_bytes, cudaStream_t st) {
+             void* workspace, size_t workspace_bytes, cudaStream_t st, int resp_form) {
     TcWorkspace w;
     int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
     if (rc != KW_OK) return rc;
@@ -1951,17 +2066,48 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
         KW_CUDA_CHECK(cudaGetLastError());
         return KW_OK;
     }
-    const unsigned lgrid = (unsigned)((N + 127) / 128);
-    tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial);
+    unsigned lgrid = (unsigned)((N + 127) / 128);
+    if (resp_form == 1) {
+        if (K > TC_RESP_FORM1_MAX_K) {
+            set_error("resp_form 1 supports at most %d components, got %d", TC_RESP_FORM1_MAX_K, K);
+            return KW_ERR_UNSUPPORTED;
+        }
+        // EM iteration: the M-step's inputs straight from the log-probabilities
+        KW_CUDA_CHECK(cudaMemsetAsync(w.item_count, 0, sizeof(int) * (size_t)K * w.m_chunks, st));
+        const int n_mt_pad = (w.n_mtiles + 3) / 4 * 4;
+        // one 64-frame tile per block: 512 K bytes of shared memory, several blocks per SM
+        const int sm = K * 64 * (int)sizeof(double);
+        lgrid = (unsigned)((N + 63) / 64);
+        KW_CUDA_CHECK(cudaFuncSetAttribute(tc::lse_prep_kernel<64>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        tc::lse_prep_kernel<64><<<lgrid, 128, sm, st>>>(
+            N, Npad, K, resp, w.lse_partial, n_mt_pad, w.tflags, w.wts, w.tsum,
+            tile_floor_tc(), w.tiles_per_chunk, w.item_count);
+    } else {
+        tc::lse_kernel<<<lgrid, 128, 0, st>>>(N, Npad, K, resp, w.lse_partial);
+    }
     KW_CUDA_CHECK(cudaGetLastError());
     launch_reduce_fixed(w.lse_partial, (long long)lgrid, (double)N, lse_out, st);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
 }
 
+// Weighted log-probabilities left by estep_tc(resp_form 1) -> responsibilities, in place.
+int normalize_resp_tc(long long N, int K, int D, double* resp, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
+    TcWorkspace w;
+    int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
+    if (rc != KW_OK) return rc;
+    tc::lse_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, resp_pad(N), K, resp,
+                                                              w.lse_partial);
+    KW_CUDA_CHECK(cudaGetLastError());
+    return KW_OK;
+}
+
 // M-step statistics on the tensor cores (frames packed by pack_frames_tc).
 int mstats_tc(long long N, const double* X, int K, int D, const double* resp, const double* centres,
-              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+              double* stats, void* workspace, size_t workspace_bytes, cudaStream_t st,
+              int resp_form) {
     TcWorkspace w;
     int rc = tc_check(N, K, D, workspace, workspace_bytes, w);
     if (rc != KW_OK) return rc;
@@ -1972,19 +2118,18 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
     const int items = K * w.m_chunks;
     const int grid = std::min(items, device_sms());
     KW_CUDA_CHECK(cudaMemsetAsync(w.item_counter, 0, sizeof(int), st));
-    KW_CUDA_CHECK(cudaMemsetAsync(w.item_count, 0, sizeof(int) * (size_t)items, st));
     const int n_mt_pad = (w.n_mtiles + 3) / 4 * 4;
-    const char* floor_env = getenv("KW_TC_TILE_FLOOR");      // experiments only
-    const float tile_floor = floor_env != nullptr ? (float)atof(floor_env) : TC_TILE_FLOOR;
-    {
+    if (resp_form == 0) {
+        // (resp_form 1: estep_tc left flags, weights, tile sums and item counts in the workspace)
+        KW_CUDA_CHECK(cudaMemsetAsync(w.item_count, 0, sizeof(int) * (size_t)items, st));
         const long long warps = (long long)K * (n_mt_pad / 4);
         tc::mstats_tc_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-            N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags, w.wts, w.tsum, tile_floor,
-            w.tiles_per_chunk, w.item_count);
-        KW_CUDA_CHECK(cudaGetLastError());
-        tc::mstats_tc_order_kernel<<<1, 1024, 0, st>>>(items, w.item_count, w.item_order);
+            N, resp_pad(N), w.n_mtiles, n_mt_pad, K, resp, w.tflags, w.wts, w.tsum,
+            tile_floor_tc(), w.tiles_per_chunk, w.item_count);
         KW_CUDA_CHECK(cudaGetLastError());
     }
+    tc::mstats_tc_order_kernel<<<1, 1024, 0, st>>>(items, w.item_count, w.item_order);
+    KW_CUDA_CHECK(cudaGetLastError());
     // timing experiments only (tools/time_mstep.py): bits that switch parts of the kernel off
     const char* dbg_env = getenv("KW_TC_MSWAP");
     const int dbg = dbg_env != nullptr ? atoi(dbg_env) : 0;

@@ -24,6 +24,7 @@ from .delta import DELTA_WINDOWS, check_windows
 PRECISIONS = {'fp64': 0, 'tc': 1, 0: 0, 1: 1, 'auto': -1}
 TC_MAX_DIM = 144          # the tcgen05 kernels hold one frame row of <= 144 features
 TC_MIN_FRAMES_PER_DIM = 8
+RESP_FORM1_MAX_COMPONENTS = 384   # kw_gmm_estep resp_form 1: K x 64 doubles of shared memory
 TC_MIN_WORK = 2e10        # N K D^2 below which the FP64 kernels take about a millisecond anyway
 
 
@@ -102,6 +103,7 @@ class GaussianMixture:
         self._x_src = None
         self._x_used = None
         self._iters_done = 0
+        self._resp_log = False      # `_resp` holds log-probabilities (see _estep)
         # per-stage precision (diagnostics: tools/tc_error_split.py); a precision-1 workspace
         # also holds what the FP64 kernels need
         self._precision_e = self._precision_m = self.precision
@@ -144,36 +146,55 @@ class GaussianMixture:
             return self._x_used
         return x
 
-    def _reorder(self, torch, n):
-        """Sort the frames (and the responsibilities in place) by dominant component and
-        re-pack them."""
+    def _reorder(self, torch, n, permute_resp):
+        """Sort the frames by dominant component (the argmax of ``_resp``, responsibilities or
+        log-probabilities alike) and re-pack them.  ``permute_resp``: carry the responsibilities
+        along (the initial ones); between iterations the next E-step rewrites them instead."""
         labels = self._resp[:, :n].argmax(dim=0)
         perm = torch.argsort(labels, stable=True)
         base = self._x_used if self._x_used is not None else self._x_src
         self._x_used = base.index_select(0, perm)
-        self._resp[:, :n] = self._resp[:, :n].index_select(1, perm)
+        if permute_resp:
+            self._resp[:, :n] = self._resp[:, :n].index_select(1, perm)
         self._pack(torch, self._x_used)
 
     def _wants_reorder(self, n):
         return self.precision == 1 and self.reorder_every > 0 and n >= 8192
 
-    def _estep(self, torch, x):
+    def _estep(self, torch, x, for_mstep=False):
+        """E-step into ``_resp``.  ``for_mstep`` (tensor-core E-step followed by the
+        tensor-core M-step only): ``_resp`` keeps the weighted log-probabilities and the M-step's
+        inputs (tile flags, fp32 weights, tile sums) go straight to the workspace -- the
+        responsibilities themselves are never written (kw_gmm_estep resp_form 1)."""
         x = self._frames(x)
         n, d = x.shape
+        self._resp_log = (bool(for_mstep) and self._precision_e == 1 and self._precision_m == 1
+                          and self.n_components <= RESP_FORM1_MAX_COMPONENTS)
         rc = _lib.lib().kw_gmm_estep(
             n, x.data_ptr(), self.n_components, d, self._means[self._cur].data_ptr(),
             self._pc.data_ptr(), self._aux.data_ptr(), self._resp.data_ptr(),
-            self._stats.data_ptr(), self._precision_e, self._ws.data_ptr(), self._ws_bytes,
-            _lib.stream_ptr(torch))
+            self._stats.data_ptr(), self._precision_e, int(self._resp_log),
+            self._ws.data_ptr(), self._ws_bytes, _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_estep')
+
+    def _normalize_resp(self, torch, x):
+        """``_resp`` from log-probabilities to responsibilities, in place (no-op otherwise)."""
+        if not self._resp_log:
+            return
+        n, d = self._frames(x).shape
+        rc = _lib.lib().kw_gmm_normalize_resp(
+            n, self.n_components, d, self._resp.data_ptr(), self._ws.data_ptr(), self._ws_bytes,
+            _lib.stream_ptr(torch))
+        _lib.check(rc, 'kw_gmm_normalize_resp')
+        self._resp_log = False
 
     def _accumulate(self, torch, x, centres):
         x = self._frames(x)
         n, d = x.shape
         rc = _lib.lib().kw_gmm_mstep_accumulate(
             n, x.data_ptr(), self.n_components, d, self._resp.data_ptr(), centres.data_ptr(),
-            self._stats.data_ptr(), self._precision_m, self._ws.data_ptr(), self._ws_bytes,
-            _lib.stream_ptr(torch))
+            self._stats.data_ptr(), self._precision_m, int(self._resp_log),
+            self._ws.data_ptr(), self._ws_bytes, _lib.stream_ptr(torch))
         _lib.check(rc, 'kw_gmm_mstep_accumulate')
 
     # all-reduce the triangle-packed statistics instead of the full vector (see
@@ -262,8 +283,9 @@ class GaussianMixture:
             print('Initialization 0')
         # GaussianMixture._initialize: one M-step from the initial responsibilities
         self._resp[:, :n].copy_(self._initial_resp(torch, x))
+        self._resp_log = False
         if self._wants_reorder(n):
-            self._reorder(torch, n)
+            self._reorder(torch, n, permute_resp=True)
         else:
             self._pack(torch, x)
         centre = x.sum(dim=0, keepdim=True)
@@ -339,10 +361,11 @@ class GaussianMixture:
         enqueued; the iteration's scalars travel to pinned host memory behind them.  Returns the
         centres the statistics are taken around and a ticket for ``_resolve``."""
         centres = self._means[self._cur]
-        self._estep(torch, x)
         self._iters_done += 1
         if self._wants_reorder(x.shape[0]) and self._iters_done % self.reorder_every == 0:
-            self._reorder(torch, x.shape[0])
+            # by the dominant components of the previous E-step; this one rewrites `_resp`
+            self._reorder(torch, x.shape[0], permute_resp=False)
+        self._estep(torch, x, for_mstep=True)
         self._accumulate(torch, x, centres)
         self._allreduce(torch)
         slot = self._tickets & 1

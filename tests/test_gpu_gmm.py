@@ -210,3 +210,49 @@ def test_tensor_core_mstep_tile_floor(cuda):
     assert abs(tc[0, 0] - ref[0, 0]) <= 1e-7 * ref[0, 0]
     scale = np.abs(ref[:2]).max(axis=1, keepdims=True)
     assert np.all(np.abs(tc[:2] - ref[:2]) <= 2e-6 * scale)
+
+
+@pytest.mark.parametrize('n,d,k', [(9000, 40, 6), (4500, 144, 3), (300, 24, 2), (8321, 32, 64)])
+def test_estep_for_mstep_form(cuda, n, d, k):
+    """kw_gmm_estep(resp_form 1): the E-step of an EM iteration leaves the weighted
+    log-probabilities in the caller's buffer and the M-step's inputs in the workspace instead of
+    writing the responsibilities.  Normalised afterwards (kw_gmm_normalize_resp) the buffer holds
+    the responsibilities of the resp_form-0 call, the log-likelihood sums agree, and the
+    tensor-core M-step gives the same statistics either way; the FP64 M-step refuses the form."""
+    import torch
+    import kwiiyatta_b200 as kw
+    from kwiiyatta_b200 import _lib
+    rng = np.random.default_rng(5)
+    lab = rng.integers(0, k, n)
+    x = rng.standard_normal((n, d)) + 3.0 * rng.standard_normal((k, d))[lab]
+    resp0 = np.zeros((n, k))
+    resp0[np.arange(n), lab] = 1.0
+    gm = kw.GaussianMixture(n_components=k, max_iter=1, tol=0.0, resp_init=resp0,
+                            precision='tc', reorder_every=0)
+    xd = gm.initialize(x)
+    centres = gm._means[gm._cur]
+    gm._estep(torch, xd)                          # responsibilities
+    assert not gm._resp_log
+    plain = gm._resp[:, :n].clone()
+    tail_plain = gm._stats[-2:].clone()
+    gm._accumulate(torch, xd, centres)
+    stats_plain = gm._stats.clone()
+    gm._estep(torch, xd, for_mstep=True)          # log-probabilities + M-step inputs
+    assert gm._resp_log
+    logp = gm._resp[:, :n].clone()
+    assert torch.allclose(gm._stats[-2:], tail_plain, rtol=1e-13, atol=0)
+    gm._accumulate(torch, xd, centres)
+    stats_log = gm._stats.clone()
+    # the FP64 M-step does not take the form
+    rc = _lib.lib().kw_gmm_mstep_accumulate(
+        n, xd.data_ptr(), k, d, gm._resp.data_ptr(), centres.data_ptr(), gm._stats.data_ptr(),
+        0, 1, gm._ws.data_ptr(), gm._ws_bytes, _lib.stream_ptr(torch))
+    assert rc != 0
+    gm._stats.copy_(stats_log)
+    gm._normalize_resp(torch, xd)
+    assert not gm._resp_log
+    assert torch.equal(gm._resp[:, :n], plain)
+    lse = torch.logsumexp(logp, dim=0)
+    assert abs(float(lse.sum()) - float(tail_plain[0])) <= 1e-9 * abs(float(tail_plain[0]))
+    scale = stats_plain.abs().max().item()
+    assert (stats_log - stats_plain).abs().max().item() <= 1e-12 * scale
