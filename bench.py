@@ -352,25 +352,36 @@ def run_b200(args):
     # end to end through the converter back-end API with host buffers
     x_pinned = torch.from_numpy(x_joint).pin_memory()
     e2e_iters = 100     # the reference's own default (GMMFeatureConverter(max_iter=100)), tol = 0
-    conv = kw.B200GMMFeatureConverter(components=N_MIX_EM, max_iter=e2e_iters, tol=0.0,
-                                      verbose=0, device=dev, precision=args.precision)
-    barrier()
-    t0 = time.perf_counter()
     import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore')
-        lab_dev = torch.from_numpy(labels0).to(dev)
-        r0 = torch.zeros((n_frames, N_MIX_EM), dtype=torch.float64, device=dev)
-        r0[torch.arange(n_frames, device=dev), lab_dev] = 1.0
-        conv.gmm.resp_init = r0
-        conv._train(x_pinned)
-    torch.cuda.synchronize()
-    em_e2e_s = time.perf_counter() - t0
+
+    def train_once():
+        """One user-level training call: labels -> resp_init on the device, _train(host array)."""
+        conv = kw.B200GMMFeatureConverter(components=N_MIX_EM, max_iter=e2e_iters, tol=0.0,
+                                          verbose=0, device=dev, precision=args.precision)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            lab_dev = torch.from_numpy(labels0).to(dev)
+            r0 = torch.zeros((n_frames, N_MIX_EM), dtype=torch.float64, device=dev)
+            r0[torch.arange(n_frames, device=dev), lab_dev] = 1.0
+            conv.gmm.resp_init = r0
+            conv._train(x_pinned)
+        torch.cuda.synchronize()
+        return conv, time.perf_counter() - t0
+
+    # the first call of a process also pays for device / pinned allocations and first launches
+    # (0.29 s against 0.19 s, tools/time_e2e_em.py): one untimed warm-up call, like the W
+    # warm-up steps of the device-timed loop, then the timed one
+    conv, em_e2e_first_s = train_once()
+    del conv
+    conv, em_e2e_s = train_once()
     em_e2e_ms = max_over_ranks(em_e2e_s * 1e3)
     em_e2e = frames_total * e2e_iters / (em_e2e_ms / 1e3)
     model_bytes = sum(a.nbytes for a in (conv.gmm.weights_, conv.gmm.means_,
                                          conv.gmm.covariances_, conv.gmm.precisions_cholesky_))
-    del conv, r0
+    del conv
     # the fit a user gets: reference defaults (tol = 1e-3, max_iter = 100, KMeans initialisation,
     # here kwiiyatta_b200.kmeans on the device), timed whole with host buffers
     fit = None
@@ -525,7 +536,9 @@ def run_b200(args):
             'h2d_bytes_per_step': int(x_joint.nbytes + labels0.nbytes),
             'd2h_bytes_per_step': int(model_bytes),
             'note': f'B200GMMFeatureConverter._train on a pinned host (N,144) array, '
-                    f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model',
+                    f'{e2e_iters} iterations incl. H2D of X, initial M-step and D2H of the model; '
+                    f'second call of the process (the first, with its allocations: '
+                    f'{em_e2e_first_s:.3f} s)',
         },
         'gpu_launches': (11 if tc else 6) * K,
         'roofline': {
