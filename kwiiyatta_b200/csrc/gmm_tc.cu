@@ -1817,9 +1817,17 @@ __global__ void mstats_tc_reduce_kernel(int K, int partial_len, int n_chunks,
     const int k = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < partial_len) {
+        // chunks in ascending order, eight loads in flight
         double t = 0.0;
-        for (int c = 0; c < n_chunks; ++c)
-            t += (double)partial[((size_t)c * K + k) * partial_len + e];
+        for (int c0 = 0; c0 < n_chunks; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[q] = partial[((size_t)min(c0 + q, n_chunks - 1) * K + k) * partial_len + e];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (c0 + q < n_chunks) t += (double)v[q];
+        }
         raw[(size_t)k * (partial_len + 1) + e] = t;
     }
 }
@@ -2157,7 +2165,8 @@ int mstats_tc(long long N, const double* X, int K, int D, const double* resp, co
     KW_CUDA_CHECK(cudaGetLastError());
     tc::mstats_tc_nk_kernel<<<K, 256, 0, st>>>(n_mt_pad, G.partial_len, w.tsum, w.mraw);
     KW_CUDA_CHECK(cudaGetLastError());
-    tc::mstats_tc_post_kernel<<<dim3(K, 8), 256, 0, st>>>(K, D, DP, w.mraw, w.xinfo, w.mu32,
+    // (a thread's element needs ~15 dependent-latency loads: many small blocks, 2-3 elements each)
+    tc::mstats_tc_post_kernel<<<dim3(K, 32), 256, 0, st>>>(K, D, DP, w.mraw, w.xinfo, w.mu32,
                                                           centres, stats, 1.0 + 0.65 / 8388608.0);
     KW_CUDA_CHECK(cudaGetLastError());
     return KW_OK;
