@@ -212,7 +212,8 @@ def test_tensor_core_mstep_tile_floor(cuda):
     assert np.all(np.abs(tc[:2] - ref[:2]) <= 2e-6 * scale)
 
 
-@pytest.mark.parametrize('n,d,k', [(9000, 40, 6), (4500, 144, 3), (300, 24, 2), (8321, 32, 64)])
+@pytest.mark.parametrize('n,d,k', [(9000, 40, 6), (4500, 144, 3), (300, 24, 2), (8321, 32, 64),
+                                   (5003, 16, 7), (6000, 16, 130), (130, 8, 1)])
 def test_estep_for_mstep_form(cuda, n, d, k):
     """kw_gmm_estep(resp_form 1): the E-step of an EM iteration leaves the weighted
     log-probabilities in the caller's buffer and the M-step's inputs in the workspace instead of
