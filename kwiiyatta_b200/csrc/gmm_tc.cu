@@ -528,7 +528,7 @@ __host__ __device__ inline EstepSmem estep_smem(int DP, int G) {
     s.b_lo = o;  o += 2u * (uint32_t)(G * bmat_elems(DP)) * 2;   // two stages
     s.scl = o;                                          // (unused)
     s.cst = o;   o += 2u * 4 * 8;                      // two stages of [log|L|, log w, 4^t, -]
-    s.qpart = o; o += 3u * 2 * TILE_M * 2 * 8;       // [part - 1][stage][row][component of the item]
+    s.qpart = o; o += 3u * 4 * TILE_M * 2 * 8;       // [part - 1][item % 4][row][component of the item]
     s.bars = o;  o += 16 * 8;
     s.tmem_ptr = o; o += 16;
     s.total = o;
@@ -545,7 +545,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 uint32_t tmem_cols, const __half* __restrict__ xt, const __half* __restrict__ bt,
                 const double* __restrict__ cst,
                 double* __restrict__ wlpT, int mode, int32_t* __restrict__ mix,
-                int32_t* __restrict__ cand, double near_tie,
+                int32_t* __restrict__ cand, double near_tie, int late_release,
                 unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const EstepSmem L = estep_smem(DP, G);
@@ -789,36 +789,40 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                 }
                 tc_fence_before();
                 __syncwarp();
+                // Every warp frees the accumulator stage as soon as its own columns are in
+                // registers, so the MMAs of item g + 2 do not wait for the rest of this item's
+                // epilogue (they did: 14 % of the MMA warp's time in EM).  With `late_release`
+                // part 0 frees it only after the partial sums (see estep_tc for when).
+                if (lane == 0 && (part > 0 || !late_release)) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
+                // The partial sums and their named barrier therefore live in a ring of their own,
+                // four slots deep: parts 1..3 can only write slot g % 4 after the MMAs of item g,
+                // which waited for every warp's arrival for item g - 2 -- and part 0 makes that
+                // arrival after it has finished item g - 3, so slots g - 2 .. g are the only ones
+                // that can be live.
+                const uint32_t q4 = g & 3u;
                 if (part > 0) {
-                    if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
-                    double* qp = qpart + ((size_t)((part - 1) * 2 + s) * TILE_M + row) * 2;
+                    double* qp = qpart + ((size_t)((part - 1) * 4 + q4) * TILE_M + row) * 2;
                     qp[0] = qa;
                     qp[1] = qb;
                 }
                 const long long e3 = tick<PROF>();
                 // The only CTA-level synchronisation of an item: parts 1..3 signal that their
-                // partial sums are in shared memory (named barrier 3 + stage, they do not wait),
-                // part 0 waits for them.  Part 0 frees the accumulator stage only AFTER it has
-                // read the partial sums: the MMAs of item g+2 (same stage) wait for that, so
-                // neither the partial sums nor the barrier of stage s are touched again before
-                // part 0 is done with item g.
-                if (part == 0) {
-                    if (s) asm volatile("bar.sync 4, 512;" ::: "memory");
-                    else asm volatile("bar.sync 3, 512;" ::: "memory");
-                } else {
-                    if (s) asm volatile("bar.arrive 4, 512;" ::: "memory");
-                    else asm volatile("bar.arrive 3, 512;" ::: "memory");
-                }
+                // partial sums are in shared memory (named barrier 3 + slot, they do not wait),
+                // part 0 waits for them.
+                if (part == 0) asm volatile("bar.sync %0, 512;" ::"r"(3u + q4) : "memory");
+                else asm volatile("bar.arrive %0, 512;" ::"r"(3u + q4) : "memory");
                 q_work += e3 - e2; q_bar += tick<PROF>() - e3;
                 if (part == 0) {
 #pragma unroll
                     for (int pp = 0; pp < 3; ++pp) {
-                        const double* qp = qpart + ((size_t)(pp * 2 + s) * TILE_M + row) * 2;
+                        const double* qp = qpart + ((size_t)(pp * 4 + q4) * TILE_M + row) * 2;
                         qa += qp[0];
                         qb += qp[1];
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
+                    if (late_release) {      // experiment: the stage freed after the partial sums
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bars + BAR_TM_EMPTY0 + s);
+                    }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const int k = item * G + c;
@@ -2039,11 +2043,17 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     uint32_t cols = 32;
     while (cols < 2u * G * DP + DP + 16) cols <<= 1;  // two accumulator stages + the frame tile (hi+ones, lo)
     const int grid = (int)std::min<long long>(n_tiles, sms);
+    // when the epilogue frees an accumulator stage: measured on one box (tools/ab_release.py),
+    // early release takes 4 % off the EM E-step (one component per item, 27 MMAs: the MMA warp was
+    // waiting for the stage) and adds 10 % to the conversion posterior (two components per item,
+    // a third of the MMA work: the MMAs running further ahead slow the epilogue's TMEM loads)
+    const char* lr_env = getenv("KW_TC_LATE_RELEASE");      // experiments only
+    const int late_release = lr_env != nullptr ? atoi(lr_env) : (G == 2 ? 1 : 0);
     auto launch = [&](auto kern, unsigned long long* pd) -> int {
         KW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)L.total));
         kern<<<grid, 576, L.total, st>>>(N, Npad, (int)n_tiles, K, D, DP, cols, w.xt, w.bt, w.cst,
-                                         resp, mode, mix, w.cand, 0.05, pd);
+                                         resp, mode, mix, w.cand, 0.05, late_release, pd);
         return KW_OK;
     };
 #ifdef KW_TC_PROFILE_BUILD
