@@ -2033,7 +2033,8 @@ int estep_tc(long long N, const double* X, int K, int D, const double* means, co
     const long long n_tiles = (N + tc::TILE_M - 1) / tc::TILE_M;
     const long long Npad = resp_pad(N);
     // two components per MMA when both accumulators fit N <= 256 and TMEM (DP <= 96)
-    const int G = (DP <= 96 && K >= 2) ? 2 : 1;
+    const char* g_env = getenv("KW_TC_G");                 // experiments only
+    const int G = (g_env != nullptr && atoi(g_env) == 1) ? 1 : ((DP <= 96 && K >= 2) ? 2 : 1);
     const int KI = (K + G - 1) / G;
     tc::pack_l_kernel<<<dim3(KI * G, tc::PACK_L_SLICES), 256, 3 * sizeof(double) * DP, st>>>(K, D, DP, G, means, pc, aux,
                                                                 w.xinfo, w.bt, w.cst);

@@ -42,8 +42,10 @@ def timed(fn, reps=10):
 
 
 for rep in range(2):
-    for late in ('0', '1'):
-        os.environ['KW_TC_LATE_RELEASE'] = late
-        tc = timed(lambda: pg.transform_device(src, off, n_utts, frames))
-        te = timed(lambda: gm._estep(torch, xd, for_mstep=True))
-        print(f'late_release={late}: conversion {tc:.3f} ms, EM E-step entry {te:.3f} ms')
+    for g in ('2', '1'):
+        for late in ('0', '1'):
+            os.environ['KW_TC_LATE_RELEASE'] = late
+            os.environ['KW_TC_G'] = g
+            tc = timed(lambda: pg.transform_device(src, off, n_utts, frames))
+            te = timed(lambda: gm._estep(torch, xd, for_mstep=True))
+            print(f'G<={g} late_release={late}: conversion {tc:.3f} ms, EM E-step entry {te:.3f} ms')
