@@ -410,13 +410,17 @@ static size_t finalize_smem_bytes(int D) {
     return sizeof(double) * ((size_t)D * S + (size_t)D * (FIN_NB + 1) + 3 * (size_t)D);
 }
 
+__device__ long long fin_prof[8];     // KW_FIN_PROF: phase clocks of block 0 (diagnostics)
+
 __global__ void __launch_bounds__(FIN_THREADS)
 gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_stats,
                     const double* __restrict__ stats, const double* __restrict__ centres,
                     double* __restrict__ weights, double* __restrict__ means,
                     double* __restrict__ covariances, double* __restrict__ prec_chol,
-                    double* __restrict__ aux, int32_t* __restrict__ info) {
+                    double* __restrict__ aux, int32_t* __restrict__ info, int prof) {
     extern __shared__ double A[];
+    const bool prof_on = prof != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+    if (prof_on) fin_prof[0] = clock64();
     const int S = D | 1;
     double* T = A + (size_t)D * S;            // [column][FIN_NB + 1] scratch of the inverse
     double* dg = T + (size_t)D * (FIN_NB + 1);   // L[j][j]
@@ -466,6 +470,7 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
     if (tid == 0) sh_fail = 0;
     __syncthreads();
 
+    if (prof_on) fin_prof[1] = clock64();
     // ---- Cholesky, left-looking by panels of FIN_NB columns --------------------------------
     // Per element the products are subtracted in ascending column order (the arithmetic of an
     // unblocked left-looking sweep).
@@ -490,6 +495,7 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
                        a02 = r0[J + min(c0 + 2, nb - 1)], a03 = r0[J + min(c0 + 3, nb - 1)];
                 double a10 = r1[J + c0], a11 = r1[J + min(c0 + 1, nb - 1)],
                        a12 = r1[J + min(c0 + 2, nb - 1)], a13 = r1[J + min(c0 + 3, nb - 1)];
+#pragma unroll 8
                 for (int p = 0; p < J; ++p) {
                     const double l0 = -r0[p], l1 = -r1[p];
                     const double b0 = q0[p], b1 = q1[p], b2 = q2[p], b3 = q3[p];
@@ -513,49 +519,68 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
             }
             __syncthreads();
         }
-        // right-looking inside the panel, one barrier per column: every thread derives the
-        // pivot itself, warp w updates panel column j + 1 + w with the column-j values scaled on
-        // the fly, and the scaled column itself goes to the scratch T (nothing reads column j of
-        // A again inside the panel), copied back once the panel is done.
-        for (int c = 0; c < nb; ++c) {
-            const int j = J + c;
-            double s = A[j * S + j];
-            if (!(s > 0.0)) {
-                if (tid == 0 && sh_fail == 0) sh_fail = j + 1;
-                s = 1.0;
-            }
-            const double rinv = rsqrt(s);
-            if (tid == 0) dg[j] = s * rinv;
-            const int w = tid >> 5, l = j + 1 + w;
-            if (l < J + nb) {
-                const double mlj = -(A[l * S + j] * rinv);
-                // loads first, stores last (D <= 160: at most 5 rows per lane)
-                double va[5], vb[5];
+        // Inside the panel, two barriers instead of one per column.  Per element the products are
+        // still subtracted in ascending column order.  (Measured with finer clocks than KW_FIN_PROF
+        // keeps: of the Cholesky's 136k clk the left-looking panel updates take 69k -- few warps
+        // are active in the late panels and the dot products wait for shared memory -- the
+        // diagonal blocks 80k, 550 clk per pivot in one warp, the rows below 22k.)
+        // (a) the nb x nb diagonal block in ONE warp: lane r keeps row r in registers, the pivot
+        //     column travels through a small shared-memory line.
+        if (tid < 32) {
+            const int lane = tid;
+            double a[FIN_NB];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int i = l + (tid & 31) + 32 * q;
-                    if (i < D) {
-                        va[q] = A[i * S + j];
-                        vb[q] = A[i * S + l];
+            for (int q = 0; q < FIN_NB; ++q)
+                a[q] = (lane < nb && q <= lane) ? A[(J + lane) * S + J + q] : 0.0;
+#pragma unroll
+            for (int c = 0; c < FIN_NB; ++c) {
+                if (c < nb) {
+                    double s = __shfl_sync(0xffffffffu, a[c], c);
+                    if (!(s > 0.0)) {
+                        if (lane == 0 && sh_fail == 0) sh_fail = J + c + 1;
+                        s = 1.0;
                     }
-                }
+                    const double rinv = rsqrt(s);
+                    if (lane == c) {
+                        dg[J + c] = s * rinv;
+                        T[FIN_NB * 2 + c] = rinv;            // 1 / L[c][c] for the rows below
+                    }
+                    const double l_rc = a[c] * rinv;         // L[r][c] for the lanes r > c
+                    T[lane] = l_rc;
+                    __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int i = l + (tid & 31) + 32 * q;
-                    if (i < D) A[i * S + l] = fma(va[q] * rinv, mlj, vb[q]);
+                    for (int q = c + 1; q < FIN_NB; ++q)
+                        if (q < nb && lane >= q) a[q] = fma(l_rc, -T[q], a[q]);
+                    __syncwarp();
+                    if (lane > c) a[c] = l_rc;
                 }
-            } else {
-                // idle warps of this step store the finished column
-                const int nidle = FIN_THREADS / 32 - (nb - 1 - c);
-                const int q = (w - (nb - 1 - c)) * 32 + (tid & 31);
-                for (int i = j + 1 + q; i < D; i += nidle * 32) T[c * D + i] = A[i * S + j] * rinv;
             }
-            __syncthreads();
+            // L values below the diagonal back into the block (the diagonal keeps its pre-pivot
+            // value, as before)
+#pragma unroll
+            for (int q = 0; q < FIN_NB; ++q)
+                if (lane < nb && q < lane) A[(J + lane) * S + J + q] = a[q];
         }
-        for (int c = tid >> 5; c < nb; c += FIN_THREADS / 32)
-            for (int i = J + c + 1 + (tid & 31); i < D; i += 32) A[i * S + J + c] = T[c * D + i];
+        __syncthreads();
+        // (b) the rows below the block, one thread per row: forward substitution against the block
+        for (int i = J + nb + tid; i < D; i += FIN_THREADS) {
+            double x[FIN_NB];
+#pragma unroll
+            for (int c = 0; c < FIN_NB; ++c) {
+                if (c < nb) {
+                    double v = A[i * S + J + c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(x[q], -A[(J + c) * S + J + q], v);
+                    x[c] = v * T[FIN_NB * 2 + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < FIN_NB; ++c)
+                if (c < nb) A[i * S + J + c] = x[c];
+        }
         __syncthreads();
     }
+    if (prof_on) fin_prof[2] = clock64();
     // (A[j][j] still holds the pre-pivot value; the diagonal of L lives in dg)
     for (int j = tid; j < D; j += FIN_THREADS) zd[j] = 1.0 / dg[j];
     __syncthreads();
@@ -603,6 +628,7 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
             t00 = fma(la[c + 1], z0[c + 1], t00);
             t10 = fma(lb[c + 1], z0[c + 1], t10);
             double t01 = la[c + 1] * zd[c + 1], t11 = lb[c + 1] * zd[c + 1];
+#pragma unroll 8
             for (int p = c + 2; p < I0; ++p) {
                 const double xa = la[p], xb = lb[p], y0 = z0[p], y1 = z1[p];
                 t00 = fma(xa, y0, t00); t01 = fma(xa, y1, t01);
@@ -626,6 +652,7 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
         }
         __syncthreads();
     }
+    if (prof_on) fin_prof[3] = clock64();
     // prec_chol (upper) = Z^T; diagonal 1 / L[j][j]
     double* pc = prec_chol + (size_t)k * D * D;
     for (int r = tid >> 5; r < D; r += FIN_THREADS / 32)
@@ -656,6 +683,7 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
         ak[D + 1] = log(wk);
         info[k] = sh_fail;
     }
+    if (prof_on) fin_prof[4] = clock64();
 }
 
 static int m_chunks(int K) {
@@ -750,9 +778,17 @@ int finalize_launch(int K, int D, double reg_covar, int weight_norm, int from_st
     const size_t smem = finalize_smem_bytes(D);
     KW_CUDA_CHECK(cudaFuncSetAttribute(gmm_finalize_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = getenv("KW_FIN_PROF") != nullptr;      // diagnostics only
     gmm_finalize_kernel<<<K, FIN_THREADS, smem, st>>>(K, D, reg_covar, weight_norm, from_stats, stats,
-                                              centres, weights, means, cov, pc, aux, info);
+                                              centres, weights, means, cov, pc, aux, info, prof);
     KW_CUDA_CHECK(cudaGetLastError());
+    if (prof) {
+        long long h[8];
+        KW_CUDA_CHECK(cudaStreamSynchronize(st));
+        KW_CUDA_CHECK(cudaMemcpyFromSymbol(h, fin_prof, sizeof(h)));
+        fprintf(stderr, "[finalize block 0] statistics -> covariance %lld clk, Cholesky %lld, inverse %lld, "
+                        "write-out %lld\n", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
+    }
     return KW_OK;
 }
 

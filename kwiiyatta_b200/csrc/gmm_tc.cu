@@ -924,9 +924,16 @@ __global__ void refine_argmax_kernel(long long N, int D, const double* __restric
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const double LOG2PI = 1.8378770664093453;
-    for (long long n = warp; n < N; n += n_warps) {
-        const int kb = cand[n];
-        if (kb < 0) continue;
+    // a warp looks at 32 frames at a time (one coalesced load of their candidates) and re-checks
+    // the flagged ones in turn
+    for (long long n0 = warp * 32; n0 < N; n0 += n_warps * 32) {
+      const int mine = (n0 + lane < N) ? cand[n0 + lane] : -1;
+      unsigned todo = __ballot_sync(0xffffffffu, mine >= 0);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long n = n0 + src;
+        const int kb = __shfl_sync(0xffffffffu, mine, src);
         const int ka = mix[n];
         double w[2];
         for (int c = 0; c < 2; ++c) {
@@ -947,6 +954,7 @@ __global__ void refine_argmax_kernel(long long N, int D, const double* __restric
             const bool take_b = (w[1] > w[0]) || (w[1] == w[0] && kb < ka);
             if (take_b) mix[n] = kb;
         }
+      }
     }
 }
 
