@@ -527,39 +527,91 @@ gmm_finalize_kernel(int K, int D, double reg_covar, int weight_norm, int from_st
         // (a) the nb x nb diagonal block in ONE warp: lane r keeps row r in registers, the pivot
         //     column travels through a small shared-memory line.
         if (tid < 32) {
+            // branch-free straight-line code (the 16 row values are named scalars: as an indexed
+            // array the compiler kept them in local memory), so that the scheduler can run the next
+            // pivot's rsqrt under the rest of this column's updates; rows past nb act as identity
+            // rows.  Lane r keeps row r of the block; L[q][c] reaches the other lanes by shuffle.
+            static_assert(FIN_NB == 16, "the diagonal-block code below is written out for 16 columns");
             const int lane = tid;
-            double a[FIN_NB];
-#pragma unroll
-            for (int q = 0; q < FIN_NB; ++q)
-                a[q] = (lane < nb && q <= lane) ? A[(J + lane) * S + J + q] : 0.0;
-#pragma unroll
-            for (int c = 0; c < FIN_NB; ++c) {
-                if (c < nb) {
-                    double s = __shfl_sync(0xffffffffu, a[c], c);
-                    if (!(s > 0.0)) {
-                        if (lane == 0 && sh_fail == 0) sh_fail = J + c + 1;
-                        s = 1.0;
-                    }
-                    const double rinv = rsqrt(s);
-                    if (lane == c) {
-                        dg[J + c] = s * rinv;
-                        T[FIN_NB * 2 + c] = rinv;            // 1 / L[c][c] for the rows below
-                    }
-                    const double l_rc = a[c] * rinv;         // L[r][c] for the lanes r > c
-                    T[lane] = l_rc;
-                    __syncwarp();
-#pragma unroll
-                    for (int q = c + 1; q < FIN_NB; ++q)
-                        if (q < nb && lane >= q) a[q] = fma(l_rc, -T[q], a[q]);
-                    __syncwarp();
-                    if (lane > c) a[c] = l_rc;
-                }
+            double a0 = (lane < nb && 0 <= lane) ? A[(J + lane) * S + J + 0] : ((lane >= nb && lane == 0) ? 1.0 : 0.0);
+            double a1 = (lane < nb && 1 <= lane) ? A[(J + lane) * S + J + 1] : ((lane >= nb && lane == 1) ? 1.0 : 0.0);
+            double a2 = (lane < nb && 2 <= lane) ? A[(J + lane) * S + J + 2] : ((lane >= nb && lane == 2) ? 1.0 : 0.0);
+            double a3 = (lane < nb && 3 <= lane) ? A[(J + lane) * S + J + 3] : ((lane >= nb && lane == 3) ? 1.0 : 0.0);
+            double a4 = (lane < nb && 4 <= lane) ? A[(J + lane) * S + J + 4] : ((lane >= nb && lane == 4) ? 1.0 : 0.0);
+            double a5 = (lane < nb && 5 <= lane) ? A[(J + lane) * S + J + 5] : ((lane >= nb && lane == 5) ? 1.0 : 0.0);
+            double a6 = (lane < nb && 6 <= lane) ? A[(J + lane) * S + J + 6] : ((lane >= nb && lane == 6) ? 1.0 : 0.0);
+            double a7 = (lane < nb && 7 <= lane) ? A[(J + lane) * S + J + 7] : ((lane >= nb && lane == 7) ? 1.0 : 0.0);
+            double a8 = (lane < nb && 8 <= lane) ? A[(J + lane) * S + J + 8] : ((lane >= nb && lane == 8) ? 1.0 : 0.0);
+            double a9 = (lane < nb && 9 <= lane) ? A[(J + lane) * S + J + 9] : ((lane >= nb && lane == 9) ? 1.0 : 0.0);
+            double a10 = (lane < nb && 10 <= lane) ? A[(J + lane) * S + J + 10] : ((lane >= nb && lane == 10) ? 1.0 : 0.0);
+            double a11 = (lane < nb && 11 <= lane) ? A[(J + lane) * S + J + 11] : ((lane >= nb && lane == 11) ? 1.0 : 0.0);
+            double a12 = (lane < nb && 12 <= lane) ? A[(J + lane) * S + J + 12] : ((lane >= nb && lane == 12) ? 1.0 : 0.0);
+            double a13 = (lane < nb && 13 <= lane) ? A[(J + lane) * S + J + 13] : ((lane >= nb && lane == 13) ? 1.0 : 0.0);
+            double a14 = (lane < nb && 14 <= lane) ? A[(J + lane) * S + J + 14] : ((lane >= nb && lane == 14) ? 1.0 : 0.0);
+            double a15 = (lane < nb && 15 <= lane) ? A[(J + lane) * S + J + 15] : ((lane >= nb && lane == 15) ? 1.0 : 0.0);
+            unsigned bad = 0u;
+            double my_dg = 0.0, my_rinv = 0.0;
+#define FIN_UPD(q)                                                        \
+    {                                                                     \
+        const double lq = __shfl_sync(0xffffffffu, l_rc, q);              \
+        if (lane >= q) a##q = fma(l_rc, -lq, a##q);                       \
+    }
+#define FIN_STEP(c, UPDS)                                                 \
+    {                                                                     \
+        double s = __shfl_sync(0xffffffffu, a##c, c);                     \
+        const bool fail = !(s > 0.0);                                     \
+        bad |= fail ? (1u << c) : 0u;                                     \
+        s = fail ? 1.0 : s;                                               \
+        const double rinv = rsqrt(s);                                     \
+        if (lane == c) {                                                  \
+            my_dg = s * rinv;                                             \
+            my_rinv = rinv;                                               \
+        }                                                                 \
+        const double l_rc = a##c * rinv; /* L[r][c] for the lanes r > c */ \
+        UPDS                                                              \
+        if (lane > c) a##c = l_rc;                                        \
+    }
+            FIN_STEP(0, FIN_UPD(1) FIN_UPD(2) FIN_UPD(3) FIN_UPD(4) FIN_UPD(5) FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(1, FIN_UPD(2) FIN_UPD(3) FIN_UPD(4) FIN_UPD(5) FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(2, FIN_UPD(3) FIN_UPD(4) FIN_UPD(5) FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(3, FIN_UPD(4) FIN_UPD(5) FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(4, FIN_UPD(5) FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(5, FIN_UPD(6) FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(6, FIN_UPD(7) FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(7, FIN_UPD(8) FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(8, FIN_UPD(9) FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(9, FIN_UPD(10) FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(10, FIN_UPD(11) FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(11, FIN_UPD(12) FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(12, FIN_UPD(13) FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(13, FIN_UPD(14) FIN_UPD(15))
+            FIN_STEP(14, FIN_UPD(15))
+            FIN_STEP(15, )
+#undef FIN_STEP
+#undef FIN_UPD
+            if (lane < nb) {
+                dg[J + lane] = my_dg;
+                T[FIN_NB * 2 + lane] = my_rinv;              // 1 / L[c][c] for the rows below
             }
+            bad &= (1u << nb) - 1u;
+            if (lane == 0 && bad != 0u && sh_fail == 0) sh_fail = J + __ffs(bad);
             // L values below the diagonal back into the block (the diagonal keeps its pre-pivot
             // value, as before)
-#pragma unroll
-            for (int q = 0; q < FIN_NB; ++q)
-                if (lane < nb && q < lane) A[(J + lane) * S + J + q] = a[q];
+            if (lane < nb && 0 < lane) A[(J + lane) * S + J + 0] = a0;
+            if (lane < nb && 1 < lane) A[(J + lane) * S + J + 1] = a1;
+            if (lane < nb && 2 < lane) A[(J + lane) * S + J + 2] = a2;
+            if (lane < nb && 3 < lane) A[(J + lane) * S + J + 3] = a3;
+            if (lane < nb && 4 < lane) A[(J + lane) * S + J + 4] = a4;
+            if (lane < nb && 5 < lane) A[(J + lane) * S + J + 5] = a5;
+            if (lane < nb && 6 < lane) A[(J + lane) * S + J + 6] = a6;
+            if (lane < nb && 7 < lane) A[(J + lane) * S + J + 7] = a7;
+            if (lane < nb && 8 < lane) A[(J + lane) * S + J + 8] = a8;
+            if (lane < nb && 9 < lane) A[(J + lane) * S + J + 9] = a9;
+            if (lane < nb && 10 < lane) A[(J + lane) * S + J + 10] = a10;
+            if (lane < nb && 11 < lane) A[(J + lane) * S + J + 11] = a11;
+            if (lane < nb && 12 < lane) A[(J + lane) * S + J + 12] = a12;
+            if (lane < nb && 13 < lane) A[(J + lane) * S + J + 13] = a13;
+            if (lane < nb && 14 < lane) A[(J + lane) * S + J + 14] = a14;
         }
         __syncthreads();
         // (b) the rows below the block, one thread per row: forward substitution against the block
