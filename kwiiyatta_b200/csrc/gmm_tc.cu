@@ -32,8 +32,7 @@ namespace kw {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int LO_SHIFT = 11;          // lo parts are stored scaled by 2^11
-constexpr double LO_SCALE = 2048.0;
+constexpr double LO_SCALE = 2048.0;   // lo parts are stored scaled by 2^11
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
