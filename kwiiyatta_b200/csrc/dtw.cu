@@ -200,7 +200,7 @@ __global__ void dtw_pyramid_kernel(const PairDesc* __restrict__ descs, int level
         // global reads and the global writes are contiguous runs
         __shared__ double tile[64][33];
         const double* in = is_y ? y_in + d.yrow0 * F : x_in + d.xrow0 * F;
-        for (int r0 = 0; r0 < T; r0 += 64) {
+        for (int r0 = 64 * blockIdx.z; r0 < T; r0 += 64 * gridDim.z) {
             const int nr = min(64, T - r0);
             for (int e = threadIdx.x; e < nr * F; e += blockDim.x) {
                 const int i = e / F, k = e - i * F;
@@ -217,7 +217,8 @@ __global__ void dtw_pyramid_kernel(const PairDesc* __restrict__ descs, int level
         const int Tp = is_y ? d.ty[level - 1] : d.tx[level - 1];
         const double* in = is_y ? ypyr + d.yoff[level - 1] : xpyr + d.xoff[level - 1];
         const long long n = (long long)T * F;
-        for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+        for (long long e = threadIdx.x + (long long)blockDim.x * blockIdx.z; e < n;
+             e += (long long)blockDim.x * gridDim.z) {
             const int k = (int)(e / T), i = (int)(e % T);
             const double a = in[(size_t)k * Tp + 2 * i];
             const double b = in[(size_t)k * Tp + 2 * i + 1];
@@ -1102,8 +1103,12 @@ extern "C" int kw_dtw_batch(int n_pairs, const double* x_dev, const double* y_de
     }
     const SweepOpts opts{tie_mode, margin_dev};
     for (int l = 0; l < plan.maxlev; ++l) {
-        dtw_pyramid_kernel<<<dim3(n_pairs, 2), 256, 0, st>>>(w.descs, l, feat_dim, x_dev, y_dev,
-                                                             w.xpyr, w.ypyr);
+        // (pair, x | y, slice of the rows): one block per sequence walked its 64-row tiles one
+        // after the other, two barriers each -- 0.1 ms of latency at level 0
+        const int longest = std::max(plan.level_max_tx[l], plan.level_max_ty[l]);
+        const int slices = std::max(1, std::min(16, (longest + 63) / 64));
+        dtw_pyramid_kernel<<<dim3(n_pairs, 2, slices), 256, 0, st>>>(w.descs, l, feat_dim, x_dev,
+                                                                     y_dev, w.xpyr, w.ypyr);
         KW_CUDA_CHECK(cudaGetLastError());
     }
     for (int l = plan.maxlev - 1; l >= 0; --l) {
