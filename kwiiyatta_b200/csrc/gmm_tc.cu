@@ -385,6 +385,10 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
         double v = 0.0;
         if (n < N && c < D) v = (X[n * D + c] - xinfo[c]) / xinfo[DP + c];
         if (c == DP) v = 1.0;
+        // E-step only: a second constant column, 2^-11, multiplies the 2^11-scaled lo part of the
+        // bias, so that ONE MMA adds -b' = -(b'_hi + b'_lo) (see pack_l_kernel)
+        const bool e_only = c == DP + 1;
+        if (e_only) v = 1.0 / LO_SCALE;
         const size_t o = ((size_t)(r >> 3) * kg_n + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7);
         const __half h = __double2half(v);
         const double res = v - (double)__half2float(h);
@@ -394,7 +398,7 @@ __global__ void pack_x_kernel(long long N, int D, int DP, const double* __restri
         lo_u[o] = __double2half(res);
         const size_t ok = (size_t)(r >> 6) * 64 * DPB + (size_t)c * 64 +
                           (size_t)((((r & 63) >> 3) ^ (c & 7)) * 8) + (r & 7);
-        hi_k[ok] = h;
+        hi_k[ok] = e_only ? __double2half(0.0) : h;
         lo_k[ok] = __double2half(res);
     }
 }
@@ -503,11 +507,15 @@ pack_l_kernel(int K, int D, int DP, int G, const double* __restrict__ means,
     if (blockIdx.y == 0) {
         for (int e = threadIdx.x; e < DP * 16; e += blockDim.x) {
             const int j = e >> 4, dd = e & 15, jg = j >> 3;
-            const double v = (dd == 0 && real) ? -bpv[j] * inv : 0.0;
+            // K index 0 (times the column of ones): hi part of -b'_j; K index 1 (times the
+            // 2^-11 column): its lo part scaled by 2^11 -- both in the hi operand, one MMA
+            const double v = (dd <= 1 && real) ? -bpv[j] * inv : 0.0;
             const size_t o = (size_t)G * bbias_off(DP) +
                              ((size_t)(G * jg + ci) * 2 + ((dd >> 3) & 1)) * 64 + (j & 7) * 8 +
                              (dd & 7);
-            split_store(v, hi + o, lo + o);
+            const __half h = __double2half(v);
+            hi[o] = dd == 0 ? h : __double2half((v - (double)__half2float(h)) * LO_SCALE);
+            lo[o] = __double2half(0.0);
         }
     }
 }
@@ -663,9 +671,6 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             cols -= 16;
                             id = make_idesc(TILE_M, (int)(Gu * cols));
                         }
-                        // 1 . (-b'_lo): the bias row, every column
-                        umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps,
-                                    (s ? d_b_lo1 : d_b_lo0) + bias_off, idesc, 1u);
                     }
                     umma_commit(bars + BAR_BLO_EMPTY0 + s);
                     const long long c3 = tick<PROF>();
@@ -693,7 +698,7 @@ estep_tc_kernel(long long N, long long Npad, int n_tiles, int K, int D, int DP,
                             umma_f16_ts(acc + Gu * 16 * ks, ta_hi + 8 * ks, db,
                                         make_idesc(TILE_M, (int)(Gu * cols)), 1u);
                         }
-                        // 1 . (-b'_hi)
+                        // [1, 2^-11] . [-b'_hi, -b'_lo 2^11]: the whole bias in one MMA
                         umma_f16_ts(acc, ta_hi + 8 * (uint32_t)ksteps, d_b_hi + bias_off, idesc, 1u);
                     }
                     umma_commit(bars + BAR_BHI_EMPTY0 + s);
