@@ -545,9 +545,9 @@ def run_b200(args):
             'bound': 'tensor', 'kernel': dominant, 'achieved': dom_tflops, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': dom_tflops / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel
-            # in the ncu --set full capture of this workload (profiles/ncu_r2d_mstats_tc2.txt,
-            # profiles/ncu_r2d_estep_tc.txt); algorithmic: packed X 113 MB + prepared weights
-            'traffic': ({'mstats_tc2_kernel': 323.9e6 + 63.6e6, 'estep_tc_kernel': 116.5e6 + 54.5e6}
+            # in the ncu --set full capture of this workload (profiles/ncu_r2h_mstats_tc2.txt,
+            # profiles/ncu_r2h_estep_tc.txt); algorithmic: packed X 113 MB + prepared weights
+            'traffic': ({'mstats_tc2_kernel': 320.2e6 + 62.9e6, 'estep_tc_kernel': 116.5e6 + 53.9e6}
                         .get(dominant) if n_frames == 176323 else None),
             'traffic_unit': 'bytes per launch (ncu, 1 GPU)',
             'peak_source': f"{peaks['source']} bf16_tflops_sustained",
