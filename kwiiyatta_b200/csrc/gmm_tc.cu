@@ -1268,11 +1268,13 @@ lse_prep_kernel(long long N, long long Npad, int K, const double* __restrict__ w
 //   * the shared memory A no longer needs holds a third B stage.
 // Rows 128..143 of S (D = 144) are the transposes of columns the big MMA already produces, except
 // the 16 x 17 corner, which two mma.sync warps compute as before from a small shared-memory copy
-// of those 16 rows of A.  Tiles without weight for the component never enter the pipeline
-// (mstats_tc_flags_kernel + the producer's ballot over 32 tiles); work items are drawn from a
-// global counter and handed to the other roles through a 4-slot ring, because frames sorted by
-// dominant component make them very uneven.  With dense data the kernel runs into the board's
-// power cap (tools/time_mstep.py): the dbg bits exist to take such measurements.
+// of those 16 rows of A.  Tiles without weight for the component never enter the pipeline (the
+// flags of mstats_tc_prep_kernel / lse_prep_kernel + the producer's ballot over 32 tiles); work
+// items are drawn from a global counter, longest first (mstats_tc_order_kernel), and handed to the
+// other roles through a 4-slot ring, because frames sorted by dominant component make them very
+// uneven.  With dense data the kernel runs into the board's power cap (tools/time_mstep.py); on
+// real posteriors the per-tile hand-offs bound it (tools/time_mstep_real.py): the dbg bits exist
+// to take such measurements.
 // ------------------------------------------------------------------------------------------
 constexpr int M2_NB = 3;           // B stages
 struct Mstep2Smem {
